@@ -1,0 +1,70 @@
+// Shared declarations for libgfx.so (sm_100a only).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <string>
+
+#include "gfx.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libgfx is written for sm_100a (B200) only"
+#endif
+
+namespace gfx {
+
+constexpr int kHidden = 128;  // model.json: hidden = out_dim = 128
+constexpr int kMlpHidden = 256;
+constexpr int kFeat = 7;
+constexpr int kMaxLayers = 8;
+constexpr int kMaxEdgeDim = 16;
+constexpr int kNumSMs = 148;  // B200
+
+void set_error(const std::string &msg);
+int fail(int code, const std::string &msg);
+
+#define GFX_CUDA(expr)                                                        \
+  do {                                                                        \
+    cudaError_t err__ = (expr);                                               \
+    if (err__ != cudaSuccess) {                                               \
+      return ::gfx::fail(GFX_ERR_CUDA, std::string(#expr) + ": " +            \
+                                           cudaGetErrorString(err__));        \
+    }                                                                         \
+  } while (0)
+
+#define GFX_LAUNCH_CHECK() GFX_CUDA(cudaGetLastError())
+
+inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+}  // namespace gfx
+
+// Device-side weights.  One allocation ("arena") holds everything.
+struct gfx_model {
+  int hidden, layers, out_dim, feature_dim, edge_dim;
+  int device;
+  void *arena;
+  float eps1[gfx::kMaxLayers];
+  // fp32 tensors; index 0 = exact (GFX_F32 path), 1 = rounded to fp16 values
+  // (what the GFX_F16 SIMT path multiplies by, so SIMT-F16 == UMMA-F16 inputs)
+  const float *w_in[2];   // [H][F]
+  const float *b_in;      // [H]
+  const float *table[2];  // [L][edge_dim][H]
+  const float *w1t[2];    // [L][H][2H]   (k-major rows: w1t[k][n] = W1'[n][k])
+  const float *b1;        // [L][2H]
+  const float *w2t[2];    // [L][2H][H]
+  const float *b2;        // [L][H]
+  const float *ln_g;      // [L][H]
+  const float *ln_b;      // [L][H]
+  const float *wat[2];    // [H][H]
+  const float *ba;        // [H]
+  const float *wbt[2];    // [H][O]
+  const float *bb;        // [O]
+  // fp16 images laid out exactly as the tcgen05 kernels want them in shared
+  // memory (K-major, 128-byte swizzle, 64-column K blocks); see gfx_umma.cu
+  const __half *w1_img;   // [L] x (2 kblocks x 256 rows x 64)   = 64 KB each
+  const __half *w2_img;   // [L] x (4 kblocks x 128 rows x 64)   = 64 KB each
+  const __half *wa_img;   //       (2 kblocks x 128 rows x 64)   = 32 KB
+  const __half *wb_img;   //       (2 kblocks x 128 rows x 64)   = 32 KB
+};

@@ -1,0 +1,330 @@
+// Integer kernels: microbatch packing (K4), destination-CSR build (K0),
+// core-row map.  All HBM-bound byte/index work; results are bit-exact and
+// run-to-run deterministic (atomics are used only where the result does not
+// depend on their order).
+#include "gfx_common.cuh"
+
+namespace gfx {
+
+// ---------------------------------------------------------------------------
+// exclusive scan of int32 (three launches: local scan, scan of block sums,
+// add offsets).  Tile = 1024 threads x 4 items.
+// ---------------------------------------------------------------------------
+constexpr int kScanThreads = 1024;
+constexpr int kScanItems = 4;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__device__ __forceinline__ int warp_inclusive_scan(int v) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, v, d);
+    if (lane >= d) v += t;
+  }
+  return v;
+}
+
+// block-wide exclusive scan of one int per thread; returns exclusive prefix,
+// *total receives the block sum.  blockDim.x == kScanThreads.
+__device__ __forceinline__ int block_exclusive_scan(int v, int *total) {
+  __shared__ int warp_sums[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = warp_inclusive_scan(v);
+  if (lane == 31) warp_sums[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int s = warp_sums[lane];
+    int sinc = warp_inclusive_scan(s);
+    warp_sums[lane] = sinc - s;  // exclusive warp offsets
+    if (lane == 31) *total = sinc;
+  }
+  __syncthreads();
+  int result = inc - v + warp_sums[warp];
+  __syncthreads();
+  return result;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_local_kernel(const int *__restrict__ in, int *__restrict__ out, int *__restrict__ block_sums,
+                  int64_t n) {
+  __shared__ int total;
+  const int64_t base = int64_t(blockIdx.x) * kScanTile + int64_t(threadIdx.x) * kScanItems;
+  int v[kScanItems];
+  int sum = 0;
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) {
+    v[i] = (base + i < n) ? in[base + i] : 0;
+    sum += v[i];
+  }
+  int prefix = block_exclusive_scan(sum, &total);
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) {
+    if (base + i < n) out[base + i] = prefix;
+    prefix += v[i];
+  }
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+// single block: exclusive scan of block_sums in place (any length)
+__global__ void __launch_bounds__(kScanThreads)
+scan_sums_kernel(int *__restrict__ sums, int count, int64_t *__restrict__ grand_total) {
+  __shared__ int total;
+  int carry = 0;
+  for (int base = 0; base < count; base += kScanThreads) {
+    int i = base + threadIdx.x;
+    int v = i < count ? sums[i] : 0;
+    int p = block_exclusive_scan(v, &total);
+    if (i < count) sums[i] = p + carry;
+    carry += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && grand_total) *grand_total = carry;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_add_kernel(int *__restrict__ out, const int *__restrict__ block_sums, int64_t n) {
+  const int add = block_sums[blockIdx.x];
+  const int64_t base = int64_t(blockIdx.x) * kScanTile + int64_t(threadIdx.x) * kScanItems;
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i)
+    if (base + i < n) out[base + i] += add;
+}
+
+static inline int scan_blocks(int64_t n) { return int((n + kScanTile - 1) / kScanTile); }
+
+// out[i] = sum(in[0..i)) for i in [0,n).  block_sums: scan_blocks(n) ints.
+static int exclusive_scan(const int *in, int *out, int64_t n, int *block_sums,
+                          int64_t *grand_total, cudaStream_t st) {
+  if (n == 0) return GFX_OK;
+  int nb = scan_blocks(n);
+  scan_local_kernel<<<nb, kScanThreads, 0, st>>>(in, out, block_sums, n);
+  scan_sums_kernel<<<1, kScanThreads, 0, st>>>(block_sums, nb, grand_total);
+  scan_add_kernel<<<nb, kScanThreads, 0, st>>>(out, block_sums, n);
+  GFX_LAUNCH_CHECK();
+  return GFX_OK;
+}
+
+// ---------------------------------------------------------------------------
+// K4  microbatch packing.
+// Greedy first-fit over monotone prefix arrays: from record s the batch
+// extends to the last stop with node_ptr[stop]-node_ptr[s] <= max_nodes and
+// edge_ptr[stop]-edge_ptr[s] <= max_edges, and always takes at least one
+// record (api.py:217-221: the limit test is skipped for the first record).
+// Phase 1 computes that stop for EVERY s in parallel (two binary searches);
+// phase 2 follows the chain from 0.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int64_t last_not_above(const int64_t *__restrict__ a, int64_t lo,
+                                                  int64_t hi, int64_t limit) {
+  // largest i in [lo, hi] with a[i] <= limit (a non-decreasing, a[lo] <= limit)
+  while (lo < hi) {
+    int64_t mid = lo + (hi - lo + 1) / 2;
+    if (a[mid] <= limit) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+__global__ void pack_next_kernel(const int64_t *__restrict__ node_ptr,
+                                 const int64_t *__restrict__ edge_ptr, int64_t B,
+                                 int64_t max_nodes, int64_t max_edges,
+                                 int64_t *__restrict__ next_stop) {
+  int64_t s = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (s >= B) return;
+  int64_t by_nodes = last_not_above(node_ptr, s, B, node_ptr[s] + max_nodes);
+  int64_t by_edges = last_not_above(edge_ptr, s, B, edge_ptr[s] + max_edges);
+  int64_t stop = by_nodes < by_edges ? by_nodes : by_edges;
+  next_stop[s] = stop > s ? stop : s + 1;
+}
+
+__global__ void pack_chase_kernel(const int64_t *__restrict__ next_stop, int64_t B,
+                                  int64_t *__restrict__ bounds, int64_t *__restrict__ n_bounds) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  int64_t count = 0, s = 0;
+  bounds[count++] = 0;
+  while (s < B) {
+    s = next_stop[s];
+    bounds[count++] = s;
+  }
+  *n_bounds = count;
+}
+
+// ---------------------------------------------------------------------------
+// K0  destination CSR.
+//   1 count      deg[dst-base] += 1                       (integer atomics)
+//   2 scan       row_ptr = exclusive_scan(deg), row_ptr[N] = E
+//   3 scatter    slot = cursor[dst]++ ; eid[row_ptr[dst]+slot] = e   (any order)
+//   4 place      within each row rank edges by their edge id, so the row is in
+//                original edge order (= stable sort = the reference's
+//                index_add_ summation order) whatever order step 3 ran in;
+//                write col_src = src-base, col_type.
+// Rows longer than kSmallRow are ranked by a whole block (step 4b).
+// ---------------------------------------------------------------------------
+constexpr int kSmallRow = 32;
+
+__global__ void csr_count_kernel(const int32_t *__restrict__ dst, int64_t E, int32_t base,
+                                 int *__restrict__ deg) {
+  for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < E;
+       e += int64_t(gridDim.x) * blockDim.x)
+    atomicAdd(&deg[dst[e] - base], 1);
+}
+
+__global__ void csr_scatter_kernel(const int32_t *__restrict__ dst, int64_t E, int32_t base,
+                                   const int32_t *__restrict__ row_ptr, int *__restrict__ cursor,
+                                   int32_t *__restrict__ eid) {
+  for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < E;
+       e += int64_t(gridDim.x) * blockDim.x) {
+    int d = dst[e] - base;
+    int slot = atomicAdd(&cursor[d], 1);
+    eid[row_ptr[d] + slot] = int32_t(e);
+  }
+}
+
+__global__ void csr_place_kernel(const int32_t *__restrict__ src, const uint8_t *__restrict__ typ,
+                                 int32_t base, const int32_t *__restrict__ row_ptr,
+                                 const int32_t *__restrict__ eid, int64_t N,
+                                 int32_t *__restrict__ col_src, uint8_t *__restrict__ col_type,
+                                 int32_t *__restrict__ big_rows, int *__restrict__ n_big) {
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < N;
+       i += int64_t(gridDim.x) * blockDim.x) {
+    const int s = row_ptr[i], t = row_ptr[i + 1];
+    if (t - s > kSmallRow) {
+      big_rows[atomicAdd(n_big, 1)] = int32_t(i);  // order of this list is irrelevant
+      continue;
+    }
+    for (int a = s; a < t; ++a) {
+      const int ea = eid[a];
+      int rank = 0;
+      for (int b = s; b < t; ++b) rank += eid[b] < ea;
+      col_src[s + rank] = src[ea] - base;
+      col_type[s + rank] = typ[ea];
+    }
+  }
+}
+
+__global__ void csr_place_big_kernel(const int32_t *__restrict__ src,
+                                     const uint8_t *__restrict__ typ, int32_t base,
+                                     const int32_t *__restrict__ row_ptr,
+                                     const int32_t *__restrict__ eid,
+                                     const int32_t *__restrict__ big_rows,
+                                     const int *__restrict__ n_big,
+                                     int32_t *__restrict__ col_src,
+                                     uint8_t *__restrict__ col_type) {
+  const int count = *n_big;
+  for (int r = blockIdx.x; r < count; r += gridDim.x) {
+    const int i = big_rows[r];
+    const int s = row_ptr[i], t = row_ptr[i + 1];
+    for (int a = s + threadIdx.x; a < t; a += blockDim.x) {
+      const int ea = eid[a];
+      int rank = 0;
+      for (int b = s; b < t; ++b) rank += eid[b] < ea;
+      col_src[s + rank] = src[ea] - base;
+      col_type[s + rank] = typ[ea];
+    }
+  }
+}
+
+__global__ void set_last_kernel(int32_t *row_ptr, int64_t N, int32_t E) { row_ptr[N] = E; }
+
+// ---------------------------------------------------------------------------
+// core-row map
+// ---------------------------------------------------------------------------
+__global__ void core_flag_kernel(const uint8_t *__restrict__ roles, int64_t N,
+                                 int *__restrict__ flag) {
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < N;
+       i += int64_t(gridDim.x) * blockDim.x)
+    flag[i] = roles[i] == 0;
+}
+
+__global__ void core_map_kernel(const uint8_t *__restrict__ roles, int64_t N,
+                                int32_t *__restrict__ out_row) {
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < N;
+       i += int64_t(gridDim.x) * blockDim.x)
+    if (roles[i] != 0) out_row[i] = -1;
+}
+
+static inline int grid_for(int64_t n, int threads) {
+  int64_t b = (n + threads - 1) / threads;
+  int64_t cap = int64_t(kNumSMs) * 16;
+  return int(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+static inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
+
+}  // namespace gfx
+
+using namespace gfx;
+
+extern "C" int gfx_pack_microbatches(const int64_t *node_ptr, const int64_t *edge_ptr, int64_t B,
+                                     int64_t max_nodes, int64_t max_edges, int64_t *next_stop,
+                                     int64_t *bounds, int64_t *n_bounds, void *stream) {
+  if (B <= 0) return fail(GFX_ERR_ARGUMENT, "gfx_pack_microbatches: a shard cannot be empty");
+  if (max_nodes <= 0 || max_edges <= 0)
+    return fail(GFX_ERR_ARGUMENT, "batch node and edge limits must be positive");
+  cudaStream_t st = as_stream(stream);
+  pack_next_kernel<<<int((B + 255) / 256), 256, 0, st>>>(node_ptr, edge_ptr, B, max_nodes,
+                                                         max_edges, next_stop);
+  pack_chase_kernel<<<1, 32, 0, st>>>(next_stop, B, bounds, n_bounds);
+  GFX_LAUNCH_CHECK();
+  return GFX_OK;
+}
+
+// workspace layout: deg/cursor int[N+1] | eid int[E] | block_sums | big_rows int[N] | n_big
+extern "C" size_t gfx_csr_workspace_bytes(int64_t N, int64_t E) {
+  return align256(size_t(N + 1) * 4) + align256(size_t(E) * 4) +
+         align256(size_t(scan_blocks(N + 1) + 1) * 4) + align256(size_t(N) * 4) + 256;
+}
+
+extern "C" int gfx_csr_build(const int32_t *edge_src, const int32_t *edge_dst,
+                             const uint8_t *edge_type, int64_t N, int64_t E, int32_t node_base,
+                             int32_t *row_ptr, int32_t *col_src, uint8_t *col_type, void *ws,
+                             size_t ws_bytes, void *stream) {
+  if (N < 0 || E < 0 || N >= (int64_t(1) << 31) - 1 || E >= (int64_t(1) << 31) - 1)
+    return fail(GFX_ERR_ARGUMENT, "gfx_csr_build: sizes must fit int32");
+  if (ws_bytes < gfx_csr_workspace_bytes(N, E))
+    return fail(GFX_ERR_WORKSPACE, "gfx_csr_build: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  char *p = static_cast<char *>(ws);
+  int *deg = reinterpret_cast<int *>(p); p += align256(size_t(N + 1) * 4);
+  int32_t *eid = reinterpret_cast<int32_t *>(p); p += align256(size_t(E) * 4);
+  int *sums = reinterpret_cast<int *>(p); p += align256(size_t(scan_blocks(N + 1) + 1) * 4);
+  int32_t *big_rows = reinterpret_cast<int32_t *>(p); p += align256(size_t(N) * 4);
+  int *n_big = reinterpret_cast<int *>(p);
+  GFX_CUDA(cudaMemsetAsync(deg, 0, size_t(N + 1) * 4, st));
+  GFX_CUDA(cudaMemsetAsync(n_big, 0, 4, st));
+  if (E > 0) csr_count_kernel<<<grid_for(E, 256), 256, 0, st>>>(edge_dst, E, node_base, deg);
+  int rc = exclusive_scan(deg, row_ptr, N + 1, sums, nullptr, st);
+  if (rc) return rc;
+  if (N == 0 || E == 0) {
+    GFX_LAUNCH_CHECK();
+    return GFX_OK;
+  }
+  GFX_CUDA(cudaMemsetAsync(deg, 0, size_t(N + 1) * 4, st));  // reuse as cursor
+  csr_scatter_kernel<<<grid_for(E, 256), 256, 0, st>>>(edge_dst, E, node_base, row_ptr, deg, eid);
+  csr_place_kernel<<<grid_for(N, 256), 256, 0, st>>>(edge_src, edge_type, node_base, row_ptr, eid,
+                                                     N, col_src, col_type, big_rows, n_big);
+  csr_place_big_kernel<<<kNumSMs, 256, 0, st>>>(edge_src, edge_type, node_base, row_ptr, eid,
+                                                big_rows, n_big, col_src, col_type);
+  GFX_LAUNCH_CHECK();
+  return GFX_OK;
+}
+
+extern "C" size_t gfx_core_rows_workspace_bytes(int64_t N) {
+  return align256(size_t(N) * 4) + align256(size_t(scan_blocks(N) + 1) * 4);
+}
+
+extern "C" int gfx_core_rows(const uint8_t *roles, int64_t N, int32_t *out_row, int64_t *n_core,
+                             void *ws, size_t ws_bytes, void *stream) {
+  if (N <= 0 || N >= (int64_t(1) << 31) - 1)
+    return fail(GFX_ERR_ARGUMENT, "gfx_core_rows: node count must be in [1, 2^31)");
+  if (ws_bytes < gfx_core_rows_workspace_bytes(N))
+    return fail(GFX_ERR_WORKSPACE, "gfx_core_rows: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  char *p = static_cast<char *>(ws);
+  int *flag = reinterpret_cast<int *>(p); p += align256(size_t(N) * 4);
+  int *sums = reinterpret_cast<int *>(p);
+  core_flag_kernel<<<grid_for(N, 256), 256, 0, st>>>(roles, N, flag);
+  int rc = exclusive_scan(flag, out_row, N, sums, n_core, st);
+  if (rc) return rc;
+  core_map_kernel<<<grid_for(N, 256), 256, 0, st>>>(roles, N, out_row);
+  GFX_LAUNCH_CHECK();
+  return GFX_OK;
+}

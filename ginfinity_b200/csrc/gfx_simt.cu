@@ -1,0 +1,426 @@
+// CUDA-core kernels: input projection, K1 neighbour aggregation (the HBM-bound
+// kernel of the path) and an fp32-accumulate MLP / head used for the
+// full-precision model and as the on-device cross-check of the tcgen05 path.
+#include "gfx_common.cuh"
+
+namespace gfx {
+
+// ---- 8-channel row slices ---------------------------------------------------
+// A node row is 128 channels.  A half-warp (16 lanes) owns one row; lane l
+// owns channels [8l, 8l+8): 16 bytes of fp16 (one 128-bit access) or 32 bytes
+// of fp32 (two 128-bit accesses), so a row is read with full 128-byte lines.
+struct Row8 {
+  float v[8];
+};
+
+__device__ __forceinline__ Row8 load8(const __half *p) {
+  uint4 raw = *reinterpret_cast<const uint4 *>(p);
+  const __half2 *h = reinterpret_cast<const __half2 *>(&raw);
+  Row8 r;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __half22float2(h[i]);
+    r.v[2 * i] = f.x;
+    r.v[2 * i + 1] = f.y;
+  }
+  return r;
+}
+__device__ __forceinline__ Row8 load8(const float *p) {
+  float4 a = reinterpret_cast<const float4 *>(p)[0];
+  float4 b = reinterpret_cast<const float4 *>(p)[1];
+  return Row8{{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w}};
+}
+__device__ __forceinline__ void store8(__half *p, const Row8 &r) {
+  uint4 raw;
+  __half2 *h = reinterpret_cast<__half2 *>(&raw);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(r.v[2 * i], r.v[2 * i + 1]);
+  *reinterpret_cast<uint4 *>(p) = raw;
+}
+__device__ __forceinline__ void store8(float *p, const Row8 &r) {
+  reinterpret_cast<float4 *>(p)[0] = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+  reinterpret_cast<float4 *>(p)[1] = make_float4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+
+// ---------------------------------------------------------------------------
+// input projection  h = x W_in^T + b_in     (28 B in, 256/512 B out per node)
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+input_linear_kernel(const float *__restrict__ x, const float *__restrict__ w_in,
+                    const float *__restrict__ b_in, int64_t n, T *__restrict__ h) {
+  const int sub = threadIdx.x & 15;                 // lane within the half-warp
+  float w[8][kFeat], b[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    b[c] = b_in[sub * 8 + c];
+#pragma unroll
+    for (int f = 0; f < kFeat; ++f) w[c][f] = w_in[(sub * 8 + c) * kFeat + f];
+  }
+  const int64_t rows_per_pass = int64_t(gridDim.x) * (blockDim.x >> 4);
+  for (int64_t i = int64_t(blockIdx.x) * (blockDim.x >> 4) + (threadIdx.x >> 4); i < n;
+       i += rows_per_pass) {
+    float xf[kFeat];
+#pragma unroll
+    for (int f = 0; f < kFeat; ++f) xf[f] = x[i * kFeat + f];
+    Row8 r;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float acc = b[c];
+#pragma unroll
+      for (int f = 0; f < kFeat; ++f) acc = fmaf(xf[f], w[c][f], acc);
+      r.v[c] = acc;
+    }
+    store8(h + i * kHidden + sub * 8, r);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K1  z_i = eps1 * h_i + sum_{e in row i} relu(h[col_src[e]] + table[col_type[e]])
+// One half-warp per destination node, edges of a row taken four at a time so
+// that four independent 128-bit row loads are in flight per lane.  Sums are
+// fp32 in CSR order (= reference edge order), so the result is deterministic.
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+aggregate_kernel(const T *__restrict__ h, const int32_t *__restrict__ row_ptr,
+                 const int32_t *__restrict__ col_src, const uint8_t *__restrict__ col_type,
+                 const float *__restrict__ table, int edge_dim, float eps1, int64_t n,
+                 T *__restrict__ z) {
+  __shared__ __align__(16) float tab[kMaxEdgeDim * kHidden];
+  for (int i = threadIdx.x; i < edge_dim * kHidden; i += blockDim.x) tab[i] = table[i];
+  __syncthreads();
+  const int sub = threadIdx.x & 15;
+  const int64_t rows_per_pass = int64_t(gridDim.x) * (blockDim.x >> 4);
+  for (int64_t i = int64_t(blockIdx.x) * (blockDim.x >> 4) + (threadIdx.x >> 4); i < n;
+       i += rows_per_pass) {
+    const int beg = row_ptr[i], end = row_ptr[i + 1];
+    Row8 self = load8(h + i * kHidden + sub * 8);
+    float acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+    int e = beg;
+    for (; e + 4 <= end; e += 4) {
+      int s[4], t[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        s[u] = col_src[e + u];
+        t[u] = col_type[e + u];
+      }
+      Row8 nb[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) nb[u] = load8(h + int64_t(s[u]) * kHidden + sub * 8);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float *tp = tab + t[u] * kHidden + sub * 8;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[c] += fmaxf(nb[u].v[c] + tp[c], 0.f);
+      }
+    }
+    for (; e < end; ++e) {
+      const int s = col_src[e], t = col_type[e];
+      Row8 nb = load8(h + int64_t(s) * kHidden + sub * 8);
+      const float *tp = tab + t * kHidden + sub * 8;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[c] += fmaxf(nb.v[c] + tp[c], 0.f);
+    }
+    Row8 out;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) out.v[c] = fmaf(eps1, self.v[c], acc[c]);
+    store8(z + i * kHidden + sub * 8, out);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// SIMT MLP.  One warp owns 8 node rows end to end (both GEMMs, LayerNorm or
+// L2 norm), so nothing but weights is shared between warps and only
+// __syncwarp is needed.  Stage 1: lane owns HID/32 hidden columns of its 8
+// rows; stage 2: lane owns 4 output columns.  Weights are read as [k][n]
+// rows (coalesced 128-bit loads, L1/L2 resident: 256 KB per layer).
+//   MODE 0:  out = res + LayerNorm(W2 relu(W1 a + b1) + b2) * g + b
+//   MODE 1:  y = W2 relu(W1 a + b1) + b2 ; out[out_row] = y / max(|y|, 1e-12)
+// ---------------------------------------------------------------------------
+constexpr int kRowsPerWarp = 8;
+constexpr int kMlpWarps = 8;
+
+template <typename T>
+__device__ __forceinline__ float to_f32(T v);
+template <>
+__device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+template <typename T>
+__device__ __forceinline__ T from_f32(float v);
+template <>
+__device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+
+template <typename TIn, typename TOut, int HID, int MODE, bool ROUND_HIDDEN>
+__global__ void __launch_bounds__(kMlpWarps * 32)
+mlp_simt_kernel(const TIn *__restrict__ a_in, const TIn *__restrict__ res,
+                const float *__restrict__ w1t, const float *__restrict__ b1,
+                const float *__restrict__ w2t, const float *__restrict__ b2,
+                const float *__restrict__ ln_g, const float *__restrict__ ln_b,
+                const int32_t *__restrict__ out_row, int64_t n, TOut *__restrict__ out) {
+  constexpr int C1 = HID / 32;  // hidden columns per lane
+  extern __shared__ __align__(16) float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float *a_s = smem + warp * (kRowsPerWarp * (kHidden + HID));  // [8][128]
+  float *h_s = a_s + kRowsPerWarp * kHidden;                    // [8][HID]
+  const int64_t tiles = (n + kRowsPerWarp - 1) / kRowsPerWarp;
+  for (int64_t tile = int64_t(blockIdx.x) * kMlpWarps + warp; tile < tiles;
+       tile += int64_t(gridDim.x) * kMlpWarps) {
+    const int64_t row0 = tile * kRowsPerWarp;
+    // stage the 8 input rows (fp32 in shared memory)
+#pragma unroll
+    for (int r = 0; r < kRowsPerWarp; ++r) {
+      const int64_t row = row0 + r;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int col = lane + 32 * c;
+        a_s[r * kHidden + col] = row < n ? to_f32<TIn>(a_in[row * kHidden + col]) : 0.f;
+      }
+    }
+    __syncwarp();
+    // ---- GEMM 1: hid[r][lane*C1 + c] -------------------------------------
+    float acc1[kRowsPerWarp][C1];
+#pragma unroll
+    for (int r = 0; r < kRowsPerWarp; ++r)
+#pragma unroll
+      for (int c = 0; c < C1; ++c) acc1[r][c] = b1[lane * C1 + c];
+    for (int k = 0; k < kHidden; k += 4) {
+      float4 av[kRowsPerWarp];
+#pragma unroll
+      for (int r = 0; r < kRowsPerWarp; ++r)
+        av[r] = *reinterpret_cast<const float4 *>(a_s + r * kHidden + k);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        float w[C1];
+        const float4 *wp = reinterpret_cast<const float4 *>(w1t + (k + kk) * HID + lane * C1);
+#pragma unroll
+        for (int c4 = 0; c4 < C1 / 4; ++c4) {
+          float4 t = __ldg(wp + c4);
+          w[4 * c4] = t.x; w[4 * c4 + 1] = t.y; w[4 * c4 + 2] = t.z; w[4 * c4 + 3] = t.w;
+        }
+#pragma unroll
+        for (int r = 0; r < kRowsPerWarp; ++r) {
+          const float a = kk == 0 ? av[r].x : kk == 1 ? av[r].y : kk == 2 ? av[r].z : av[r].w;
+#pragma unroll
+          for (int c = 0; c < C1; ++c) acc1[r][c] = fmaf(a, w[c], acc1[r][c]);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < kRowsPerWarp; ++r)
+#pragma unroll
+      for (int c = 0; c < C1; ++c) {
+        float v = fmaxf(acc1[r][c], 0.f);
+        if (ROUND_HIDDEN) v = __half2float(__float2half_rn(v));
+        h_s[r * HID + lane * C1 + c] = v;
+      }
+    __syncwarp();
+    // ---- GEMM 2: u[r][lane*4 + c] -----------------------------------------
+    float acc2[kRowsPerWarp][4];
+#pragma unroll
+    for (int r = 0; r < kRowsPerWarp; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc2[r][c] = b2[lane * 4 + c];
+    for (int k = 0; k < HID; k += 4) {
+      float4 hv[kRowsPerWarp];
+#pragma unroll
+      for (int r = 0; r < kRowsPerWarp; ++r)
+        hv[r] = *reinterpret_cast<const float4 *>(h_s + r * HID + k);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const float4 w = __ldg(reinterpret_cast<const float4 *>(w2t + (k + kk) * kHidden + lane * 4));
+#pragma unroll
+        for (int r = 0; r < kRowsPerWarp; ++r) {
+          const float a = kk == 0 ? hv[r].x : kk == 1 ? hv[r].y : kk == 2 ? hv[r].z : hv[r].w;
+          acc2[r][0] = fmaf(a, w.x, acc2[r][0]);
+          acc2[r][1] = fmaf(a, w.y, acc2[r][1]);
+          acc2[r][2] = fmaf(a, w.z, acc2[r][2]);
+          acc2[r][3] = fmaf(a, w.w, acc2[r][3]);
+        }
+      }
+    }
+    // ---- epilogue: a row's 128 values live in this warp (4 per lane) -------
+#pragma unroll
+    for (int r = 0; r < kRowsPerWarp; ++r) {
+      const int64_t row = row0 + r;
+      if (MODE == 0) {
+        float s = acc2[r][0] + acc2[r][1] + acc2[r][2] + acc2[r][3];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+        const float mean = s * (1.f / kHidden);
+        float q = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float dlt = acc2[r][c] - mean;
+          q = fmaf(dlt, dlt, q);
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) q += __shfl_xor_sync(0xffffffffu, q, d);
+        const float rstd = rsqrtf(q * (1.f / kHidden) + 1e-5f);
+        if (row < n) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int col = lane * 4 + c;
+            const float u = (acc2[r][c] - mean) * rstd * ln_g[col] + ln_b[col];
+            out[row * kHidden + col] =
+                from_f32<TOut>(to_f32<TIn>(res[row * kHidden + col]) + u);
+          }
+        }
+      } else {
+        float q = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) q = fmaf(acc2[r][c], acc2[r][c], q);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) q += __shfl_xor_sync(0xffffffffu, q, d);
+        const float inv = 1.f / fmaxf(sqrtf(q), 1e-12f);
+        if (row < n) {
+          const int64_t orow = out_row ? int64_t(out_row[row]) : row;
+          if (orow >= 0) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              out[orow * kHidden + lane * 4 + c] = from_f32<TOut>(acc2[r][c] * inv);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+template <typename TIn, typename TOut, int HID, int MODE, bool RH>
+static int launch_mlp(const TIn *a, const TIn *res, const float *w1t, const float *b1,
+                      const float *w2t, const float *b2, const float *g, const float *b,
+                      const int32_t *out_row, int64_t n, TOut *out, cudaStream_t st) {
+  auto kern = mlp_simt_kernel<TIn, TOut, HID, MODE, RH>;
+  const size_t smem = size_t(kMlpWarps) * kRowsPerWarp * (kHidden + HID) * sizeof(float);
+  GFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  const int64_t tiles = (n + kRowsPerWarp - 1) / kRowsPerWarp;
+  int64_t blocks = (tiles + kMlpWarps - 1) / kMlpWarps;
+  if (blocks > 2 * kNumSMs) blocks = 2 * kNumSMs;
+  kern<<<int(blocks), kMlpWarps * 32, smem, st>>>(a, res, w1t, b1, w2t, b2, g, b, out_row, n, out);
+  GFX_LAUNCH_CHECK();
+  return GFX_OK;
+}
+
+static inline int row_grid(int64_t n) {
+  int64_t b = (n + 15) / 16;
+  int64_t cap = int64_t(kNumSMs) * 8;
+  return int(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+// implemented in gfx_umma.cu
+int umma_mlp_ln_residual(const gfx_model *m, int layer, const __half *z, const __half *h,
+                         int64_t n, __half *h_out, cudaStream_t st);
+int umma_head_l2norm(const gfx_model *m, const __half *h, const int32_t *out_row, int64_t n,
+                     void *out, int out_dtype, cudaStream_t st);
+
+}  // namespace gfx
+
+using namespace gfx;
+
+extern "C" int gfx_input_linear(const gfx_model *m, const float *x, int64_t n, void *h, int dtype,
+                                void *stream) {
+  if (!m) return fail(GFX_ERR_ARGUMENT, "gfx_input_linear: null model");
+  if (n <= 0) return GFX_OK;
+  cudaStream_t st = as_stream(stream);
+  if (dtype == GFX_F16)
+    input_linear_kernel<__half><<<row_grid(n), 256, 0, st>>>(x, m->w_in[1], m->b_in, n,
+                                                             static_cast<__half *>(h));
+  else if (dtype == GFX_F32)
+    input_linear_kernel<float><<<row_grid(n), 256, 0, st>>>(x, m->w_in[0], m->b_in, n,
+                                                            static_cast<float *>(h));
+  else
+    return fail(GFX_ERR_ARGUMENT, "gfx_input_linear: unknown dtype");
+  GFX_LAUNCH_CHECK();
+  return GFX_OK;
+}
+
+extern "C" int gfx_aggregate(const gfx_model *m, int layer, const void *h, const int32_t *row_ptr,
+                             const int32_t *col_src, const uint8_t *col_type, int64_t n, void *z,
+                             int dtype, void *stream) {
+  if (!m || layer < 0 || layer >= m->layers)
+    return fail(GFX_ERR_ARGUMENT, "gfx_aggregate: bad model or layer");
+  if (n <= 0) return GFX_OK;
+  cudaStream_t st = as_stream(stream);
+  const size_t toff = size_t(layer) * m->edge_dim * kHidden;
+  if (dtype == GFX_F16)
+    aggregate_kernel<__half><<<row_grid(n), 256, 0, st>>>(
+        static_cast<const __half *>(h), row_ptr, col_src, col_type, m->table[1] + toff,
+        m->edge_dim, m->eps1[layer], n, static_cast<__half *>(z));
+  else if (dtype == GFX_F32)
+    aggregate_kernel<float><<<row_grid(n), 256, 0, st>>>(
+        static_cast<const float *>(h), row_ptr, col_src, col_type, m->table[0] + toff,
+        m->edge_dim, m->eps1[layer], n, static_cast<float *>(z));
+  else
+    return fail(GFX_ERR_ARGUMENT, "gfx_aggregate: unknown dtype");
+  GFX_LAUNCH_CHECK();
+  return GFX_OK;
+}
+
+extern "C" int gfx_mlp_ln_residual(const gfx_model *m, int layer, const void *z, const void *h,
+                                   int64_t n, void *h_out, int dtype, int impl, void *stream) {
+  if (!m || layer < 0 || layer >= m->layers)
+    return fail(GFX_ERR_ARGUMENT, "gfx_mlp_ln_residual: bad model or layer");
+  if (n <= 0) return GFX_OK;
+  cudaStream_t st = as_stream(stream);
+  const int H = kHidden, M = kMlpHidden;
+  if (impl == GFX_IMPL_AUTO) impl = dtype == GFX_F16 ? GFX_IMPL_UMMA : GFX_IMPL_SIMT;
+  if (impl == GFX_IMPL_UMMA) {
+    if (dtype != GFX_F16)
+      return fail(GFX_ERR_UNSUPPORTED, "tcgen05 MLP exists for GFX_F16 only");
+    return umma_mlp_ln_residual(m, layer, static_cast<const __half *>(z),
+                                static_cast<const __half *>(h), n, static_cast<__half *>(h_out), st);
+  }
+  const int q = dtype == GFX_F16 ? 1 : 0;
+  const float *w1t = m->w1t[q] + size_t(layer) * H * M, *b1 = m->b1 + size_t(layer) * M;
+  const float *w2t = m->w2t[q] + size_t(layer) * M * H, *b2 = m->b2 + size_t(layer) * H;
+  const float *g = m->ln_g + size_t(layer) * H, *b = m->ln_b + size_t(layer) * H;
+  if (dtype == GFX_F16)
+    return launch_mlp<__half, __half, kMlpHidden, 0, true>(
+        static_cast<const __half *>(z), static_cast<const __half *>(h), w1t, b1, w2t, b2, g, b,
+        nullptr, n, static_cast<__half *>(h_out), st);
+  if (dtype == GFX_F32)
+    return launch_mlp<float, float, kMlpHidden, 0, false>(
+        static_cast<const float *>(z), static_cast<const float *>(h), w1t, b1, w2t, b2, g, b,
+        nullptr, n, static_cast<float *>(h_out), st);
+  return fail(GFX_ERR_ARGUMENT, "gfx_mlp_ln_residual: unknown dtype");
+}
+
+extern "C" int gfx_head_l2norm(const gfx_model *m, const void *h, const int32_t *out_row,
+                               int64_t n, void *out, int dtype, int out_dtype, int impl,
+                               void *stream) {
+  if (!m) return fail(GFX_ERR_ARGUMENT, "gfx_head_l2norm: null model");
+  if (n <= 0) return GFX_OK;
+  if (out_dtype != GFX_F16 && out_dtype != GFX_F32)
+    return fail(GFX_ERR_ARGUMENT, "gfx_head_l2norm: unknown out_dtype");
+  cudaStream_t st = as_stream(stream);
+  if (impl == GFX_IMPL_AUTO) impl = dtype == GFX_F16 ? GFX_IMPL_UMMA : GFX_IMPL_SIMT;
+  if (impl == GFX_IMPL_UMMA) {
+    if (dtype != GFX_F16)
+      return fail(GFX_ERR_UNSUPPORTED, "tcgen05 head exists for GFX_F16 only");
+    return umma_head_l2norm(m, static_cast<const __half *>(h), out_row, n, out, out_dtype, st);
+  }
+  const int q = dtype == GFX_F16 ? 1 : 0;
+  if (dtype == GFX_F16 && out_dtype == GFX_F16)
+    return launch_mlp<__half, __half, kHidden, 1, true>(
+        static_cast<const __half *>(h), nullptr, m->wat[q], m->ba, m->wbt[q], m->bb, nullptr,
+        nullptr, out_row, n, static_cast<__half *>(out), st);
+  if (dtype == GFX_F16 && out_dtype == GFX_F32)
+    return launch_mlp<__half, float, kHidden, 1, true>(
+        static_cast<const __half *>(h), nullptr, m->wat[q], m->ba, m->wbt[q], m->bb, nullptr,
+        nullptr, out_row, n, static_cast<float *>(out), st);
+  if (dtype == GFX_F32 && out_dtype == GFX_F16)
+    return launch_mlp<float, __half, kHidden, 1, false>(
+        static_cast<const float *>(h), nullptr, m->wat[q], m->ba, m->wbt[q], m->bb, nullptr,
+        nullptr, out_row, n, static_cast<__half *>(out), st);
+  if (dtype == GFX_F32 && out_dtype == GFX_F32)
+    return launch_mlp<float, float, kHidden, 1, false>(
+        static_cast<const float *>(h), nullptr, m->wat[q], m->ba, m->wbt[q], m->bb, nullptr,
+        nullptr, out_row, n, static_cast<float *>(out), st);
+  return fail(GFX_ERR_ARGUMENT, "gfx_head_l2norm: unknown dtype");
+}

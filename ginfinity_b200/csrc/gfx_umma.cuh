@@ -1,0 +1,164 @@
+// Inline-PTX wrappers for the Blackwell (sm_100a) tensor-core path:
+// tcgen05.mma with TMEM accumulators, mbarriers, bulk async copies (TMA
+// engine) and shared-memory matrix descriptors.
+#pragma once
+#include <stdint.h>
+
+namespace gfx {
+namespace ptx {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ---- mbarrier ---------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+
+// ---- async copies -------------------------------------------------------------
+// 1-D bulk copy global -> shared on the TMA engine (SASS: UBLKCP); completion
+// is counted in bytes on `bar`.  dst/src 16-byte aligned, bytes % 16 == 0.
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes,
+                                         uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+// 1-D bulk copy shared -> global (SASS: UBLKCP), tracked by bulk groups.
+__device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
+               "r"(smem_u32(src_smem)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// 16-byte cp.async (SASS: LDGSTS); src_bytes == 0 zero-fills the destination.
+__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src_gmem, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// generic-proxy writes to shared memory -> visible to the async proxy (MMA/TMA)
+__device__ __forceinline__ void fence_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// ---- TMEM -----------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t cols) {  // one full warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+               "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {  // same warp
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem]^T, fp16 inputs, fp32 accumulate; one thread issues.
+__device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                           uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on `bar` when all previously issued tcgen05.mma of this thread are done
+__device__ __forceinline__ void mma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+
+// 32 lanes x 32 columns of fp32: thread i of the warp receives row (lane) i,
+// columns [col, col+32).  The warp may only touch lanes 32*(warp%4) .. +31.
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
+  uint32_t *r = reinterpret_cast<uint32_t *>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- descriptors ----------------------------------------------------------------
+// Shared-memory matrix descriptor for a K-major operand tile stored as rows of
+// 128 bytes (64 fp16) with the 128-byte swizzle; 8-row groups 1024 bytes apart.
+//   [0,14)  start address >> 4       [16,30) leading byte offset >> 4 (unused: 1)
+//   [32,46) stride byte offset >> 4  [46,48) descriptor version = 1 (Blackwell)
+//   [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= uint64_t((smem_addr & 0x3FFFFu) >> 4);
+  d |= uint64_t(1) << 16;
+  d |= uint64_t(1024 >> 4) << 32;
+  d |= uint64_t(1) << 46;
+  d |= uint64_t(2) << 61;
+  return d;
+}
+
+// Instruction descriptor, kind::f16: fp16 A and B (both K-major), fp32 D.
+//   [4,6) D format = 1 (f32)   [7,10) A = 0 (f16)   [10,13) B = 0 (f16)
+//   [15] A major = 0 (K)       [16] B major = 0 (K)
+//   [17,23) N >> 3             [24,29) M >> 4
+__host__ __device__ constexpr uint32_t idesc_f16(int m, int n) {
+  return (1u << 4) | (uint32_t(n >> 3) << 17) | (uint32_t(m >> 4) << 24);
+}
+
+}  // namespace ptx
+}  // namespace gfx

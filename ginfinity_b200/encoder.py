@@ -1,0 +1,398 @@
+"""`Ginfinity`: the reference's encoder facade over libgfx.so.
+
+Mirrors src/ginfinity/api.py (reference): `Ginfinity.load`, `encode`,
+`encode_many`, `encode_graph`, `encode_graphs`, `graph_spec`,
+`embedding_dimension`, `info`, `device`, `full_precision`, with the same
+keyword arguments, argument checks, exception types and message fragments
+(api.py:64-230), so the reference's tests for this path read the same.
+
+What runs underneath is different.  `_run_graph_shard` in the reference
+(api.py:232-260) converts indices to int64, materialises one-hot edge
+attributes, runs ~40 eager torch ops per microbatch, normalises in float64
+on the host and splits rows in a Python loop.  Here the shard's compact
+arrays (float32 features, int32 edge index, uint8 edge types) go to the
+device as they are; microbatch boundaries are computed on the device
+(gfx_pack_microbatches); consecutive microbatches are grouped into device
+chunks; per chunk a destination CSR is built (gfx_csr_build) and the
+forward runs as hand-written sm_100a kernels (gfx_encode) ending in the
+L2-normalise + cast + core-row compaction epilogue; one device->host copy
+per chunk lands in a pinned buffer that the returned per-record arrays are
+row-range views of.
+
+Deviations from the reference, all deliberate:
+  * only CUDA devices are accepted (no CPU path by mandate);
+  * the CUDA path is deterministic (CSR segmented sums, no atomics in
+    floating point), so `allow_nondeterministic_cuda` is accepted but not
+    required (reference: api.py:71-74);
+  * microbatch boundaries do not change any output bit (graphs never
+    interact), so chunks of several microbatches are launched together.
+"""
+from __future__ import annotations
+
+import json
+from pathlib import Path
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from .graph import (Graph, GraphBuilder, GraphCompatibilityError, GraphShard,
+                    GraphSpec)
+from .weights import (BUNDLED_CONFIG, EncoderConfig, FoldedWeights,
+                      ModelIntegrityError, default_model_dir, fold,
+                      load_checkpoint, parameter_count)
+
+DEFAULT_CHUNK_NODES = 1 << 19
+
+
+def _embedding_dtype(value) -> np.dtype:
+    try:
+        dtype = np.dtype(value)
+    except TypeError as exc:
+        raise ValueError(f"unsupported embedding dtype {value!r}") from exc
+    if dtype.kind != "f":
+        raise ValueError(f"embedding dtype must be floating-point, got {dtype}")
+    return dtype
+
+
+def default_alignment_parameters(model_dir=None) -> dict:
+    """Scoring parameters for the separate SW aligner (api.py:47-50)."""
+    root = Path(model_dir) if model_dir is not None else default_model_dir()
+    if root is None:
+        raise ModelIntegrityError("no model directory has been staged")
+    try:
+        data = json.loads((root / "alignment.json").read_text())
+    except (OSError, json.JSONDecodeError) as exc:
+        raise ModelIntegrityError(
+            f"cannot read model metadata {root / 'alignment.json'}: {exc}") from exc
+    return dict(data["scoring_parameters"])
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class DeviceShard:
+    """A GraphShard's numeric arrays resident in HBM (same dtypes and
+    layout as graph.py:261-275; strings stay on the host)."""
+
+    def __init__(self, node_features, edge_index, edge_types, node_ptr,
+                 edge_ptr, node_roles, *, max_nodes_per_record: int,
+                 max_edges_per_record: int, core_count: int, spec: GraphSpec,
+                 core_ptr_host: Optional[np.ndarray] = None):
+        self.node_features = node_features
+        self.edge_index = edge_index
+        self.edge_types = edge_types
+        self.node_ptr = node_ptr
+        self.edge_ptr = edge_ptr
+        self.node_roles = node_roles           # None when every node is core
+        self.record_count = int(node_ptr.shape[0]) - 1
+        self.node_count = int(node_features.shape[0])
+        self.edge_count = int(edge_types.shape[0])
+        self.max_nodes_per_record = int(max_nodes_per_record)
+        self.max_edges_per_record = int(max_edges_per_record)
+        self.core_count = int(core_count)
+        self.spec = spec
+        self.core_ptr_host = core_ptr_host
+
+    @property
+    def device(self):
+        return self.node_features.device
+
+    @classmethod
+    def from_shard(cls, shard: GraphShard, device, *, non_blocking=True):
+        def up(a):
+            return torch.from_numpy(np.ascontiguousarray(a)).to(
+                device, non_blocking=non_blocking)
+
+        all_core = shard.all_core
+        counts = np.diff(shard.node_ptr)
+        ecounts = np.diff(shard.edge_ptr)
+        if all_core:
+            core_ptr, core_count = shard.node_ptr, shard.node_count
+        else:
+            core_ptr = np.zeros(shard.record_count + 1, np.int64)
+            np.cumsum(shard.core_count_array(), out=core_ptr[1:])
+            core_count = int(core_ptr[-1])
+        return cls(up(shard.node_features), up(shard.edge_index),
+                   up(shard.edge_types), up(shard.node_ptr),
+                   up(shard.edge_ptr),
+                   None if all_core else up(shard.node_roles),
+                   max_nodes_per_record=int(counts.max()),
+                   max_edges_per_record=int(ecounts.max()),
+                   core_count=core_count, spec=shard.spec,
+                   core_ptr_host=core_ptr)
+
+
+class _Scratch:
+    """Named device buffers that only ever grow (no allocation in steady state)."""
+
+    def __init__(self, device):
+        self.device = device
+        self._buf: dict = {}
+
+    def get(self, name: str, nbytes: int) -> torch.Tensor:
+        have = self._buf.get(name)
+        if have is None or have.numel() < nbytes:
+            grow = max(int(nbytes), 1024)
+            have = torch.empty(grow + grow // 8, dtype=torch.uint8,
+                               device=self.device)
+            self._buf[name] = have
+        return have
+
+
+class Ginfinity:
+    """Loaded GINFINITY encoder ready for repeated inference on one GPU."""
+
+    def __init__(self, weights: FoldedWeights, metadata: dict, device: str,
+                 graph_spec: GraphSpec, *, full_precision: bool):
+        self._weights = weights
+        self._metadata = metadata
+        self._graph_spec = graph_spec
+        self.device = device
+        self.full_precision = bool(full_precision)
+        self._torch_device = torch.device(device)
+        if self._torch_device.type != "cuda":
+            raise ValueError("device must be a CUDA device")
+        with torch.cuda.device(self._torch_device):
+            self._handle = nat.model_create(weights)
+        self._scratch = _Scratch(self._torch_device)
+        # dense-stage implementation: 0 auto (tcgen05 for fp16), 1 SIMT
+        self.impl = nat.IMPL_AUTO
+        self.fused = False
+        self.chunk_nodes = DEFAULT_CHUNK_NODES
+        self.last_microbatch_bounds: Optional[np.ndarray] = None
+
+    def __del__(self):
+        handle, self._handle = getattr(self, "_handle", None), None
+        if handle:
+            try:
+                nat.model_destroy(handle)
+            except Exception:
+                pass
+
+    # -- construction ------------------------------------------------------
+    @staticmethod
+    def _check_device(device: str) -> None:
+        if not isinstance(device, str) or not device.startswith("cuda"):
+            if device == "cpu":
+                raise ValueError(
+                    "device must be a CUDA device: this build has no CPU path")
+            raise ValueError("device must be 'cpu' or a CUDA device")
+        if not torch.cuda.is_available():
+            raise ValueError("CUDA was requested but is unavailable")
+
+    @classmethod
+    def load(cls, device: str = "cuda", *,
+             allow_nondeterministic_cuda: bool = False,
+             model_dir=None, full_precision: bool = False) -> "Ginfinity":
+        """Verify and load a checkpoint directory (api.py:64-114).
+
+        `allow_nondeterministic_cuda` is accepted for signature
+        compatibility; this CUDA path is deterministic and does not need it.
+        """
+        cls._check_device(device)
+        root = Path(model_dir) if model_dir is not None else default_model_dir()
+        if root is None:
+            raise ModelIntegrityError(
+                "missing checkpoint: no model_dir given and none staged; run "
+                "`python -m ginfinity_b200.stage_model <dir with encoder.pt>`")
+        state, cfg, spec, metadata = load_checkpoint(root)
+        return cls(fold(state, cfg), metadata, device, spec,
+                   full_precision=full_precision)
+
+    @classmethod
+    def from_state(cls, state, cfg: EncoderConfig = BUNDLED_CONFIG,
+                   device: str = "cuda", *, full_precision: bool = False
+                   ) -> "Ginfinity":
+        """Build an encoder from an in-memory state dict (tests, benchmarks
+        with random-init weights)."""
+        cls._check_device(device)
+        spec = GraphSpec.from_encoder_config(cfg)
+        metadata = {"format_version": 1, "package": "ginfinity_b200",
+                    "parameter_count": parameter_count(state),
+                    "embedding_dimension": cfg.out_dim,
+                    "graph_spec": spec.to_dict(),
+                    "graph_spec_sha256": spec.sha256,
+                    "checkpoint_sha256": None}
+        return cls(fold(state, cfg), metadata, device, spec,
+                   full_precision=full_precision)
+
+    # -- properties (api.py:116-126) ---------------------------------------
+    @property
+    def embedding_dimension(self) -> int:
+        return self._weights.cfg.out_dim
+
+    @property
+    def graph_spec(self) -> GraphSpec:
+        return self._graph_spec
+
+    def info(self) -> dict:
+        return json.loads(json.dumps(self._metadata))
+
+    # -- record-level API (api.py:128-178) -----------------------------------
+    def encode(self, record, *, keep_paired_neighbours: bool = False,
+               context_hops: int = 1, embedding_dtype=np.float16) -> np.ndarray:
+        return self.encode_many(
+            [record], keep_paired_neighbours=keep_paired_neighbours,
+            context_hops=context_hops, embedding_dtype=embedding_dtype)[0]
+
+    def encode_many(self, records: Sequence, *, max_batch_nodes: int = 60_000,
+                    max_batch_edges: int = 300_000,
+                    keep_paired_neighbours: bool = False, context_hops: int = 1,
+                    embedding_dtype=np.float16) -> list:
+        records = list(records)
+        if not records:
+            return []
+        shard = GraphBuilder(
+            self._graph_spec, keep_paired_neighbours=keep_paired_neighbours,
+            context_hops=context_hops).build_shard(records)
+        return self.encode_graphs(shard, max_batch_nodes=max_batch_nodes,
+                                  max_batch_edges=max_batch_edges,
+                                  embedding_dtype=embedding_dtype)
+
+    def encode_graph(self, graph: Graph, *, embedding_dtype=np.float16
+                     ) -> np.ndarray:
+        return self.encode_graphs([graph], embedding_dtype=embedding_dtype)[0]
+
+    # -- shard-level API (api.py:180-230) ------------------------------------
+    def _check_request(self, spec, max_nodes_per_record, max_edges_per_record,
+                       max_batch_nodes, max_batch_edges, embedding_dtype):
+        if spec.sha256 != self._graph_spec.sha256:
+            raise GraphCompatibilityError(
+                "graphs were built with a specification incompatible with "
+                "this encoder")
+        if max_batch_nodes <= 0 or max_batch_edges <= 0:
+            raise ValueError("batch node and edge limits must be positive")
+        dtype = _embedding_dtype(embedding_dtype)
+        if max_nodes_per_record > max_batch_nodes:
+            raise ValueError("max_batch_nodes is smaller than the longest graph")
+        if max_edges_per_record > max_batch_edges:
+            raise ValueError("max_batch_edges is smaller than the largest graph")
+        return dtype
+
+    def encode_graphs(self, graphs, *, max_batch_nodes: int = 60_000,
+                      max_batch_edges: int = 300_000,
+                      embedding_dtype=np.float16) -> list:
+        """Encode prebuilt graphs; one (core_count_i, 128) array per record,
+        in input order."""
+        if isinstance(graphs, GraphShard):
+            shard = graphs
+        else:
+            graph_list = list(graphs)
+            if not graph_list:
+                return []
+            shard = GraphShard.from_graphs(graph_list)
+        # all argument errors are raised before any device work (api.py:196-210)
+        counts = np.diff(shard.node_ptr)
+        ecounts = np.diff(shard.edge_ptr)
+        dtype = self._check_request(shard.spec, int(counts.max()),
+                                    int(ecounts.max()), max_batch_nodes,
+                                    max_batch_edges, embedding_dtype)
+        with torch.cuda.device(self._torch_device), torch.inference_mode():
+            dshard = DeviceShard.from_shard(shard, self._torch_device)
+            out_code = nat.GFX_F16 if dtype == np.float16 else nat.GFX_F32
+            out = self.encode_device_shard(
+                dshard, max_batch_nodes=max_batch_nodes,
+                max_batch_edges=max_batch_edges, out_dtype=out_code,
+                _checked=True)
+            host = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+            host.copy_(out, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        table = host.numpy()
+        if table.dtype != dtype:
+            table = table.astype(dtype)
+        return split_rows(table, dshard.core_ptr_host)
+
+    def encode_device_shard(self, ds: DeviceShard, *, max_batch_nodes=60_000,
+                            max_batch_edges=300_000, out_dtype=nat.GFX_F16,
+                            out: Optional[torch.Tensor] = None,
+                            _checked: bool = False) -> torch.Tensor:
+        """Device-resident encode: HBM in, HBM out ([core_count, 128] in
+        `out_dtype`).  Everything is enqueued on the current stream; the only
+        host synchronisation is the read-back of the microbatch boundaries."""
+        if not _checked:
+            self._check_request(ds.spec, ds.max_nodes_per_record,
+                                ds.max_edges_per_record, max_batch_nodes,
+                                max_batch_edges, np.float16)
+        dev = self._torch_device
+        stream = torch.cuda.current_stream().cuda_stream
+        B, N = ds.record_count, ds.node_count
+        # ---- K4: microbatch boundaries on the device ----------------------
+        next_stop = torch.empty(B, dtype=torch.int64, device=dev)
+        bounds = torch.empty(B + 2, dtype=torch.int64, device=dev)
+        nat.check(nat.lib.gfx_pack_microbatches(
+            ds.node_ptr.data_ptr(), ds.edge_ptr.data_ptr(), B,
+            int(max_batch_nodes), int(max_batch_edges), next_stop.data_ptr(),
+            bounds.data_ptr(), bounds[B + 1:].data_ptr(), stream))
+        stops = bounds[:B + 1].clamp_(0, B)     # the tail past n_bounds is unset
+        packed = torch.stack((stops, ds.node_ptr[stops], ds.edge_ptr[stops]))
+        count = int(bounds[B + 1].item())
+        plan = packed[:, :count].cpu().numpy()
+        self.last_microbatch_bounds = plan[0].copy()
+        # ---- output and core-row map ---------------------------------------
+        tdtype = torch.float16 if out_dtype == nat.GFX_F16 else torch.float32
+        if out is None:
+            out = torch.empty((ds.core_count, 128), dtype=tdtype, device=dev)
+        out_row = None
+        if ds.node_roles is not None:
+            out_row = torch.empty(N, dtype=torch.int32, device=dev)
+            n_core = torch.empty(1, dtype=torch.int64, device=dev)
+            need = nat.lib.gfx_core_rows_workspace_bytes(N)
+            ws = self._scratch.get("core", need)
+            nat.check(nat.lib.gfx_core_rows(
+                ds.node_roles.data_ptr(), N, out_row.data_ptr(),
+                n_core.data_ptr(), ws.data_ptr(), need, stream))
+        # ---- chunks of consecutive microbatches ------------------------------
+        act = nat.GFX_F32 if self.full_precision else nat.GFX_F16
+        node_at, edge_at = plan[1], plan[2]
+        start = 0
+        while start < count - 1:
+            stop = start + 1
+            while (stop < count - 1 and
+                   node_at[stop + 1] - node_at[start] <= self.chunk_nodes):
+                stop += 1
+            n0, n1 = int(node_at[start]), int(node_at[stop])
+            e0, e1 = int(edge_at[start]), int(edge_at[stop])
+            self._run_chunk(ds, n0, n1, e0, e1, out_row, out, act, out_dtype,
+                            stream)
+            start = stop
+        return out
+
+    def _run_chunk(self, ds, n0, n1, e0, e1, out_row, out, act, out_dtype,
+                   stream) -> None:
+        n, e = n1 - n0, e1 - e0
+        lib = nat.lib
+        csr_ws_bytes = lib.gfx_csr_workspace_bytes(n, e)
+        enc_ws_bytes = lib.gfx_encode_workspace_bytes(n, act)
+        row_ptr = self._scratch.get("row_ptr", 4 * (n + 1))
+        col_src = self._scratch.get("col_src", 4 * max(e, 1))
+        col_type = self._scratch.get("col_type", max(e, 1))
+        csr_ws = self._scratch.get("csr_ws", csr_ws_bytes)
+        enc_ws = self._scratch.get("enc_ws", enc_ws_bytes)
+        ei = ds.edge_index
+        nat.check(lib.gfx_csr_build(
+            ei[0, e0:].data_ptr() if e else None,
+            ei[1, e0:].data_ptr() if e else None,
+            ds.edge_types[e0:].data_ptr() if e else None, n, e, n0,
+            row_ptr.data_ptr(), col_src.data_ptr(), col_type.data_ptr(),
+            csr_ws.data_ptr(), csr_ws_bytes, stream))
+        if out_row is None:
+            out_base = out[n0:].data_ptr()      # identity map: row i -> n0 + i
+            map_ptr = None
+        else:
+            out_base = out.data_ptr()           # ranks in out_row are global
+            map_ptr = out_row[n0:].data_ptr()
+        nat.check(lib.gfx_encode(
+            self._handle, ds.node_features[n0:].data_ptr(), row_ptr.data_ptr(),
+            col_src.data_ptr(), col_type.data_ptr(), map_ptr, n, out_base, act,
+            out_dtype, self.impl, 1 if self.fused else 0, enc_ws.data_ptr(),
+            enc_ws_bytes, stream))
+
+
+def split_rows(table: np.ndarray, row_ptr: np.ndarray) -> list:
+    """Per-record row-range views of the [total_core, 128] result
+    (replaces the per-record mask loop of api.py:253-259)."""
+    edges = row_ptr.tolist()
+    return [table[a:b] for a, b in zip(edges[:-1], edges[1:])]

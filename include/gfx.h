@@ -1,0 +1,198 @@
+/*
+ * gfx.h -- C ABI of libgfx.so, the B200 (sm_100a) GINFINITY encoder path.
+ *
+ * The reference (nicoaira/GINFINITY 1.2.1) has no FFI layer: its hot path is
+ * the Python method Ginfinity._run_graph_shard (src/ginfinity/api.py:232-260)
+ * calling GINEEncoder.forward (src/ginfinity/_model.py:65-72).  The entry
+ * points below are what a binding for that path replaces; each one cites the
+ * reference lines it stands in for.  INTEGRATION.md shows the ctypes stub a
+ * reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross the boundary
+ *   - every pointer is a DEVICE pointer unless the name ends in _host
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default)
+ *   - all work is enqueued on `stream`; no call synchronises the device
+ *     except gfx_model_create / gfx_model_destroy
+ *   - return 0 on success, a GFX_ERR_* code otherwise; the message for the
+ *     calling thread's last failure is gfx_last_error()
+ *   - no hidden device allocation after gfx_model_create: scratch space is
+ *     passed in, sized by the *_workspace_bytes queries
+ *   - dtype codes: GFX_F16 = IEEE half storage with fp32 accumulation
+ *     (reference default, api.py:111-112), GFX_F32 = fp32 storage
+ *     (full_precision=True)
+ */
+#ifndef GFX_H_
+#define GFX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GFX_ABI_VERSION 1
+
+enum {
+  GFX_OK = 0,
+  GFX_ERR_ARGUMENT = 1,
+  GFX_ERR_CUDA = 2,
+  GFX_ERR_WORKSPACE = 3,
+  GFX_ERR_UNSUPPORTED = 4
+};
+
+enum { GFX_F16 = 0, GFX_F32 = 1 };
+
+/* which implementation runs the dense stages */
+enum {
+  GFX_IMPL_AUTO = 0,  /* tcgen05 for GFX_F16, SIMT for GFX_F32 */
+  GFX_IMPL_SIMT = 1,  /* CUDA-core fp32-accumulate kernels */
+  GFX_IMPL_UMMA = 2   /* tcgen05.mma / TMEM kernels (GFX_F16 only) */
+};
+
+int gfx_abi_version(void);
+const char *gfx_last_error(void);
+
+/* ------------------------------------------------------------------------
+ * Model.  Folded weights as produced by ginfinity_b200.weights.fold():
+ * eval BatchNorm folded into W1/b1 (_model.py:35), edge_lin(one_hot(t))
+ * tabulated as table[l][t][:] = W_e[:,t] + b_e (_model.py:33,43 with
+ * api.py:243-245), eps1[l] = 1 + eps_l (_model.py:46).
+ * Replaces: model.load_state_dict + .to(device) + .half() (api.py:101-112).
+ * ------------------------------------------------------------------------ */
+typedef struct {
+  int32_t hidden;      /* 128 */
+  int32_t layers;      /* 4   */
+  int32_t out_dim;     /* 128 */
+  int32_t feature_dim; /* 7   */
+  int32_t edge_dim;    /* 10  */
+  const float *w_in_host; /* [hidden, feature_dim] */
+  const float *b_in_host; /* [hidden] */
+  const float *table_host; /* [layers, edge_dim, hidden] */
+  const float *eps1_host;  /* [layers] */
+  const float *w1_host;    /* [layers, 2*hidden, hidden]  (BN folded) */
+  const float *b1_host;    /* [layers, 2*hidden] */
+  const float *w2_host;    /* [layers, hidden, 2*hidden] */
+  const float *b2_host;    /* [layers, hidden] */
+  const float *ln_g_host;  /* [layers, hidden] */
+  const float *ln_b_host;  /* [layers, hidden] */
+  const float *wa_host;    /* [hidden, hidden]   head.0 */
+  const float *ba_host;    /* [hidden] */
+  const float *wb_host;    /* [out_dim, hidden]  head.2 */
+  const float *bb_host;    /* [out_dim] */
+} gfx_folded_weights;
+
+typedef struct gfx_model gfx_model;
+
+int gfx_model_create(const gfx_folded_weights *weights, gfx_model **out);
+int gfx_model_destroy(gfx_model *model);
+
+/* ------------------------------------------------------------------------
+ * K4  microbatch packing on device.  Replaces the greedy contiguous
+ * first-fit loop of encode_graphs (api.py:211-229); bit-identical
+ * boundaries.  node_ptr / edge_ptr are the shard's int64 [B+1] arrays
+ * (graph.py:271-272).  next_stop is scratch [B].  bounds receives
+ * [0, stop_1, ..., B] and n_bounds its length (both device).
+ * ------------------------------------------------------------------------ */
+int gfx_pack_microbatches(const int64_t *node_ptr, const int64_t *edge_ptr,
+                          int64_t num_records, int64_t max_batch_nodes,
+                          int64_t max_batch_edges, int64_t *next_stop,
+                          int64_t *bounds, int64_t *n_bounds, void *stream);
+
+/* ------------------------------------------------------------------------
+ * K0  destination-CSR build.  Replaces the per-layer
+ * index_select / index_add_ addressing (_model.py:41-45): edges
+ * [edge_begin, edge_begin+E) of a shard's (2,E_total) int32 edge_index are
+ * stably sorted by destination.  node_base is subtracted from both
+ * endpoints (what GraphShard.slice does on the host, graph.py:424-427).
+ * Output: row_ptr int32 [N+1], col_src int32 [E], col_type uint8 [E];
+ * bit-identical to numpy.argsort(dst, kind="stable").
+ * ------------------------------------------------------------------------ */
+size_t gfx_csr_workspace_bytes(int64_t num_nodes, int64_t num_edges);
+int gfx_csr_build(const int32_t *edge_src, const int32_t *edge_dst,
+                  const uint8_t *edge_type, int64_t num_nodes,
+                  int64_t num_edges, int32_t node_base, int32_t *row_ptr,
+                  int32_t *col_src, uint8_t *col_type, void *workspace,
+                  size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Core-row map.  Replaces the per-record boolean masks of api.py:253-259:
+ * out_row[i] = rank of node i among nodes with node_roles == 0, or -1 for
+ * context nodes; n_core receives the number of core nodes (device int64).
+ * ------------------------------------------------------------------------ */
+size_t gfx_core_rows_workspace_bytes(int64_t num_nodes);
+int gfx_core_rows(const uint8_t *node_roles, int64_t num_nodes,
+                  int32_t *out_row, int64_t *n_core, void *workspace,
+                  size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Stage kernels (one reference op group each).  h / z buffers are
+ * [num_nodes, hidden] row-major in `dtype` storage.
+ * ------------------------------------------------------------------------ */
+
+/* h = x W_in^T + b_in            (_model.py:55,67; x is float32 [N,7]) */
+int gfx_input_linear(const gfx_model *model, const float *x,
+                     int64_t num_nodes, void *h, int dtype, void *stream);
+
+/* K1: z_i = (1+eps_l) h_i + sum_{e: dst=i} relu(h[src_e] + table_l[type_e])
+ *                                (_model.py:41-46) */
+int gfx_aggregate(const gfx_model *model, int layer, const void *h,
+                  const int32_t *row_ptr, const int32_t *col_src,
+                  const uint8_t *col_type, int64_t num_nodes, void *z,
+                  int dtype, void *stream);
+
+/* K2: h_out = h + LayerNorm_l(W2 relu(W1' z + b1') + b2)
+ *                                (_model.py:34-36, 68-71) */
+int gfx_mlp_ln_residual(const gfx_model *model, int layer, const void *z,
+                        const void *h, int64_t num_nodes, void *h_out,
+                        int dtype, int impl, void *stream);
+
+/* K1+K2 in one kernel (z never leaves the SM); GFX_F16 only */
+int gfx_layer_fused(const gfx_model *model, int layer, const void *h,
+                    const int32_t *row_ptr, const int32_t *col_src,
+                    const uint8_t *col_type, int64_t num_nodes, void *h_out,
+                    void *stream);
+
+/* K3: y = Wb relu(Wa h + ba) + bb; out[out_row[i]] = y_i / max(|y_i|, 1e-12)
+ * cast to out_dtype.  out_row == NULL means identity.
+ *                                (_model.py:61-63,72; api.py:250-259) */
+int gfx_head_l2norm(const gfx_model *model, const void *h,
+                    const int32_t *out_row, int64_t num_nodes, void *out,
+                    int dtype, int out_dtype, int impl, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Whole forward over one packed chunk of graphs (all stages above in
+ * order).  Replaces Ginfinity._run_graph_shard's device work
+ * (api.py:236-252).  workspace holds the activation ping-pong buffers.
+ * ------------------------------------------------------------------------ */
+size_t gfx_encode_workspace_bytes(int64_t num_nodes, int dtype);
+int gfx_encode(const gfx_model *model, const float *x, const int32_t *row_ptr,
+               const int32_t *col_src, const uint8_t *col_type,
+               const int32_t *out_row, int64_t num_nodes, void *out, int dtype,
+               int out_dtype, int impl, int fused, void *workspace,
+               size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------
+ * K5  similarity search (no reference counterpart; north-star item 4).
+ * queries [Q,dim], database [D,dim] are GFX_F16 row-major unit vectors.
+ * metric 0 = cosine (dot product), 1 = L2 (ranked by -|q-d|^2).
+ * Result order: score descending, database index ascending on ties;
+ * out_scores float32 [Q,k], out_index int64 [Q,k] (index + index_base).
+ * ------------------------------------------------------------------------ */
+size_t gfx_topk_workspace_bytes(int64_t num_queries, int64_t num_rows, int k);
+int gfx_topk(const void *queries, int64_t num_queries, const void *database,
+             int64_t num_rows, int dim, int k, int metric, int64_t index_base,
+             float *out_scores, int64_t *out_index, void *workspace,
+             size_t workspace_bytes, void *stream);
+
+/* k-way merge of `parts` per-query sorted lists (all-gathered from the
+ * ranks) into the global top-k: in_* are [parts, Q, k]. */
+int gfx_topk_merge(const float *in_scores, const int64_t *in_index, int parts,
+                   int64_t num_queries, int k, float *out_scores,
+                   int64_t *out_index, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GFX_H_ */

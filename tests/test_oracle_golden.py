@@ -1,0 +1,144 @@
+"""Pin the oracle (oracle/gine_oracle.py) to the reference.
+
+The reference's tests store no embedding vectors, so the
+oracle is checked against outputs of the reference itself, recorded by
+oracle/make_golden.py into tests/golden/, and against the reference's exact
+integer known-answers (its tests/test_graph.py:21-33 and
+tests/test_sliced_graphs.py:23-69).
+"""
+import numpy as np
+import pytest
+
+from oracle import gine_oracle as O
+
+ARRAYS = ("node_features", "edge_index", "edge_types", "node_ptr", "edge_ptr",
+          "residue_index", "node_roles")
+
+
+def test_oracle_graph_builder_matches_reference_arrays(golden_meta, golden_graphs):
+    x_all, ei_all, et_all = golden_graphs["full/node_features"], golden_graphs["full/edge_index"], golden_graphs["full/edge_types"]
+    nptr, eptr = golden_graphs["full/node_ptr"], golden_graphs["full/edge_ptr"]
+    for i, (_, seq, dbn) in enumerate(golden_meta["full"]):
+        x, ei, et = O.build_full_graph(seq, dbn)
+        n0, n1, e0, e1 = nptr[i], nptr[i + 1], eptr[i], eptr[i + 1]
+        assert np.array_equal(x, x_all[n0:n1])                  # bit-exact incl. sin/cos
+        assert np.array_equal(ei + np.int32(n0), ei_all[:, e0:e1])
+        assert np.array_equal(et, et_all[e0:e1])
+
+
+def test_reference_integer_known_answers():
+    # tests/test_graph.py:21-33 : ACGUACGU/((....)) has 30 edges
+    x, ei, et = O.build_full_graph("ACGUACGU", "((....))")
+    assert x.shape == (8, 7) and ei.shape == (2, 30) and et.shape == (30,)
+    # E = 4L - 6 + 2P  
+    for seq, dbn in (("A", "."), ("AC", ".."), ("GAC", "(.)"), ("GGAA", "(())")):
+        L, P = len(seq), dbn.count("(")
+        assert O.build_full_graph(seq, dbn)[1].shape[1] == 2 * max(L - 1, 0) + 2 * max(L - 2, 0) + 2 * P
+    # tests/test_sliced_graphs.py:23-69
+    seq, dbn = "GGGAAACCCUUUUGGG", "......(((....)))"
+    _, ei, _ = O.build_full_graph(seq, dbn)
+    res, roles = O.select_slice_nodes(16, ei, dbn, 9, 16, False, 1)
+    assert res.tolist() == list(range(9, 16)) and not roles.any()
+    res, roles = O.select_slice_nodes(16, ei, dbn, 9, 16, True, 1)
+    assert res.tolist() == list(range(6, 16)) and roles.tolist() == [1, 1, 1] + [0] * 7
+    res, roles = O.select_slice_nodes(16, ei, dbn, 9, 16, True, 2)
+    assert res[roles == 1].tolist() == [4, 5, 6, 7, 8]
+    res, roles = O.select_slice_nodes(16, ei, dbn, 9, 16, True, 3)
+    assert res.tolist() == list(range(2, 16)) and res[roles == 1].tolist() == list(range(2, 9))
+
+
+def test_oracle_slices_match_reference_arrays(golden_meta, golden_graphs):
+    for k, w in enumerate(golden_meta["windows"]):
+        _, seq, dbn, start, end = w["record"]
+        x, ei, et = O.build_full_graph(seq, dbn)
+        res, roles = O.select_slice_nodes(len(seq), ei, dbn, start, end, w["keep"], w["hops"])
+        xs, eis, ets = O.extract_slice(x, ei, et, res)
+        assert np.array_equal(res, golden_graphs[f"window{k}/residue_index"])
+        assert np.array_equal(roles, golden_graphs[f"window{k}/node_roles"])
+        assert np.array_equal(xs, golden_graphs[f"window{k}/node_features"])
+        assert np.array_equal(eis, golden_graphs[f"window{k}/edge_index"])
+        assert np.array_equal(ets, golden_graphs[f"window{k}/edge_types"])
+
+
+def test_oracle_packing_matches_reference_loop(golden_meta, golden_graphs):
+    lengths = np.diff(golden_graphs["full/node_ptr"]).tolist()
+    ecounts = np.diff(golden_graphs["full/edge_ptr"]).tolist()
+    seen = 0
+    for case in golden_meta["packing"]:
+        if isinstance(case["bounds"], dict):
+            assert "smaller than" in case["bounds"]["error"]
+            continue
+        got = O.pack_microbatches(lengths, ecounts, case["max_batch_nodes"], case["max_batch_edges"])
+        assert got.tolist() == case["bounds"]
+        seen += 1
+    assert seen >= 3
+
+
+def _normalised(y, graphs, prefix, dtype=np.float32):
+    return np.concatenate(O.normalise_and_split(
+        y, graphs[f"{prefix}/node_ptr"], graphs[f"{prefix}/node_roles"], dtype))
+
+
+def test_oracle_forward_matches_reference_fp32(real_state, golden_graphs, golden_embeddings):
+    g = golden_graphs
+    ref = golden_embeddings["full/fp32_model_f32"]
+    y = O.forward_literal(real_state, g["full/node_features"], g["full/edge_index"], g["full/edge_types"])
+    assert np.abs(_normalised(y, g, "full") - ref).max() <= 2e-6      # measured 2.8e-7
+    fw = O.fold_state(real_state)
+    rp, cs, ct = O.csr_by_destination(g["full/edge_index"], g["full/edge_types"], g["full/node_features"].shape[0])
+    y2 = O.forward_folded(fw, g["full/node_features"], rp, cs, ct)
+    assert np.abs(_normalised(y2, g, "full") - ref).max() <= 2e-6     # measured 5.6e-7
+
+
+def test_oracle_fp16_storage_model_is_within_the_stated_tolerances(real_state, golden_graphs, golden_embeddings):
+    g = golden_graphs
+    fw = O.fold_state(real_state)
+    rp, cs, ct = O.csr_by_destination(g["full/edge_index"], g["full/edge_types"], g["full/node_features"].shape[0])
+    y = O.forward_folded(fw, g["full/node_features"], rp, cs, ct, half_storage=True)
+    got = _normalised(y, g, "full")
+    ref32 = golden_embeddings["full/fp32_model_f32"]
+    ref16 = golden_embeddings["full/fp16_model_f16"].astype(np.float32)
+    cos = (got.astype(np.float64) * ref32).sum(1) / np.linalg.norm(got.astype(np.float64), axis=1)
+    assert cos.min() >= 0.999
+    assert np.abs(got - ref16).max() <= 4e-3
+
+
+def test_oracle_windows_match_reference(real_state, golden_meta, golden_graphs, golden_embeddings):
+    fw = O.fold_state(real_state)
+    for k in range(len(golden_meta["windows"])):
+        p = f"window{k}"
+        g = golden_graphs
+        rp, cs, ct = O.csr_by_destination(g[p + "/edge_index"], g[p + "/edge_types"], g[p + "/node_features"].shape[0])
+        y = O.forward_folded(fw, g[p + "/node_features"], rp, cs, ct)
+        got = _normalised(y, g, p)
+        assert got.shape == golden_embeddings[p + "/fp32_model_f32"].shape
+        assert np.abs(got - golden_embeddings[p + "/fp32_model_f32"]).max() <= 2e-6
+
+
+def test_csr_is_a_stable_sort():
+    rng = np.random.default_rng(0)
+    ei = rng.integers(0, 50, (2, 400)).astype(np.int32)
+    et = rng.integers(0, 6, 400).astype(np.uint8)
+    rp, cs, ct = O.csr_by_destination(ei, et, 50)
+    assert rp[0] == 0 and rp[-1] == 400
+    for i in range(50):
+        mine = np.flatnonzero(ei[1] == i)            # original order
+        assert np.array_equal(cs[rp[i]:rp[i + 1]], ei[0][mine])
+        assert np.array_equal(ct[rp[i]:rp[i + 1]], et[mine])
+
+
+def test_topk_oracle_orders_ties_by_index():
+    q = np.eye(4, dtype=np.float32)[:2]
+    db = np.concatenate([np.eye(4, dtype=np.float32)] * 3)      # every row appears 3x
+    val, idx = O.topk_bruteforce(q, db, 4)
+    assert idx[0].tolist() == [0, 4, 8, 1] and idx[1].tolist() == [1, 5, 9, 0]
+    assert val[0].tolist() == [1, 1, 1, 0]
+
+
+def test_encode_shard_oracle_is_microbatch_invariant(synthetic_state, golden_shard):
+    fw = O.fold_state(synthetic_state)
+    a = O.encode_shard(fw, golden_shard, embedding_dtype=np.float32)
+    b = O.encode_shard(fw, golden_shard, max_batch_nodes=700, max_batch_edges=3000, embedding_dtype=np.float32)
+    assert len(a) == len(b) == golden_shard.record_count
+    for u, v in zip(a, b):
+        np.testing.assert_allclose(u, v, rtol=1e-5, atol=3e-7)   # reference tests/test_graph.py:85-98
