@@ -65,7 +65,13 @@ _SIGNATURES = {
     "gfx_topk": (C.c_int, [_p, _i64, _p, _i64, C.c_int, C.c_int, C.c_int, _i64,
                            _p, _p, _p, _sz, _p]),
     "gfx_topk_merge": (C.c_int, [_p, _p, C.c_int, _i64, C.c_int, _p, _p, _p]),
+    "gfx_profile_enable": (C.c_int, [C.c_uint32]),
+    "gfx_profile_read": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(_i64), C.c_int]),
+    "gfx_launch_counts": (C.c_int, [C.POINTER(_i64), C.c_int]),
 }
+
+STAGES = ("pack", "csr", "core_rows", "input", "aggregate", "mlp", "head",
+          "fused_layer", "topk")
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
@@ -107,3 +113,24 @@ def model_create(folded) -> int:
 def model_destroy(handle) -> None:
     if handle:
         lib.gfx_model_destroy(_p(handle))
+
+
+def launch_counts(reset: bool = False) -> dict:
+    buf = (_i64 * len(STAGES))()
+    check(lib.gfx_launch_counts(buf, 1 if reset else 0))
+    return dict(zip(STAGES, list(buf)))
+
+
+def profile_enable(*stages: str) -> None:
+    mask = 0
+    for name in stages:
+        mask |= 1 << STAGES.index(name)
+    check(lib.gfx_profile_enable(mask))
+
+
+def profile_read(stage: str, reset: bool = True) -> tuple:
+    """(total device milliseconds, number of timed calls) for one stage."""
+    ms, calls = C.c_double(0), _i64(0)
+    check(lib.gfx_profile_read(STAGES.index(stage), C.byref(ms), C.byref(calls),
+                               1 if reset else 0))
+    return ms.value, calls.value

@@ -1,5 +1,7 @@
 // Error plumbing, model upload and the whole-chunk forward driver.
+#include <atomic>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "gfx_common.cuh"
@@ -12,6 +14,35 @@ void set_error(const std::string &msg) { g_last_error = msg; }
 int fail(int code, const std::string &msg) {
   g_last_error = msg;
   return code;
+}
+
+// ---- instrumentation ----------------------------------------------------------
+struct TimedCall { cudaEvent_t start, stop; int stage; };
+static std::mutex g_prof_mutex;
+static std::atomic<uint32_t> g_prof_mask{0};
+static std::atomic<int64_t> g_launches[GFX_NUM_STAGES];
+static std::vector<TimedCall> g_timed;          // recorded, not yet read
+static std::vector<TimedCall> g_free;           // event pairs for reuse
+
+StageScope::StageScope(int stage, cudaStream_t st, int launches) : st_(st), stop_(nullptr) {
+  g_launches[stage].fetch_add(launches, std::memory_order_relaxed);
+  if (!(g_prof_mask.load(std::memory_order_relaxed) & (1u << stage))) return;
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
+  TimedCall c;
+  if (!g_free.empty()) {
+    c = g_free.back();
+    g_free.pop_back();
+  } else if (cudaEventCreate(&c.start) != cudaSuccess || cudaEventCreate(&c.stop) != cudaSuccess) {
+    return;
+  }
+  c.stage = stage;
+  cudaEventRecord(c.start, st);
+  stop_ = c.stop;
+  g_timed.push_back(c);
+}
+
+StageScope::~StageScope() {
+  if (stop_) cudaEventRecord(stop_, st_);
 }
 
 // Round-trip through fp16 (round-to-nearest-even), on the host.
@@ -76,6 +107,43 @@ using namespace gfx;
 
 extern "C" int gfx_abi_version(void) { return GFX_ABI_VERSION; }
 extern "C" const char *gfx_last_error(void) { return gfx::g_last_error.c_str(); }
+
+extern "C" int gfx_profile_enable(uint32_t mask) {
+  gfx::g_prof_mask.store(mask);
+  return GFX_OK;
+}
+
+extern "C" int gfx_profile_read(int stage, double *total_ms, int64_t *timed_calls, int reset) {
+  if (stage < 0 || stage >= GFX_NUM_STAGES) return fail(GFX_ERR_ARGUMENT, "gfx_profile_read: bad stage");
+  std::lock_guard<std::mutex> lock(gfx::g_prof_mutex);
+  double total = 0;
+  int64_t calls = 0;
+  std::vector<gfx::TimedCall> keep;
+  for (auto &c : gfx::g_timed) {
+    if (c.stage != stage) {
+      keep.push_back(c);
+      continue;
+    }
+    float ms = 0;
+    GFX_CUDA(cudaEventSynchronize(c.stop));
+    GFX_CUDA(cudaEventElapsedTime(&ms, c.start, c.stop));
+    total += ms;
+    ++calls;
+    if (reset) gfx::g_free.push_back(c); else keep.push_back(c);
+  }
+  gfx::g_timed.swap(keep);
+  if (total_ms) *total_ms = total;
+  if (timed_calls) *timed_calls = calls;
+  return GFX_OK;
+}
+
+extern "C" int gfx_launch_counts(int64_t *counts, int reset) {
+  for (int s = 0; s < GFX_NUM_STAGES; ++s) {
+    if (counts) counts[s] = gfx::g_launches[s].load();
+    if (reset) gfx::g_launches[s].store(0);
+  }
+  return GFX_OK;
+}
 
 extern "C" int gfx_model_create(const gfx_folded_weights *w, gfx_model **out) {
   if (!w || !out) return fail(GFX_ERR_ARGUMENT, "gfx_model_create: null argument");

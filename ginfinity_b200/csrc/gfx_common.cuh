@@ -38,6 +38,20 @@ int fail(int code, const std::string &msg);
 
 inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// Counts `launches` kernel launches for `stage`; if the stage is being
+// profiled, brackets the enclosing scope with CUDA events on `st`.
+class StageScope {
+ public:
+  StageScope(int stage, cudaStream_t st, int launches);
+  ~StageScope();
+  StageScope(const StageScope &) = delete;
+  StageScope &operator=(const StageScope &) = delete;
+
+ private:
+  cudaStream_t st_;
+  cudaEvent_t stop_;
+};
+
 }  // namespace gfx
 
 // Device-side weights.  One allocation ("arena") holds everything.

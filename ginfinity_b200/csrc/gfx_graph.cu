@@ -222,8 +222,6 @@ __global__ void csr_place_big_kernel(const int32_t *__restrict__ src,
   }
 }
 
-__global__ void set_last_kernel(int32_t *row_ptr, int64_t N, int32_t E) { row_ptr[N] = E; }
-
 // ---------------------------------------------------------------------------
 // core-row map
 // ---------------------------------------------------------------------------
@@ -260,6 +258,7 @@ extern "C" int gfx_pack_microbatches(const int64_t *node_ptr, const int64_t *edg
   if (max_nodes <= 0 || max_edges <= 0)
     return fail(GFX_ERR_ARGUMENT, "batch node and edge limits must be positive");
   cudaStream_t st = as_stream(stream);
+  StageScope scope(GFX_STAGE_PACK, st, 2);
   pack_next_kernel<<<int((B + 255) / 256), 256, 0, st>>>(node_ptr, edge_ptr, B, max_nodes,
                                                          max_edges, next_stop);
   pack_chase_kernel<<<1, 32, 0, st>>>(next_stop, B, bounds, n_bounds);
@@ -288,6 +287,7 @@ extern "C" int gfx_csr_build(const int32_t *edge_src, const int32_t *edge_dst,
   int *sums = reinterpret_cast<int *>(p); p += align256(size_t(scan_blocks(N + 1) + 1) * 4);
   int32_t *big_rows = reinterpret_cast<int32_t *>(p); p += align256(size_t(N) * 4);
   int *n_big = reinterpret_cast<int *>(p);
+  StageScope scope(GFX_STAGE_CSR, st, (E > 0 ? 1 : 0) + 3 + ((N == 0 || E == 0) ? 0 : 3));
   GFX_CUDA(cudaMemsetAsync(deg, 0, size_t(N + 1) * 4, st));
   GFX_CUDA(cudaMemsetAsync(n_big, 0, 4, st));
   if (E > 0) csr_count_kernel<<<grid_for(E, 256), 256, 0, st>>>(edge_dst, E, node_base, deg);
@@ -321,6 +321,7 @@ extern "C" int gfx_core_rows(const uint8_t *roles, int64_t N, int32_t *out_row, 
   char *p = static_cast<char *>(ws);
   int *flag = reinterpret_cast<int *>(p); p += align256(size_t(N) * 4);
   int *sums = reinterpret_cast<int *>(p);
+  StageScope scope(GFX_STAGE_CORE_ROWS, st, 5);
   core_flag_kernel<<<grid_for(N, 256), 256, 0, st>>>(roles, N, flag);
   int rc = exclusive_scan(flag, out_row, N, sums, n_core, st);
   if (rc) return rc;

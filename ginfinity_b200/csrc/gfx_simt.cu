@@ -328,6 +328,7 @@ extern "C" int gfx_input_linear(const gfx_model *m, const float *x, int64_t n, v
   if (!m) return fail(GFX_ERR_ARGUMENT, "gfx_input_linear: null model");
   if (n <= 0) return GFX_OK;
   cudaStream_t st = as_stream(stream);
+  StageScope scope(GFX_STAGE_INPUT, st, 1);
   if (dtype == GFX_F16)
     input_linear_kernel<__half><<<row_grid(n), 256, 0, st>>>(x, m->w_in[1], m->b_in, n,
                                                              static_cast<__half *>(h));
@@ -347,6 +348,7 @@ extern "C" int gfx_aggregate(const gfx_model *m, int layer, const void *h, const
     return fail(GFX_ERR_ARGUMENT, "gfx_aggregate: bad model or layer");
   if (n <= 0) return GFX_OK;
   cudaStream_t st = as_stream(stream);
+  StageScope scope(GFX_STAGE_AGGREGATE, st, 1);
   const size_t toff = size_t(layer) * m->edge_dim * kHidden;
   if (dtype == GFX_F16)
     aggregate_kernel<__half><<<row_grid(n), 256, 0, st>>>(
@@ -369,6 +371,7 @@ extern "C" int gfx_mlp_ln_residual(const gfx_model *m, int layer, const void *z,
   if (n <= 0) return GFX_OK;
   cudaStream_t st = as_stream(stream);
   const int H = kHidden, M = kMlpHidden;
+  StageScope scope(GFX_STAGE_MLP, st, 1);
   if (impl == GFX_IMPL_AUTO) impl = dtype == GFX_F16 ? GFX_IMPL_UMMA : GFX_IMPL_SIMT;
   if (impl == GFX_IMPL_UMMA) {
     if (dtype != GFX_F16)
@@ -399,6 +402,7 @@ extern "C" int gfx_head_l2norm(const gfx_model *m, const void *h, const int32_t 
   if (out_dtype != GFX_F16 && out_dtype != GFX_F32)
     return fail(GFX_ERR_ARGUMENT, "gfx_head_l2norm: unknown out_dtype");
   cudaStream_t st = as_stream(stream);
+  StageScope scope(GFX_STAGE_HEAD, st, 1);
   if (impl == GFX_IMPL_AUTO) impl = dtype == GFX_F16 ? GFX_IMPL_UMMA : GFX_IMPL_SIMT;
   if (impl == GFX_IMPL_UMMA) {
     if (dtype != GFX_F16)

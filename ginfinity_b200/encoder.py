@@ -391,6 +391,24 @@ class Ginfinity:
             enc_ws_bytes, stream))
 
 
+def pin_shard(shard: GraphShard) -> GraphShard:
+    """Copy of `shard` whose numeric arrays live in page-locked host memory,
+    so `encode_graphs` can feed the device with asynchronous DMA copies."""
+    def pinned(a):
+        t = torch.empty(a.shape, dtype=torch.from_numpy(a[:0]).dtype, pin_memory=True)
+        view = t.numpy()
+        np.copyto(view, a)
+        return view
+
+    clone = object.__new__(GraphShard)          # already validated: skip re-validation
+    for name in ("identifiers", "sequences", "structures", "spec"):
+        object.__setattr__(clone, name, getattr(shard, name))
+    for name in ("node_features", "edge_index", "edge_types", "node_ptr",
+                 "edge_ptr", "residue_index", "node_roles"):
+        object.__setattr__(clone, name, pinned(getattr(shard, name)))
+    return clone
+
+
 def split_rows(table: np.ndarray, row_ptr: np.ndarray) -> list:
     """Per-record row-range views of the [total_core, 128] result
     (replaces the per-record mask loop of api.py:253-259)."""

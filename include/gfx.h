@@ -192,6 +192,29 @@ int gfx_topk_merge(const float *in_scores, const int64_t *in_index, int parts,
                    int64_t num_queries, int k, float *out_scores,
                    int64_t *out_index, void *stream);
 
+/* ------------------------------------------------------------------------
+ * Instrumentation (used by bench.py; no effect on results).
+ * Every kernel launch made by this library is counted per stage.  When a
+ * stage's bit is set in the profile mask, each call of that stage is
+ * bracketed by CUDA events on the launching stream; gfx_profile_read
+ * synchronises those events and returns the summed device time.
+ * ------------------------------------------------------------------------ */
+enum {
+  GFX_STAGE_PACK = 0,
+  GFX_STAGE_CSR = 1,
+  GFX_STAGE_CORE_ROWS = 2,
+  GFX_STAGE_INPUT = 3,
+  GFX_STAGE_AGGREGATE = 4,
+  GFX_STAGE_MLP = 5,
+  GFX_STAGE_HEAD = 6,
+  GFX_STAGE_FUSED_LAYER = 7,
+  GFX_STAGE_TOPK = 8,
+  GFX_NUM_STAGES = 9
+};
+int gfx_profile_enable(uint32_t stage_mask);
+int gfx_profile_read(int stage, double *total_ms, int64_t *timed_calls, int reset);
+int gfx_launch_counts(int64_t *counts /* [GFX_NUM_STAGES] */, int reset);
+
 #ifdef __cplusplus
 }
 #endif

@@ -142,3 +142,17 @@ def test_encode_shard_oracle_is_microbatch_invariant(synthetic_state, golden_sha
     assert len(a) == len(b) == golden_shard.record_count
     for u, v in zip(a, b):
         np.testing.assert_allclose(u, v, rtol=1e-5, atol=3e-7)   # reference tests/test_graph.py:85-98
+
+
+def test_cpu_port_matches_reference(real_state, golden_shard, golden_embeddings):
+    """The timed CPU baseline (oracle/cpu_port.py) reproduces the reference:
+    fp32 model to float rounding, fp16 model bit-for-bit in most rows (same
+    torch ops in the same order)."""
+    from oracle.cpu_port import CpuPort
+    got32 = np.concatenate(CpuPort(real_state, full_precision=True).encode_graphs(
+        golden_shard, embedding_dtype=np.float32))
+    assert np.abs(got32 - golden_embeddings["full/fp32_model_f32"]).max() <= 2e-6
+    got16 = np.concatenate(CpuPort(real_state).encode_graphs(golden_shard))
+    ref16 = golden_embeddings["full/fp16_model_f16"]
+    assert got16.dtype == np.float16
+    assert np.abs(got16.astype(np.float32) - ref16.astype(np.float32)).max() <= 1e-3

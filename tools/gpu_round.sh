@@ -1,0 +1,13 @@
+#!/bin/bash
+# One GPU session: smoke, tests, bench (both arms), ncu launch list + full capture of the top kernel.
+mkdir -p gpurun_out
+python -c "import __graft_entry__ as e; e.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log
+timeout 600 python -m pytest tests -m gpu -q -x 2>&1 | tail -15 > gpurun_out/pytest_gpu.log
+timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?" >> gpurun_out/bench.err
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
+NCU_CMD="python bench.py --steps 1 --warmup 1 --records 20000 --no-cpu-baseline"
+timeout 300 $NCU_CMD > gpurun_out/ncu_plain.log 2>&1 && \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches.csv $NCU_CMD > gpurun_out/ncu_launches.log 2>&1
+timeout 300 $NCU_CMD > gpurun_out/ncu_plain2.log 2>&1 && \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"umma_mlp|aggregate" -s 8 -c 4 -o gpurun_out/prof_top $NCU_CMD > gpurun_out/ncu_full.log 2>&1
+tail -3 gpurun_out/smoke.log; tail -3 gpurun_out/pytest_gpu.log; cat gpurun_out/bench.json | head -c 1500; tail -3 gpurun_out/bench.err; head -c 600 gpurun_out/bench_ref.json
