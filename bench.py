@@ -64,10 +64,10 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
-        self.index, self.rows, self._stop = index, [], threading.Event()
+        self.index, self.rows, self._halt = index, [], threading.Event()
 
     def run(self):
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 out = subprocess.run(
                     ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}",
@@ -77,10 +77,10 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._halt.wait(0.2)
 
     def finish(self) -> dict:
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=6)
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}

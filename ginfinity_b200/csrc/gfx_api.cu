@@ -185,6 +185,9 @@ extern "C" int gfx_model_create(const gfx_folded_weights *w, gfx_model **out) {
   append_umma_image(ia, w->wa_host, H, H);
   append_umma_image(ib, w->wb_host, H, H);
   size_t o_i1 = ab.put(i1), o_i2 = ab.put(i2), o_ia = ab.put(ia), o_ib = ab.put(ib);
+  std::vector<__half> t16(size_t(L) * ED * H);
+  for (size_t i = 0; i < t16.size(); ++i) t16[i] = __float2half_rn(w->table_host[i]);
+  size_t o_t16 = ab.put(t16);
 
   gfx_model *m = new gfx_model();
   m->hidden = H; m->layers = L; m->out_dim = w->out_dim; m->feature_dim = F; m->edge_dim = ED;
@@ -206,7 +209,7 @@ extern "C" int gfx_model_create(const gfx_folded_weights *w, gfx_model **out) {
   }
   m->b_in = f(o_b_in); m->b1 = f(o_b1); m->b2 = f(o_b2); m->ln_g = f(o_g); m->ln_b = f(o_b);
   m->ba = f(o_ba); m->bb = f(o_bb);
-  m->w1_img = h(o_i1); m->w2_img = h(o_i2); m->wa_img = h(o_ia); m->wb_img = h(o_ib);
+  m->w1_img = h(o_i1); m->w2_img = h(o_i2); m->wa_img = h(o_ia); m->wb_img = h(o_ib); m->table16 = h(o_t16);
   *out = m;
   return GFX_OK;
 }

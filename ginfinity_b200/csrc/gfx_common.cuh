@@ -81,4 +81,5 @@ struct gfx_model {
   const __half *w2_img;   // [L] x (4 kblocks x 128 rows x 64)   = 64 KB each
   const __half *wa_img;   //       (2 kblocks x 128 rows x 64)   = 32 KB
   const __half *wb_img;   //       (2 kblocks x 128 rows x 64)   = 32 KB
+  const __half *table16;  // [L][edge_dim][H] fp16 (fused layer kernel)
 };

@@ -263,7 +263,7 @@ static int launch_umma(const __half *a, const __half *res, const __half *w1, con
   return GFX_OK;
 }
 
-int umma_mlp_ln_residual(const gfx_model *m, int layer, const __half *z, const __half *h,
+int umma1_mlp_ln_residual(const gfx_model *m, int layer, const __half *z, const __half *h,
                          int64_t n, __half *h_out, cudaStream_t st) {
   const size_t wi = size_t(layer) * kMlpHidden * kHidden;
   return launch_umma<kMlpHidden, 0, __half>(
@@ -272,7 +272,7 @@ int umma_mlp_ln_residual(const gfx_model *m, int layer, const __half *z, const _
       m->ln_b + size_t(layer) * kHidden, nullptr, n, h_out, st);
 }
 
-int umma_head_l2norm(const gfx_model *m, const __half *h, const int32_t *out_row, int64_t n,
+int umma1_head_l2norm(const gfx_model *m, const __half *h, const int32_t *out_row, int64_t n,
                      void *out, int out_dtype, cudaStream_t st) {
   if (out_dtype == GFX_F16)
     return launch_umma<kHidden, 1, __half>(h, nullptr, m->wa_img, m->ba, m->wb_img, m->bb, nullptr,
@@ -283,7 +283,3 @@ int umma_head_l2norm(const gfx_model *m, const __half *h, const int32_t *out_row
 
 }  // namespace gfx
 
-extern "C" int gfx_layer_fused(const gfx_model *, int, const void *, const int32_t *,
-                               const int32_t *, const uint8_t *, int64_t, void *, void *) {
-  return gfx::fail(GFX_ERR_UNSUPPORTED, "gfx_layer_fused: not built yet");
-}

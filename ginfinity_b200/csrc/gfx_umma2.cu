@@ -1,0 +1,475 @@
+// K2 / K3 / fused layer on tcgen05: warp-specialised, software-pipelined.
+//
+//   K2     h_out = h + LayerNorm(W2 relu(W1' z + b1') + b2)          HID = 256
+//   K3     out   = l2norm(Wb relu(Wa h + ba) + bb)                   HID = 128
+//   FUSED  K1 + K2: z is produced by aggregation warps straight into the
+//          swizzled shared-memory A operand and never touches HBM
+//
+// One persistent CTA per SM.  Roles (warps):
+//   0-3   epilogue A   D1 (TMEM) -> bias + ReLU -> fp16 -> A2 (TMEM)
+//   4-7   epilogue B   D2 (TMEM) -> bias + LayerNorm + residual | L2 norm -> HBM
+//   8     MMA issuer   one thread issues every tcgen05.mma; also owns TMEM
+//                      allocation and the one-time weight fetch (TMA bulk copy)
+//   9..   producers    fill the A1 ring (2 stages x 128 rows x 128 fp16,
+//                      K-major, 128-byte swizzle): cp.async of z rows (K2/K3)
+//                      or CSR aggregation (FUSED)
+//
+// Tensor-pipe schedule per 128-node tile (H = HID/2):
+//     MMA1a  D1[:, :H]  = A1 * W1[:H]^T      | epilogue A on the previous half
+//     MMA1b  D1[:, H:]  = A1 * W1[H:]^T      | epilogue A on D1[:, :H]
+//     MMA2a  D2  = A2[:, :H] * W2[:, :H]^T   | epilogue A on D1[:, H:]
+//     MMA2b  D2 += A2[:, H:] * W2[:, H:]^T   | epilogue B on the previous tile
+// The hidden activation A2 is written to tensor memory and consumed from
+// there (tcgen05.mma with A in TMEM), so it costs neither shared-memory space
+// nor shared-memory bandwidth; TMEM columns: D1 [0,HID) A2 [256,256+HID/2)
+// D2 [384,512).
+#include "gfx_common.cuh"
+#include "gfx_umma.cuh"
+
+namespace gfx {
+
+using namespace ptx;
+
+namespace v2 {
+
+constexpr int kTileM = 128;
+constexpr int kTileBytes = kTileM * 128;      // one [128 x 64] fp16 K-block tile (16 KB)
+constexpr int kA1Bytes = 2 * kTileBytes;      // [128 x 128] fp16
+constexpr int kStages = 2;
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kA2Col = 256, kD2Col = 384;
+constexpr int kEpiAWarp0 = 0, kEpiBWarp0 = 4, kMmaWarp = 8, kProdWarp0 = 9;
+
+enum Bar {
+  kBarW = 0, kBarA1Full = 1, kBarA1Empty = 3, kBarD1aFull = 5, kBarD1bFull = 6,
+  kBarA2aFull = 7, kBarA2bFull = 8, kBarD2Full = 9, kBarD2Empty = 10,
+  kBarHsFull = 11, kBarHsEmpty = 13, kNumBars = 15
+};
+
+template <int HID, bool FUSED>
+struct Smem {
+  static constexpr int w1_bytes = HID * kHidden * 2;
+  static constexpr int w2_bytes = kHidden * HID * 2;
+  static constexpr int off_w1 = 0;
+  static constexpr int off_w2 = off_w1 + w1_bytes;
+  static constexpr int off_a1 = off_w2 + w2_bytes;                 // kStages x 32 KB
+  static constexpr int off_hs = off_a1 + kStages * kA1Bytes;       // FUSED: 2 x 64 rows of h
+  static constexpr int off_b1 = off_hs + (FUSED ? kA1Bytes : 0);   // float[HID]
+  static constexpr int off_vec = off_b1 + HID * 4;                 // float[3][128]
+  static constexpr int off_bar = off_vec + 3 * kHidden * 4;
+  static constexpr int off_tmem = off_bar + kNumBars * 8;
+  static constexpr int total = off_tmem + 8;
+};
+
+struct Args {
+  const __half *a_in;     // K2/K3: the GEMM-1 input rows; FUSED: h (aggregation input)
+  const __half *res;      // residual rows (MODE 0)
+  const __half *w1_img, *w2_img;
+  const float *b1, *b2, *ln_g, *ln_b;
+  const int32_t *out_row;
+  int64_t n;
+  void *out;
+  // FUSED only
+  const int32_t *row_ptr, *col_src;
+  const uint8_t *col_type;
+  const __half *table16;  // [edge_dim][128]
+  float eps1;
+};
+
+__device__ __forceinline__ uint32_t a_chunk_offset(int r, int c16) {
+  return uint32_t(c16 >> 3) * kTileBytes + uint32_t(r) * 128 + uint32_t(((c16 & 7) ^ (r & 7)) << 4);
+}
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t *>(&h);
+}
+
+__device__ __forceinline__ uint4 pack8(const float *v) {
+  return make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+}
+
+__device__ __forceinline__ void unpack8(const uint4 &raw, float *f) {
+  const __half2 *h = reinterpret_cast<const __half2 *>(&raw);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __half22float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// FUSED producer: one half-warp per destination node, lane l owns channels
+// [8l, 8l+8).  In-tile neighbours (87 % of edges are within +-2 rows) are read
+// from the shared-memory copy of the current 64-row block of h; the others
+// come from global memory.  z = eps1*h_i + sum relu(h_src + table[type]) is
+// written as fp16 into the swizzled A1 stage.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void aggregate_block(const Args &p, const uint8_t *hs, int64_t blk_row0,
+                                                uint8_t *a1, int a1_row0, int hw, int n_hw,
+                                                int sub) {
+  for (int r = hw; r < 64; r += n_hw) {
+    const int64_t i = blk_row0 + r;
+    float acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+    float self[8];
+    if (i < p.n) {
+      unpack8(*reinterpret_cast<const uint4 *>(hs + r * 256 + sub * 16), self);
+      const int beg = p.row_ptr[i], end = p.row_ptr[i + 1];
+      for (int e = beg; e < end; ++e) {
+        const int64_t s = p.col_src[e];
+        const int t = p.col_type[e];
+        const int64_t local = s - blk_row0;
+        uint4 raw;
+        if (local >= 0 && local < 64)
+          raw = *reinterpret_cast<const uint4 *>(hs + local * 256 + sub * 16);
+        else
+          raw = __ldg(reinterpret_cast<const uint4 *>(p.a_in + s * kHidden + sub * 8));
+        const uint4 traw = __ldg(reinterpret_cast<const uint4 *>(p.table16 + t * kHidden + sub * 8));
+        float nb[8], tb[8];
+        unpack8(raw, nb);
+        unpack8(traw, tb);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[c] += fmaxf(nb[c] + tb[c], 0.f);
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[c] = fmaf(p.eps1, self[c], acc[c]);
+    }
+    *reinterpret_cast<uint4 *>(a1 + a_chunk_offset(a1_row0 + r, sub)) = pack8(acc);
+  }
+}
+
+template <int HID, int MODE, typename TOut, int NPROD, bool FUSED>
+__global__ void __launch_bounds__((kProdWarp0 + NPROD) * 32, 1)
+umma2_kernel(const Args p) {
+  using L = Smem<HID, FUSED>;
+  constexpr int H = HID / 2;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t *w1s = smem + L::off_w1, *w2s = smem + L::off_w2, *a1s = smem + L::off_a1;
+  uint8_t *hss = smem + L::off_hs;
+  float *b1s = reinterpret_cast<float *>(smem + L::off_b1);
+  float *b2s = reinterpret_cast<float *>(smem + L::off_vec);
+  float *gs = b2s + kHidden, *bs = gs + kHidden;
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smem + L::off_bar);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::off_tmem);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (warp == kMmaWarp) {
+    tmem_alloc(tmem_slot, kTmemCols);
+  } else if (tid == 0) {
+    mbar_init(bar + kBarW, 1);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(bar + kBarA1Full + s, NPROD);
+      mbar_init(bar + kBarA1Empty + s, 1);
+      mbar_init(bar + kBarHsFull + s, 1);
+      mbar_init(bar + kBarHsEmpty + s, NPROD);
+    }
+    mbar_init(bar + kBarD1aFull, 1);
+    mbar_init(bar + kBarD1bFull, 1);
+    mbar_init(bar + kBarA2aFull, 4);
+    mbar_init(bar + kBarA2bFull, 4);
+    mbar_init(bar + kBarD2Full, 1);
+    mbar_init(bar + kBarD2Empty, 4);
+    fence_mbar_init();
+  }
+  for (int i = tid; i < HID; i += blockDim.x) b1s[i] = p.b1[i];
+  for (int i = tid; i < kHidden; i += blockDim.x) {
+    b2s[i] = p.b2[i];
+    if (MODE == 0) {
+      gs[i] = p.ln_g[i];
+      bs[i] = p.ln_b[i];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int64_t tiles = (p.n + kTileM - 1) / kTileM;
+
+  if (warp == kMmaWarp) {
+    // ======================= MMA issuer (one thread) ==========================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar + kBarW, L::w1_bytes + L::w2_bytes);
+      for (int off = 0; off < L::w1_bytes; off += 16384)
+        bulk_g2s(w1s + off, reinterpret_cast<const uint8_t *>(p.w1_img) + off, 16384, bar + kBarW);
+      for (int off = 0; off < L::w2_bytes; off += 16384)
+        bulk_g2s(w2s + off, reinterpret_cast<const uint8_t *>(p.w2_img) + off, 16384, bar + kBarW);
+      mbar_wait(bar + kBarW, 0);
+      constexpr uint32_t idesc1 = idesc_f16(kTileM, H);
+      constexpr uint32_t idesc2 = idesc_f16(kTileM, kHidden);
+      const uint32_t w1a = smem_u32(w1s), w2a = smem_u32(w2s);
+      uint32_t it = 0;
+      for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+        const uint32_t s = it & 1, ph2 = (it >> 1) & 1, ph = it & 1;
+        const uint32_t a1a = smem_u32(a1s) + s * kA1Bytes;
+        mbar_wait(bar + kBarA1Full + s, ph2);
+        tc_fence_after();
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            const int kb = kk >> 2, k = kk & 3;
+            const uint64_t da = smem_desc_sw128(a1a + kb * kTileBytes + k * 32);
+            const uint64_t db = smem_desc_sw128(w1a + kb * (HID * 128) + half * (H * 128) + k * 32);
+            mma_f16_ss(tmem + half * H, da, db, idesc1, kk != 0);
+          }
+          mma_commit(bar + (half ? kBarD1bFull : kBarD1aFull));
+        }
+        mma_commit(bar + kBarA1Empty + s);     // both halves have consumed this A1 stage
+        // GEMM-2, first K half: needs A2[:, :H] (epilogue A) and a drained D2
+        mbar_wait(bar + kBarA2aFull, ph);
+        mbar_wait(bar + kBarD2Empty, ph ^ 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < HID / 16; ++kk) {
+          if (kk == H / 16) {
+            mbar_wait(bar + kBarA2bFull, ph);
+            tc_fence_after();
+          }
+          const uint64_t db = smem_desc_sw128(w2a + (kk >> 2) * kTileBytes + (kk & 3) * 32);
+          mma_f16_ts(tmem + kD2Col, tmem + kA2Col + kk * 8, db, idesc2, kk != 0);
+        }
+        mma_commit(bar + kBarD2Full);
+      }
+    }
+    __syncwarp();
+  } else if (warp < kEpiBWarp0) {
+    // ================= epilogue A: D1 -> relu -> fp16 -> A2 (TMEM) ===============
+    const uint32_t trow = tmem + (uint32_t(warp * 32) << 16);
+    uint32_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+      const uint32_t ph = it & 1;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        mbar_wait(bar + (half ? kBarD1bFull : kBarD1aFull), ph);
+        tc_fence_after();
+#pragma unroll
+        for (int cb = 0; cb < H / 32; ++cb) {
+          const int col = half * H + cb * 32;
+          float v[32];
+          tmem_ld32(trow + col, v);
+          tmem_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            pk[j] = pack2(fmaxf(v[2 * j] + b1s[col + 2 * j], 0.f),
+                          fmaxf(v[2 * j + 1] + b1s[col + 2 * j + 1], 0.f));
+          tmem_st16(trow + kA2Col + col / 2, pk);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar + (half ? kBarA2bFull : kBarA2aFull));
+      }
+    }
+  } else if (warp < kMmaWarp) {
+    // ============ epilogue B: D2 -> LayerNorm + residual | L2 norm -> HBM ==========
+    const int wq = warp - kEpiBWarp0;
+    const uint32_t trow = tmem + (uint32_t(wq * 32) << 16) + kD2Col;
+    uint32_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+      const int64_t row = tile * kTileM + wq * 32 + lane;
+      mbar_wait(bar + kBarD2Full, it & 1);
+      tc_fence_after();
+      // pass 1: statistics.  Shifting by the first element keeps the one-pass
+      // variance free of cancellation.
+      float shift = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int cb = 0; cb < 4; ++cb) {
+        float v[32];
+        tmem_ld32(trow + cb * 32, v);
+        tmem_ld_wait();
+        if (cb == 0) shift = MODE == 0 ? v[0] + b2s[0] : 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float d = v[j] + b2s[cb * 32 + j] - shift;
+          s1 += d;
+          s2 = fmaf(d, d, s2);
+        }
+      }
+      float mul, sub;   // out = (x - sub) * mul [* g + b]
+      if (MODE == 0) {
+        const float m = s1 * (1.f / kHidden);
+        const float var = fmaxf(s2 * (1.f / kHidden) - m * m, 0.f);
+        mul = rsqrtf(var + 1e-5f);
+        sub = shift + m;
+      } else {
+        mul = 1.f / fmaxf(sqrtf(s2), 1e-12f);
+        sub = 0.f;
+      }
+      const bool live = row < p.n;
+      int64_t orow = row;
+      if (MODE == 1 && live && p.out_row) orow = p.out_row[row];
+      const bool store = live && orow >= 0;
+      // pass 2: normalise and store
+#pragma unroll
+      for (int cb = 0; cb < 4; ++cb) {
+        float v[32];
+        tmem_ld32(trow + cb * 32, v);
+        tmem_ld_wait();
+        if (cb == 3) {              // D2 fully read: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar + kBarD2Empty);
+        }
+        if (!store) continue;
+        if (MODE == 0) {
+          const uint4 *rp = reinterpret_cast<const uint4 *>(p.res + row * kHidden + cb * 32);
+          uint4 *op = reinterpret_cast<uint4 *>(static_cast<__half *>(p.out) + row * kHidden + cb * 32);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float r8[8], o[8];
+            unpack8(rp[g], r8);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int c = cb * 32 + g * 8 + j;
+              o[j] = r8[j] + ((v[g * 8 + j] + b2s[c] - sub) * mul * gs[c] + bs[c]);
+            }
+            op[g] = pack8(o);
+          }
+        } else if (sizeof(TOut) == 2) {
+          uint4 *op = reinterpret_cast<uint4 *>(static_cast<__half *>(p.out) + orow * kHidden + cb * 32);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = (v[g * 8 + j] + b2s[cb * 32 + g * 8 + j]) * mul;
+            op[g] = pack8(o);
+          }
+        } else {
+          float4 *op = reinterpret_cast<float4 *>(static_cast<float *>(p.out) + orow * kHidden + cb * 32);
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const int c = cb * 32 + g * 4;
+            op[g] = make_float4((v[g * 4] + b2s[c]) * mul, (v[g * 4 + 1] + b2s[c + 1]) * mul,
+                                (v[g * 4 + 2] + b2s[c + 2]) * mul, (v[g * 4 + 3] + b2s[c + 3]) * mul);
+          }
+        }
+      }
+    }
+  } else {
+    // ================================ producers ===================================
+    const int pw = warp - kProdWarp0;
+    const int ptid = pw * 32 + lane;
+    uint32_t it = 0;
+    if (!FUSED) {
+      for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+        const uint32_t s = it & 1, ph2 = (it >> 1) & 1;
+        const int64_t row0 = tile * kTileM;
+        uint8_t *a1 = a1s + s * kA1Bytes;
+        mbar_wait(bar + kBarA1Empty + s, ph2 ^ 1);
+        for (int q = ptid; q < kTileM * 16; q += NPROD * 32) {
+          const int r = q >> 4, c16 = q & 15;
+          const bool ok = row0 + r < p.n;
+          const __half *src = p.a_in + (ok ? (row0 + r) : 0) * kHidden + c16 * 8;
+          cp_async16(a1 + a_chunk_offset(r, c16), src, ok ? 16u : 0u);
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar + kBarA1Full + s);
+      }
+    } else {
+      // 64-row blocks of h are double-buffered in shared memory (TMA bulk copy
+      // issued one block ahead by producer thread 0); two blocks make one tile.
+      const int hw = ptid >> 4, n_hw = NPROD * 2, sub = ptid & 15;
+      const int64_t my_tiles = tiles > blockIdx.x ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+      const int64_t blocks = my_tiles * 2;
+      auto block_row0 = [&](int64_t b) {
+        return (int64_t(blockIdx.x) + (b >> 1) * gridDim.x) * kTileM + (b & 1) * 64;
+      };
+      auto issue_load = [&](int64_t b) {
+        const int hb = b & 1;
+        const int64_t r0 = block_row0(b);
+        int64_t rows = p.n - r0;
+        rows = rows > 64 ? 64 : (rows < 0 ? 0 : rows);
+        mbar_wait(bar + kBarHsEmpty + hb, ((b >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(bar + kBarHsFull + hb, uint32_t(rows * 256));
+        if (rows > 0)
+          bulk_g2s(hss + hb * (64 * 256), p.a_in + r0 * kHidden, uint32_t(rows * 256),
+                   bar + kBarHsFull + hb);
+      };
+      if (ptid == 0 && blocks > 0) issue_load(0);
+      for (int64_t b = 0; b < blocks; ++b) {
+        const int hb = b & 1;
+        const uint32_t s = (b >> 1) & 1, ph2 = (b >> 2) & 1;
+        if (ptid == 0 && b + 1 < blocks) issue_load(b + 1);
+        if ((b & 1) == 0) mbar_wait(bar + kBarA1Empty + s, ph2 ^ 1);
+        mbar_wait(bar + kBarHsFull + hb, (b >> 1) & 1);
+        aggregate_block(p, hss + hb * (64 * 256), block_row0(b), a1s + s * kA1Bytes, (b & 1) * 64,
+                        hw, n_hw, sub);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar + kBarHsEmpty + hb);
+        if (b & 1) {
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar + kBarA1Full + s);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) tmem_dealloc(tmem, kTmemCols);
+}
+
+template <int HID, int MODE, typename TOut, int NPROD, bool FUSED>
+static int launch(const Args &args, cudaStream_t st) {
+  auto kern = umma2_kernel<HID, MODE, TOut, NPROD, FUSED>;
+  constexpr int smem = Smem<HID, FUSED>::total;
+  static_assert(smem <= 232448, "exceeds the 227 KB shared-memory limit of sm_100");
+  GFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int64_t tiles = (args.n + kTileM - 1) / kTileM;
+  const int grid = int(tiles < kNumSMs ? tiles : kNumSMs);
+  kern<<<grid, (kProdWarp0 + NPROD) * 32, smem, st>>>(args);
+  GFX_LAUNCH_CHECK();
+  return GFX_OK;
+}
+
+}  // namespace v2
+
+int umma_mlp_ln_residual(const gfx_model *m, int layer, const __half *z, const __half *h,
+                         int64_t n, __half *h_out, cudaStream_t st) {
+  const size_t wi = size_t(layer) * kMlpHidden * kHidden;
+  v2::Args a{};
+  a.a_in = z; a.res = h; a.w1_img = m->w1_img + wi; a.w2_img = m->w2_img + wi;
+  a.b1 = m->b1 + size_t(layer) * kMlpHidden; a.b2 = m->b2 + size_t(layer) * kHidden;
+  a.ln_g = m->ln_g + size_t(layer) * kHidden; a.ln_b = m->ln_b + size_t(layer) * kHidden;
+  a.n = n; a.out = h_out;
+  return v2::launch<kMlpHidden, 0, __half, 4, false>(a, st);
+}
+
+int umma_head_l2norm(const gfx_model *m, const __half *h, const int32_t *out_row, int64_t n,
+                     void *out, int out_dtype, cudaStream_t st) {
+  v2::Args a{};
+  a.a_in = h; a.w1_img = m->wa_img; a.w2_img = m->wb_img; a.b1 = m->ba; a.b2 = m->bb;
+  a.out_row = out_row; a.n = n; a.out = out;
+  if (out_dtype == GFX_F16) return v2::launch<kHidden, 1, __half, 4, false>(a, st);
+  return v2::launch<kHidden, 1, float, 4, false>(a, st);
+}
+
+}  // namespace gfx
+
+extern "C" int gfx_layer_fused(const gfx_model *m, int layer, const void *h,
+                               const int32_t *row_ptr, const int32_t *col_src,
+                               const uint8_t *col_type, int64_t n, void *h_out, void *stream) {
+  using namespace gfx;
+  if (!m || layer < 0 || layer >= m->layers)
+    return fail(GFX_ERR_ARGUMENT, "gfx_layer_fused: bad model or layer");
+  if (n <= 0) return GFX_OK;
+  cudaStream_t st = as_stream(stream);
+  StageScope scope(GFX_STAGE_FUSED_LAYER, st, 1);
+  const size_t wi = size_t(layer) * kMlpHidden * kHidden;
+  v2::Args a{};
+  a.a_in = static_cast<const __half *>(h); a.res = a.a_in;
+  a.w1_img = m->w1_img + wi; a.w2_img = m->w2_img + wi;
+  a.b1 = m->b1 + size_t(layer) * kMlpHidden; a.b2 = m->b2 + size_t(layer) * kHidden;
+  a.ln_g = m->ln_g + size_t(layer) * kHidden; a.ln_b = m->ln_b + size_t(layer) * kHidden;
+  a.n = n; a.out = h_out;
+  a.row_ptr = row_ptr; a.col_src = col_src; a.col_type = col_type;
+  a.table16 = m->table16 + size_t(layer) * m->edge_dim * kHidden; a.eps1 = m->eps1[layer];
+  return v2::launch<kMlpHidden, 0, __half, 10, true>(a, st);
+}

@@ -1,0 +1,56 @@
+#!/usr/bin/env python
+"""Summarise ncu output for profiles/: launch list (CSV from --metrics
+gpu__time_duration.sum) -> per-kernel share table; .ncu-rep (--set full) ->
+selected raw metrics per captured launch."""
+import collections
+import csv
+import subprocess
+import sys
+
+KEEP = ("gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_tensor", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum",
+        "sm__cycles_active.avg", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+        "smsp__warp_issue_stalled", "sm__inst_executed.avg.per_cycle_active")
+
+
+def launches(path):
+    rows = list(csv.reader(open(path)))
+    hi = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
+    hdr = rows[hi]
+    ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for r in rows[hi + 1:]:
+        if len(r) <= vi:
+            continue
+        v = float(r[vi].replace(",", ""))
+        v = v / 1e3 if r[ui] == "ns" else (v * 1e3 if r[ui] == "ms" else v)
+        name = r[ki].split("(")[0]
+        agg[name][0] += 1
+        agg[name][1] += v
+    total = sum(v[1] for v in agg.values())
+    print(f"# {path}: {sum(v[0] for v in agg.values())} launches, {total:.1f} us (cold-cache, serialised)")
+    print(f"{'total_us':>12} {'share':>7} {'launches':>8}  kernel")
+    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f"{v[1]:12.1f} {100 * v[1] / total:6.1f}% {v[0]:8d}  {k}")
+
+
+def full(path):
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True,
+                         text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    cols = [i for i, h in enumerate(hdr) if h == "Kernel Name" or any(h.startswith(k) for k in KEEP)]
+    print(f"# {path}: ncu --set full, selected raw metrics per captured launch")
+    for r in rows[2:]:
+        print("----")
+        for i in cols:
+            print(f"  {hdr[i]} [{units[i]}] = {r[i][:110]}")
+
+
+if __name__ == "__main__":
+    (launches if sys.argv[1].endswith(".csv") else full)(sys.argv[1])
