@@ -322,6 +322,8 @@ int umma1_mlp_ln_residual(const gfx_model *m, int layer, const __half *z, const 
                           int64_t n, __half *h_out, cudaStream_t st);
 int umma1_head_l2norm(const gfx_model *m, const __half *h, const int32_t *out_row, int64_t n,
                       void *out, int out_dtype, cudaStream_t st);
+int umma3_mlp_ln_residual(const gfx_model *m, int layer, const __half *z, const __half *h,
+                          int64_t n, __half *h_out, cudaStream_t st);
 
 }  // namespace gfx
 
@@ -376,12 +378,15 @@ extern "C" int gfx_mlp_ln_residual(const gfx_model *m, int layer, const void *z,
   cudaStream_t st = as_stream(stream);
   const int H = kHidden, M = kMlpHidden;
   StageScope scope(GFX_STAGE_MLP, st, 1);
-  if (impl == GFX_IMPL_AUTO) impl = dtype == GFX_F16 ? GFX_IMPL_UMMA : GFX_IMPL_SIMT;
-  if (impl == GFX_IMPL_UMMA || impl == GFX_IMPL_UMMA_SERIAL) {
+  if (impl == GFX_IMPL_AUTO) impl = dtype == GFX_F16 ? GFX_IMPL_UMMA_TMA : GFX_IMPL_SIMT;
+  if (impl == GFX_IMPL_UMMA || impl == GFX_IMPL_UMMA_SERIAL || impl == GFX_IMPL_UMMA_TMA) {
     if (dtype != GFX_F16)
       return fail(GFX_ERR_UNSUPPORTED, "tcgen05 MLP exists for GFX_F16 only");
-    return (impl == GFX_IMPL_UMMA ? umma_mlp_ln_residual : umma1_mlp_ln_residual)(m, layer, static_cast<const __half *>(z),
-                                static_cast<const __half *>(h), n, static_cast<__half *>(h_out), st);
+    auto fn = impl == GFX_IMPL_UMMA_TMA ? umma3_mlp_ln_residual
+              : impl == GFX_IMPL_UMMA   ? umma_mlp_ln_residual
+                                        : umma1_mlp_ln_residual;
+    return fn(m, layer, static_cast<const __half *>(z), static_cast<const __half *>(h), n,
+              static_cast<__half *>(h_out), st);
   }
   const int q = dtype == GFX_F16 ? 1 : 0;
   const float *w1t = m->w1t[q] + size_t(layer) * H * M, *b1 = m->b1 + size_t(layer) * M;
@@ -408,10 +413,12 @@ extern "C" int gfx_head_l2norm(const gfx_model *m, const void *h, const int32_t 
   cudaStream_t st = as_stream(stream);
   StageScope scope(GFX_STAGE_HEAD, st, 1);
   if (impl == GFX_IMPL_AUTO) impl = dtype == GFX_F16 ? GFX_IMPL_UMMA : GFX_IMPL_SIMT;
+  if (impl == GFX_IMPL_UMMA_TMA) impl = GFX_IMPL_UMMA;      // the head has no TMA-I/O variant yet
   if (impl == GFX_IMPL_UMMA || impl == GFX_IMPL_UMMA_SERIAL) {
     if (dtype != GFX_F16)
       return fail(GFX_ERR_UNSUPPORTED, "tcgen05 head exists for GFX_F16 only");
-    return (impl == GFX_IMPL_UMMA ? umma_head_l2norm : umma1_head_l2norm)(m, static_cast<const __half *>(h), out_row, n, out, out_dtype, st);
+    return (impl == GFX_IMPL_UMMA ? umma_head_l2norm : umma1_head_l2norm)(
+        m, static_cast<const __half *>(h), out_row, n, out, out_dtype, st);
   }
   const int q = dtype == GFX_F16 ? 1 : 0;
   if (dtype == GFX_F16 && out_dtype == GFX_F16)

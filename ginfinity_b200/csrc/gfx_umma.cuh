@@ -65,6 +65,31 @@ __device__ __forceinline__ void bulk_wait_read_all() {
 }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// 2-D tiled TMA (tensor map in kernel parameter space; SASS: UTMALDG / UTMASTG).
+// Coordinates are {innermost (column), row}; rows outside the tensor are
+// zero-filled on load and clipped on store.
+__device__ __forceinline__ void tma_load_2d(void *dst_smem, const void *tmap, int x, int y,
+                                            uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst_smem)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const void *tmap, int x, int y, const void *src_smem) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tmap)),
+               "r"(smem_u32(src_smem)), "r"(x), "r"(y)
+               : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const void *tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
+}
+
 // 16-byte cp.async (SASS: LDGSTS); src_bytes == 0 zero-fills the destination.
 __device__ __forceinline__ void cp_async16(void *dst_smem, const void *src_gmem, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)),

@@ -290,20 +290,163 @@ class Ginfinity:
         dtype = self._check_request(shard.spec, int(counts.max()),
                                     int(ecounts.max()), max_batch_nodes,
                                     max_batch_edges, embedding_dtype)
+        out_code = nat.GFX_F16 if dtype == np.float16 else nat.GFX_F32
         with torch.cuda.device(self._torch_device), torch.inference_mode():
-            dshard = DeviceShard.from_shard(shard, self._torch_device)
-            out_code = nat.GFX_F16 if dtype == np.float16 else nat.GFX_F32
-            out = self.encode_device_shard(
-                dshard, max_batch_nodes=max_batch_nodes,
-                max_batch_edges=max_batch_edges, out_dtype=out_code,
-                _checked=True)
-            host = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
-            host.copy_(out, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-        table = host.numpy()
+            table, core_ptr = self._encode_streaming(
+                shard, int(max_batch_nodes), int(max_batch_edges), out_code)
         if table.dtype != dtype:
             table = table.astype(dtype)
-        return split_rows(table, dshard.core_ptr_host)
+        return split_rows(table, core_ptr)
+
+    # -- host shard -> host embeddings, copies overlapped with compute -----------
+    def _plan(self, node_ptr_d, edge_ptr_d, B, max_batch_nodes, max_batch_edges,
+              stream) -> np.ndarray:
+        """K4 on the device, then one small read-back: rows of (record stop,
+        node offset, edge offset) per microbatch boundary."""
+        dev = self._torch_device
+        next_stop = torch.empty(B, dtype=torch.int64, device=dev)
+        bounds = torch.empty(B + 2, dtype=torch.int64, device=dev)
+        nat.check(nat.lib.gfx_pack_microbatches(
+            node_ptr_d.data_ptr(), edge_ptr_d.data_ptr(), B, max_batch_nodes,
+            max_batch_edges, next_stop.data_ptr(), bounds.data_ptr(),
+            bounds[B + 1:].data_ptr(), stream))
+        stops = bounds[:B + 1].clamp_(0, B)     # the tail past n_bounds is unset
+        packed = torch.stack((stops, node_ptr_d[stops], edge_ptr_d[stops]))
+        count = int(bounds[B + 1].item())
+        plan = packed[:, :count].cpu().numpy()
+        self.last_microbatch_bounds = plan[0].copy()
+        return plan
+
+    def _chunks(self, plan: np.ndarray) -> list:
+        """Group consecutive microbatches into device chunks of at most
+        `chunk_nodes` nodes (always at least one microbatch)."""
+        node_at, count = plan[1], plan.shape[1]
+        out, start = [], 0
+        while start < count - 1:
+            stop = start + 1
+            while (stop < count - 1 and
+                   node_at[stop + 1] - node_at[start] <= self.chunk_nodes):
+                stop += 1
+            out.append((start, stop))
+            start = stop
+        return out
+
+    def _encode_streaming(self, shard: GraphShard, max_batch_nodes: int,
+                          max_batch_edges: int, out_code: int):
+        """Three-stream pipeline over chunks: while chunk c runs on the compute
+        stream, chunk c+1's arrays are copied in and chunk c-1's embeddings
+        are copied out into one pinned [core_count, 128] table."""
+        dev = self._torch_device
+        lib = nat.lib
+        B, N = shard.record_count, shard.node_count
+        act = nat.GFX_F32 if self.full_precision else nat.GFX_F16
+        tdtype = torch.float16 if out_code == nat.GFX_F16 else torch.float32
+        esize = 2 if out_code == nat.GFX_F16 else 4
+        all_core = shard.all_core
+        if all_core:
+            core_ptr = shard.node_ptr
+        else:
+            core_ptr = np.zeros(B + 1, np.int64)
+            np.cumsum(shard.core_count_array(), out=core_ptr[1:])
+        host = torch.empty((int(core_ptr[-1]), 128), dtype=tdtype, pin_memory=True)
+
+        main = torch.cuda.current_stream()
+        if not hasattr(self, "_streams"):
+            self._streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+        s_in, s_out = self._streams
+        as_t = lambda a: torch.from_numpy(a)  # noqa: E731  (zero-copy view)
+        node_ptr_d = as_t(shard.node_ptr).to(dev, non_blocking=True)
+        edge_ptr_d = as_t(shard.edge_ptr).to(dev, non_blocking=True)
+        plan = self._plan(node_ptr_d, edge_ptr_d, B, max_batch_nodes,
+                          max_batch_edges, main.cuda_stream)
+        chunks = self._chunks(plan)
+        rec_at, node_at, edge_at = plan[0], plan[1], plan[2]
+        out_row = None
+        if not all_core:
+            roles_d = as_t(shard.node_roles).to(dev, non_blocking=True)
+            out_row = torch.empty(N, dtype=torch.int32, device=dev)
+            n_core = torch.empty(1, dtype=torch.int64, device=dev)
+            need = lib.gfx_core_rows_workspace_bytes(N)
+            ws = self._scratch.get("core", need)
+            nat.check(lib.gfx_core_rows(roles_d.data_ptr(), N, out_row.data_ptr(),
+                                        n_core.data_ptr(), ws.data_ptr(), need,
+                                        main.cuda_stream))
+        max_n = max(int(node_at[b] - node_at[a]) for a, b in chunks)
+        max_e = max(int(edge_at[b] - edge_at[a]) for a, b in chunks)
+        feats = as_t(shard.node_features)
+        eidx = as_t(shard.edge_index)
+        etyp = as_t(shard.edge_types)
+        slots = []
+        for k in range(2):
+            slots.append(dict(
+                x=self._scratch.get(f"in_x{k}", 28 * max_n).view(torch.float32),
+                src=self._scratch.get(f"in_src{k}", 4 * max(max_e, 1)).view(torch.int32),
+                dst=self._scratch.get(f"in_dst{k}", 4 * max(max_e, 1)).view(torch.int32),
+                typ=self._scratch.get(f"in_typ{k}", max(max_e, 1)),
+                out=self._scratch.get(f"out{k}", 128 * esize * max_n),
+                in_ready=torch.cuda.Event(), in_free=torch.cuda.Event(),
+                out_ready=torch.cuda.Event(), out_free=torch.cuda.Event()))
+        row_ptr = self._scratch.get("row_ptr", 4 * (max_n + 1))
+        col_src = self._scratch.get("col_src", 4 * max(max_e, 1))
+        col_type = self._scratch.get("col_type", max(max_e, 1))
+        csr_ws_bytes = lib.gfx_csr_workspace_bytes(max_n, max_e)
+        enc_ws_bytes = lib.gfx_encode_workspace_bytes(max_n, act)
+        csr_ws = self._scratch.get("csr_ws", csr_ws_bytes)
+        enc_ws = self._scratch.get("enc_ws", enc_ws_bytes)
+        s_in.wait_stream(main)
+        s_out.wait_stream(main)
+
+        def copy_in(c):
+            a, b = chunks[c]
+            slot = slots[c & 1]
+            n0, n1 = int(node_at[a]), int(node_at[b])
+            e0, e1 = int(edge_at[a]), int(edge_at[b])
+            with torch.cuda.stream(s_in):
+                if c >= 2:
+                    s_in.wait_event(slot["in_free"])
+                slot["x"][:7 * (n1 - n0)].copy_(feats[n0:n1].reshape(-1), non_blocking=True)
+                if e1 > e0:
+                    slot["src"][:e1 - e0].copy_(eidx[0, e0:e1], non_blocking=True)
+                    slot["dst"][:e1 - e0].copy_(eidx[1, e0:e1], non_blocking=True)
+                    slot["typ"][:e1 - e0].copy_(etyp[e0:e1], non_blocking=True)
+                slot["in_ready"].record(s_in)
+
+        copy_in(0)
+        for c, (a, b) in enumerate(chunks):
+            slot = slots[c & 1]
+            if c + 1 < len(chunks):
+                copy_in(c + 1)
+            n0, n1 = int(node_at[a]), int(node_at[b])
+            e0, e1 = int(edge_at[a]), int(edge_at[b])
+            n, e = n1 - n0, e1 - e0
+            c0, c1 = int(core_ptr[rec_at[a]]), int(core_ptr[rec_at[b]])
+            main.wait_event(slot["in_ready"])
+            if c >= 2:
+                main.wait_event(slot["out_free"])
+            nat.check(lib.gfx_csr_build(
+                slot["src"].data_ptr(), slot["dst"].data_ptr(), slot["typ"].data_ptr(),
+                n, e, n0, row_ptr.data_ptr(), col_src.data_ptr(), col_type.data_ptr(),
+                csr_ws.data_ptr(), csr_ws_bytes, main.cuda_stream))
+            # ranks in out_row are shard-global: bias the base so rank c0 lands on row 0
+            out_base = slot["out"].data_ptr() - (0 if out_row is None else c0 * 128 * esize)
+            nat.check(lib.gfx_encode(
+                self._handle, slot["x"].data_ptr(), row_ptr.data_ptr(),
+                col_src.data_ptr(), col_type.data_ptr(),
+                None if out_row is None else out_row[n0:].data_ptr(), n, out_base,
+                act, out_code, self.impl, 1 if self.fused else 0, enc_ws.data_ptr(),
+                enc_ws_bytes, main.cuda_stream))
+            slot["in_free"].record(main)
+            slot["out_ready"].record(main)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(slot["out_ready"])
+                rows = c1 - c0
+                if rows:
+                    src = slot["out"][:rows * 128 * esize].view(tdtype).view(rows, 128)
+                    host[c0:c1].copy_(src, non_blocking=True)
+                slot["out_free"].record(s_out)
+        main.wait_stream(s_out)
+        main.synchronize()
+        return host.numpy(), core_ptr
 
     def encode_device_shard(self, ds: DeviceShard, *, max_batch_nodes=60_000,
                             max_batch_edges=300_000, out_dtype=nat.GFX_F16,

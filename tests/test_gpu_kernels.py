@@ -237,9 +237,9 @@ def test_aggregate_layer0(nat, dev, problem, code):
     assert torch.equal(z, z2)
 
 
-@pytest.mark.parametrize("code,impl", [(1, 1), (0, 1), (0, 2)])
+@pytest.mark.parametrize("code,impl", [(1, 1), (0, 1), (0, 2), (0, 3), (0, 4)])
 def test_mlp_layernorm_residual_layer0(nat, dev, problem, code, impl):
-    """K2 (SIMT fp32, SIMT fp16-storage, tcgen05 fp16) against the oracle's h1."""
+    """K2 (SIMT fp32, SIMT fp16-storage, pipelined tcgen05, serial tcgen05) against the oracle's h1."""
     keep = problem["keep32" if code == 1 else "keep16"]
     tdt = torch.float32 if code == 1 else torch.float16
     n = keep["h0"].shape[0]
@@ -257,7 +257,7 @@ def test_mlp_layernorm_residual_layer0(nat, dev, problem, code, impl):
     assert err <= (2e-5 if code == 1 else 4e-3) * scale, (err, scale)
 
 
-@pytest.mark.parametrize("code,impl,out_code", [(1, 1, 1), (0, 1, 0), (0, 2, 0), (0, 2, 1)])
+@pytest.mark.parametrize("code,impl,out_code", [(1, 1, 1), (0, 1, 0), (0, 2, 0), (0, 2, 1), (0, 3, 0)])
 def test_head_l2norm(nat, dev, problem, code, impl, out_code):
     keep = problem["keep32" if code == 1 else "keep16"]
     y = problem["y32" if code == 1 else "y16"]
@@ -276,8 +276,45 @@ def test_head_l2norm(nat, dev, problem, code, impl, out_code):
         1e-5 if out_code == 1 else 2e-3)
 
 
-@pytest.mark.parametrize("code,impl", [(1, 1), (0, 1), (0, 2)])
-def test_whole_forward(nat, dev, problem, code, impl):
+def test_fused_layer_matches_oracle(nat, dev, problem):
+    """K1+K2 in one kernel (aggregation warps feed the tcgen05 pipeline through
+    shared memory) against the oracle's h1 given its h0."""
+    keep = problem["keep16"]
+    rp, cs, ct = problem["csr"]
+    n = keep["h0"].shape[0]
+    h = _up(keep["h0"], dev).to(torch.float16)
+    out = _buf(n, 0, dev)
+    nat.check(nat.lib.gfx_layer_fused(problem["handle"], 0, h.data_ptr(), rp.data_ptr(),
+                                      cs.data_ptr(), ct.data_ptr(), n, out.data_ptr(), _stream()))
+    torch.cuda.synchronize()
+    got, want = out.float().cpu().numpy(), keep["h1"]
+    assert np.abs(got - want).max() <= 4e-3 * np.abs(want).max()
+    out2 = _buf(n, 0, dev)
+    nat.check(nat.lib.gfx_layer_fused(problem["handle"], 0, h.data_ptr(), rp.data_ptr(),
+                                      cs.data_ptr(), ct.data_ptr(), n, out2.data_ptr(), _stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2)          # deterministic
+
+
+@pytest.mark.parametrize("n", [1, 127, 128, 129, 200, 64 * 3 + 1])
+def test_tile_edges(nat, dev, problem, n):
+    """Ragged sizes around the 128-row tile / 64-row block boundaries: all
+    dense paths agree with SIMT on the first n rows."""
+    keep = problem["keep16"]
+    z, h = _up(keep["z0"][:n], dev).half(), _up(keep["h0"][:n], dev).half()
+    outs = []
+    for impl in (1, 2, 3, 4):
+        o = _buf(n, 0, dev)
+        nat.check(nat.lib.gfx_mlp_ln_residual(problem["handle"], 0, z.data_ptr(), h.data_ptr(),
+                                              n, o.data_ptr(), 0, impl, _stream()))
+        outs.append(o)
+    torch.cuda.synchronize()
+    for o in outs[1:]:
+        assert (o.float() - outs[0].float()).abs().max().item() <= 4e-3 * float(np.abs(keep["h1"]).max())
+
+
+@pytest.mark.parametrize("code,impl,fused", [(1, 1, 0), (0, 1, 0), (0, 2, 0), (0, 3, 0), (0, 4, 0), (0, 2, 1)])
+def test_whole_forward(nat, dev, problem, code, impl, fused):
     """gfx_encode (all stages chained on device) against the oracle."""
     x = _up(problem["shard"].node_features, dev)
     rp, cs, ct = problem["csr"]
@@ -287,7 +324,7 @@ def test_whole_forward(nat, dev, problem, code, impl):
     ws = torch.empty(need, dtype=torch.uint8, device=dev)
     nat.check(nat.lib.gfx_encode(problem["handle"], x.data_ptr(), rp.data_ptr(),
                                  cs.data_ptr(), ct.data_ptr(), None, n, out.data_ptr(),
-                                 code, 1, impl, 0, ws.data_ptr(), need, _stream()))
+                                 code, 1, impl, fused, ws.data_ptr(), need, _stream()))
     torch.cuda.synchronize()
     y = problem["y32" if code == 1 else "y16"]
     want = y / np.maximum(np.linalg.norm(y.astype(np.float64), axis=1, keepdims=True), 1e-12)
