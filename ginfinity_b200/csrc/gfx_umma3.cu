@@ -15,9 +15,8 @@
 //
 // Warps: 0-3 epilogue A, 4-7 epilogue B, 8 MMA issuer, 9 z loader (1 thread),
 // 10 residual/output manager (1 thread).
-#include <cuda.h>
-
 #include "gfx_common.cuh"
+#include "gfx_tma.cuh"
 #include "gfx_umma.cuh"
 
 namespace gfx {
@@ -310,40 +309,6 @@ umma3_mlp_kernel(const __grid_constant__ Maps maps, const Args p) {
   if (warp == kMmaWarp) tmem_dealloc(tmem, kTmemCols);
 }
 
-// ---- host side: tensor maps -------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
-                                  const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
-                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = [] {
-    void *ptr = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess ||
-        q != cudaDriverEntryPointSuccess)
-      ptr = nullptr;
-    return reinterpret_cast<EncodeTiledFn>(ptr);
-  }();
-  return fn;
-}
-
-// [rows, 128] fp16 row-major, box = 64 columns x 128 rows, 128-byte swizzle
-static int make_map(CUtensorMap *map, const void *base, int64_t rows) {
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) return fail(GFX_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
-  const cuuint64_t dims[2] = {cuuint64_t(kHidden), cuuint64_t(rows)};
-  const cuuint64_t strides[1] = {cuuint64_t(kHidden) * 2};
-  const cuuint32_t box[2] = {64, cuuint32_t(kTileM)};
-  const cuuint32_t estr[2] = {1, 1};
-  CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), dims, strides,
-                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (rc != CUDA_SUCCESS)
-    return fail(GFX_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(int(rc)));
-  return GFX_OK;
-}
-
 }  // namespace v3
 
 int umma3_mlp_ln_residual(const gfx_model *m, int layer, const __half *z, const __half *h,
@@ -352,9 +317,9 @@ int umma3_mlp_ln_residual(const gfx_model *m, int layer, const __half *z, const 
        reinterpret_cast<uintptr_t>(h_out)) & 15)
     return fail(GFX_ERR_ARGUMENT, "tcgen05 MLP: activation buffers must be 16-byte aligned");
   v3::Maps maps;
-  int rc = v3::make_map(&maps.z, z, n);
-  if (!rc) rc = v3::make_map(&maps.res, h, n);
-  if (!rc) rc = v3::make_map(&maps.out, h_out, n);
+  int rc = tma::make_rows128_map(&maps.z, z, n, v3::kTileM);
+  if (!rc) rc = tma::make_rows128_map(&maps.res, h, n, v3::kTileM);
+  if (!rc) rc = tma::make_rows128_map(&maps.out, h_out, n, v3::kTileM);
   if (rc) return rc;
   const size_t wi = size_t(layer) * kMlpHidden * kHidden;
   v3::Args a{};

@@ -136,8 +136,8 @@ class _Scratch:
         have = self._buf.get(name)
         if have is None or have.numel() < nbytes:
             grow = max(int(nbytes), 1024)
-            have = torch.empty(grow + grow // 8, dtype=torch.uint8,
-                               device=self.device)
+            grow = (grow + grow // 8 + 255) & ~255      # viewable as any dtype
+            have = torch.empty(grow, dtype=torch.uint8, device=self.device)
             self._buf[name] = have
         return have
 
@@ -292,11 +292,12 @@ class Ginfinity:
                                     max_batch_edges, embedding_dtype)
         out_code = nat.GFX_F16 if dtype == np.float16 else nat.GFX_F32
         with torch.cuda.device(self._torch_device), torch.inference_mode():
-            table, core_ptr = self._encode_streaming(
-                shard, int(max_batch_nodes), int(max_batch_edges), out_code)
+            table, core_ptr, rows = self._encode_streaming(
+                shard, int(max_batch_nodes), int(max_batch_edges), out_code,
+                presplit=(dtype.itemsize <= 4))
         if table.dtype != dtype:
-            table = table.astype(dtype)
-        return split_rows(table, core_ptr)
+            return split_rows(table.astype(dtype), core_ptr)
+        return rows
 
     # -- host shard -> host embeddings, copies overlapped with compute -----------
     def _plan(self, node_ptr_d, edge_ptr_d, B, max_batch_nodes, max_batch_edges,
@@ -332,7 +333,7 @@ class Ginfinity:
         return out
 
     def _encode_streaming(self, shard: GraphShard, max_batch_nodes: int,
-                          max_batch_edges: int, out_code: int):
+                          max_batch_edges: int, out_code: int, presplit=True):
         """Three-stream pipeline over chunks: while chunk c runs on the compute
         stream, chunk c+1's arrays are copied in and chunk c-1's embeddings
         are copied out into one pinned [core_count, 128] table."""
@@ -445,8 +446,11 @@ class Ginfinity:
                     host[c0:c1].copy_(src, non_blocking=True)
                 slot["out_free"].record(s_out)
         main.wait_stream(s_out)
+        # the per-record views are built while the device is still working
+        table = host.numpy()
+        rows = split_rows(table, core_ptr) if presplit else None
         main.synchronize()
-        return host.numpy(), core_ptr
+        return table, core_ptr, rows
 
     def encode_device_shard(self, ds: DeviceShard, *, max_batch_nodes=60_000,
                             max_batch_edges=300_000, out_dtype=nat.GFX_F16,

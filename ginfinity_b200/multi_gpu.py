@@ -1,0 +1,53 @@
+"""Host-side plumbing for one-process-per-GPU runs (torchrun / torch.distributed).
+
+Encoding partitions by graph shard with NO collective: graphs never interact
+(reference docs/GRAPH_PIPELINE.md:22-24 hands independent shard files to an
+external scheduler), so each rank takes whole shards, balanced by node count.
+Similarity search shards database rows (search.shard_bounds) and has exactly
+one exchange step, the all-gather of per-query top-k lists (search.py).
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, List, Sequence, Tuple
+
+
+def rank_info() -> Tuple[int, int, int]:
+    """(rank, local_rank, world_size) from the torchrun environment."""
+    return (int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")),
+            int(os.environ.get("WORLD_SIZE", "1")))
+
+
+def assign_shards(node_counts: Sequence[int], world_size: int) -> List[List[int]]:
+    """Deterministic longest-first greedy assignment of shards to ranks,
+    balanced by node count (ties: lower shard index first, lower rank first).
+    Returns, per rank, the shard indices in ascending order."""
+    if world_size < 1:
+        raise ValueError("world_size must be positive")
+    order = sorted(range(len(node_counts)), key=lambda i: (-int(node_counts[i]), i))
+    load = [0] * world_size
+    mine: List[List[int]] = [[] for _ in range(world_size)]
+    for i in order:
+        r = min(range(world_size), key=lambda j: (load[j], j))
+        load[r] += int(node_counts[i])
+        mine[r].append(i)
+    return [sorted(m) for m in mine]
+
+
+def encode_shard_files(encoder, paths: Sequence, *, rank: int, world_size: int,
+                       node_counts: Sequence[int] = None, **encode_kwargs) -> Dict[str, list]:
+    """Encode this rank's share of a list of graph-shard files (the
+    reference's `embed-graphs` unit of work, cli.py:139-197).  Every rank must
+    pass the same `paths`; when `node_counts` is not given the JSON sidecars
+    are read for the node totals.  Returns {path: [embeddings per record]}."""
+    import json
+
+    from .graph import graph_metadata_path, load_graph_shard
+    paths = [str(p) for p in paths]
+    if node_counts is None:
+        node_counts = [int(json.loads(graph_metadata_path(p).read_text())["node_count"])
+                       for p in paths]
+    out = {}
+    for i in assign_shards(node_counts, world_size)[rank]:
+        out[paths[i]] = encoder.encode_graphs(load_graph_shard(paths[i]), **encode_kwargs)
+    return out

@@ -316,3 +316,61 @@ def topk_bruteforce(queries, database, k, metric="cosine"):
         order = np.lexsort((ids, -s[r]))[:k]
         idx[r], val[r] = order, s[r][order]
     return val, idx
+
+
+def exact_scores_fp32(queries, rows, metric="cosine"):
+    """The score definition of ginfinity_b200's search (no reference
+    counterpart): a sequential fp32 FMA chain over dimensions 0..d-1 of the
+    fp16 inputs.  queries [Q,d], rows [R,d] float16 -> float32 [Q,R].
+
+    fma(a, b, acc) in fp32 is emulated as float32(float64(acc) + float64(a) *
+    float64(b)): the product of two fp16 (or of an fp32 difference with
+    itself) is exact in float64, so apart from astronomically rare double
+    roundings this is the correctly rounded single-precision FMA."""
+    q = np.asarray(queries, np.float16).astype(np.float32)
+    x = np.asarray(rows, np.float16).astype(np.float32)
+    acc = np.zeros((q.shape[0], x.shape[0]), np.float32)
+    for d in range(q.shape[1]):
+        if metric == "cosine":
+            a = q[:, d, None].astype(np.float64)
+            b = x[None, :, d].astype(np.float64)
+        elif metric == "l2":
+            diff = (q[:, d, None] - x[None, :, d]).astype(np.float32)
+            a = b = diff.astype(np.float64)
+        else:
+            raise ValueError(metric)
+        acc = (acc.astype(np.float64) + a * b).astype(np.float32)
+    return acc if metric == "cosine" else -acc
+
+
+def topk_exact(queries, database, k, metric="cosine", index_base=0):
+    """Brute force under the package's own score definition
+    (`exact_scores_fp32`), ordered by (score desc, index asc); slots beyond
+    the number of rows hold (-inf, -1).  Small inputs only."""
+    Q, D = queries.shape[0], database.shape[0]
+    val = np.full((Q, k), -np.inf, np.float32)
+    idx = np.full((Q, k), -1, np.int64)
+    if D == 0 or Q == 0:
+        return val, idx
+    s = exact_scores_fp32(queries, database, metric)
+    ids = np.arange(D)
+    kk = min(k, D)
+    for r in range(Q):
+        order = np.lexsort((ids, -s[r].astype(np.float64)))[:kk]
+        idx[r, :kk], val[r, :kk] = order + index_base, s[r][order]
+    return val, idx
+
+
+def merge_topk(all_scores, all_index, k):
+    """k-way merge of [parts, Q, k] lists by (score desc, index asc);
+    index < 0 marks padding."""
+    parts, Q, kk = all_scores.shape
+    s = np.transpose(all_scores, (1, 0, 2)).reshape(Q, parts * kk)
+    i = np.transpose(all_index, (1, 0, 2)).reshape(Q, parts * kk)
+    val = np.full((Q, k), -np.inf, np.float32)
+    idx = np.full((Q, k), -1, np.int64)
+    for r in range(Q):
+        ok = i[r] >= 0
+        order = np.lexsort((i[r][ok], -s[r][ok].astype(np.float64)))[:k]
+        idx[r, :len(order)], val[r, :len(order)] = i[r][ok][order], s[r][ok][order]
+    return val, idx

@@ -1,0 +1,147 @@
+"""K5 similarity search on the GPU against the oracle (oracle/gine_oracle.py:
+topk_exact / topk_bruteforce / merge_topk).  The reference has no search, so
+parity here is against this package's own stated contract (parity unpinned):
+indices bit-exact under (score desc, index asc), scores equal to the
+sequential-fp32 definition."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import gine_oracle as O  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def search():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from ginfinity_b200 import search as S
+    return S
+
+
+def unit_rows(seed, n, dim=128, scale=None):
+    rng = np.random.default_rng(seed)
+    a = rng.normal(size=(n, dim)).astype(np.float32)
+    a /= np.maximum(np.linalg.norm(a, axis=1, keepdims=True), 1e-12)
+    if scale is not None:
+        a *= rng.uniform(*scale, size=(n, 1)).astype(np.float32)
+    return a.astype(np.float16)
+
+
+def run(search, q, db, k, metric, index_base=0):
+    index = search.EmbeddingIndex(db, device="cuda:0", index_base=index_base)
+    s, i = index.search(q, k, metric)
+    torch.cuda.synchronize()
+    return s.cpu().numpy(), i.cpu().numpy()
+
+
+@pytest.mark.parametrize("metric", ["cosine", "l2"])
+@pytest.mark.parametrize("Q,D,k", [(300, 5000, 10), (1, 129, 1), (257, 4096, 24), (64, 127, 5)])
+def test_topk_matches_the_exact_oracle(search, metric, Q, D, k):
+    q = unit_rows(1, Q)
+    db = unit_rows(2, D, scale=(0.5, 1.5) if metric == "l2" else None)
+    got_s, got_i = run(search, q, db, k, metric)
+    want_s, want_i = O.topk_exact(q, db, k, metric)
+    assert got_i.dtype == np.int64 and got_s.dtype == np.float32
+    np.testing.assert_array_equal(got_i, want_i)
+    np.testing.assert_allclose(got_s, want_s, rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("metric", ["cosine", "l2"])
+def test_topk_agrees_with_float64_bruteforce_where_gaps_are_resolvable(search, metric):
+    q, db = unit_rows(3, 200), unit_rows(4, 3000)
+    k = 10
+    got_s, got_i = run(search, q, db, k, metric)
+    want_s, want_i = O.topk_bruteforce(q, db, k + 1, metric)
+    np.testing.assert_allclose(got_s, want_s[:, :k], rtol=0, atol=2e-6)
+    gaps = want_s[:, :-1] - want_s[:, 1:]                # float64 gaps between ranks
+    clear = np.all(gaps > 1e-5, axis=1)
+    assert clear.mean() > 0.9
+    np.testing.assert_array_equal(got_i[clear], want_i[clear, :k])
+
+
+def test_ties_break_by_ascending_index(search):
+    base = unit_rows(5, 40)
+    db = np.tile(base, (30, 1))                           # every row appears 30 times
+    q = unit_rows(6, 130)
+    got_s, got_i = run(search, q, db, 12, "cosine")
+    want_s, want_i = O.topk_exact(q, db, 12, "cosine")
+    np.testing.assert_array_equal(got_i, want_i)
+    # the 12 best are the best distinct row at its 12 lowest positions
+    assert np.all(np.diff(got_i, axis=1) == 40)
+    assert np.all(got_s == got_s[:, :1])
+
+
+def test_short_and_empty_databases_pad_with_minus_inf(search):
+    q = unit_rows(7, 33)
+    db = unit_rows(8, 5)
+    s, i = run(search, q, db, 8, "cosine", index_base=1000)
+    want_s, want_i = O.topk_exact(q, db, 8, "cosine", index_base=1000)
+    np.testing.assert_array_equal(i, want_i)
+    assert np.all(i[:, 5:] == -1) and np.all(np.isneginf(s[:, 5:]))
+    s, i = run(search, q, db[:0], 3, "l2")
+    assert np.all(i == -1) and np.all(np.isneginf(s))
+    s, i = run(search, q[:0], db, 3, "cosine")
+    assert s.shape == (0, 3) and i.shape == (0, 3)
+
+
+def test_many_segments_and_query_tiles(search):
+    """One query tile forces the database to be split into many segments;
+    several query tiles with a tail exercise the work-item loop."""
+    db = unit_rows(9, 40_000)
+    for Q in (7, 700):
+        q = unit_rows(10 + Q, Q)
+        got_s, got_i = run(search, q, db, 10, "cosine")
+        want_s, want_i = O.topk_exact(q[:64], db, 10, "cosine")
+        np.testing.assert_array_equal(got_i[:64], want_i[:min(Q, 64)])
+        ref = torch.from_numpy(q.astype(np.float32)).cuda() @ torch.from_numpy(db.astype(np.float32)).cuda().T
+        top = ref.topk(10, dim=1)
+        overlap = (torch.from_numpy(got_i).cuda()[:, :1] == top.indices[:, :1]).float().mean().item()
+        assert overlap > 0.99
+
+
+def test_sharded_results_merge_to_the_global_answer(search):
+    q, db = unit_rows(11, 150), unit_rows(12, 9000)
+    k, world = 10, 3
+    parts_s, parts_i = [], []
+    for rank in range(world):
+        index = search.EmbeddingIndex.shard(db, rank=rank, world_size=world, device="cuda:0")
+        s, i = index.search(q, k, "cosine")
+        parts_s.append(s)
+        parts_i.append(i)
+    all_s, all_i = torch.stack(parts_s), torch.stack(parts_i)
+    got_s, got_i = search.merge_lists(all_s, all_i)
+    torch.cuda.synchronize()
+    want_s, want_i = O.topk_exact(q, db, k, "cosine")
+    np.testing.assert_array_equal(got_i.cpu().numpy(), want_i)
+    np.testing.assert_allclose(got_s.cpu().numpy(), want_s, rtol=1e-6)
+    m_s, m_i = O.merge_topk(all_s.cpu().numpy(), all_i.cpu().numpy(), k)
+    np.testing.assert_array_equal(got_i.cpu().numpy(), m_i)
+
+
+def test_argument_checks(search):
+    db, q = unit_rows(13, 10), unit_rows(14, 2)
+    index = search.EmbeddingIndex(db, device="cuda:0")
+    with pytest.raises(ValueError, match="k must be"):
+        index.search(q, 25)
+    with pytest.raises(ValueError, match="metric"):
+        index.search(q, 3, "dot")
+    with pytest.raises(ValueError, match="float16"):
+        index.search(q.astype(np.float32), 3)
+    with pytest.raises(ValueError, match="CUDA device"):
+        search.EmbeddingIndex(db, device="cpu")
+
+
+def test_search_over_real_embeddings(search, synthetic_state):
+    """Encoder output -> index -> every nucleotide's best hit is itself."""
+    import ginfinity_b200 as g
+    from helpers import random_records
+    enc = g.Ginfinity.from_state(synthetic_state, device="cuda:0")
+    emb = np.concatenate(enc.encode_many(random_records(21, 30)))
+    index = search.EmbeddingIndex(emb, device="cuda:0")
+    s, i = index.search(emb[:500], 3, "cosine")
+    torch.cuda.synchronize()
+    want_s, want_i = O.topk_exact(emb[:500], emb, 3, "cosine")
+    np.testing.assert_array_equal(i.cpu().numpy(), want_i)
+    assert np.all(np.abs(s.cpu().numpy()[:, 0] - 1.0) < 2e-3)

@@ -1,0 +1,99 @@
+"""world_size-2 `gloo` tests (CPU) of the N>1 host logic: shard assignment for
+the collective-free encode, and the one exchange step of the similarity search
+(row sharding -> local lists -> all-gather -> merge).  The local search and
+the merge are GPU kernels in the product; here the ORACLE stands in for them so
+the plumbing (row ranges, index bases, gather layout, rank order) is what is
+tested.  The bench's max-over-ranks / sum-over-ranks reduction is covered too."""
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def _free_port() -> int:
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, tmp):
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+    from ginfinity_b200 import multi_gpu, search
+    from oracle import gine_oracle as O
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        assert multi_gpu.rank_info() == (rank, rank, world)
+        rng = np.random.default_rng(0)                       # same data on every rank
+        db = rng.normal(size=(1001, 128)).astype(np.float16)
+        q = rng.normal(size=(37, 128)).astype(np.float16)
+        k = 6
+        lo, hi = search.shard_bounds(len(db), world, rank)
+        s, i = O.topk_exact(q, db[lo:hi], k, "cosine", index_base=lo)
+        all_s, all_i = search.gather_lists(torch.from_numpy(s), torch.from_numpy(i), world)
+        assert tuple(all_s.shape) == (world, 37, k)
+        # slice r of the gathered tensor is rank r's list
+        assert torch.equal(all_s[rank], torch.from_numpy(s))
+        got_s, got_i = O.merge_topk(all_s.numpy(), all_i.numpy(), k)
+        want_s, want_i = O.topk_exact(q, db, k, "cosine")
+        np.testing.assert_array_equal(got_i, want_i)
+        np.testing.assert_array_equal(got_s, want_s)
+        # bench.py's reduction: time = max over ranks, work = sum over ranks
+        t = torch.tensor([10.0 + rank], dtype=torch.float64)
+        n = torch.tensor([100.0 * (rank + 1)], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(n, op=dist.ReduceOp.SUM)
+        assert t.item() == 10.0 + world - 1 and n.item() == 100.0 * world * (world + 1) / 2
+        # collective-free encode: every shard is taken by exactly one rank
+        mine = multi_gpu.assign_shards([500, 100, 400, 300, 50, 250], world)[rank]
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        assert sorted(sum(gathered, [])) == list(range(6))
+        (Path(tmp) / f"ok{rank}").write_text("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_search_exchange_and_shard_assignment(tmp_path):
+    import torch.multiprocessing as mp
+    world, port = 2, _free_port()
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / f"ok{r}").is_file() for r in range(world))
+
+
+def test_assign_shards_is_balanced_and_deterministic():
+    sys.path.insert(0, str(ROOT))
+    from ginfinity_b200.multi_gpu import assign_shards
+    rng = np.random.default_rng(1)
+    counts = rng.integers(1_000_000, 30_000_000, size=50).tolist()
+    for world in (1, 2, 4, 8):
+        parts = assign_shards(counts, world)
+        assert sorted(sum(parts, [])) == list(range(50))
+        loads = [sum(counts[i] for i in p) for p in parts]
+        assert max(loads) <= 1.1 * (sum(counts) / world) + max(counts) * (world > 1) * 0.2
+        assert parts == assign_shards(counts, world)
+    assert assign_shards([], 4) == [[], [], [], []]
+    with pytest.raises(ValueError):
+        assign_shards([1], 0)
+
+
+def test_shard_bounds_cover_the_database_exactly():
+    sys.path.insert(0, str(ROOT))
+    from ginfinity_b200.search import shard_bounds
+    for rows in (0, 1, 7, 1000, 10**8):
+        for world in (1, 2, 3, 8):
+            spans = [shard_bounds(rows, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == rows
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_bounds(10, 2, 2)
