@@ -192,6 +192,12 @@ extern "C" int gfx_model_create(const gfx_folded_weights *w, gfx_model **out) {
   gfx_model *m = new gfx_model();
   m->hidden = H; m->layers = L; m->out_dim = w->out_dim; m->feature_dim = F; m->edge_dim = ED;
   for (int l = 0; l < L; ++l) m->eps1[l] = w->eps1_host[l];
+  m->host.b1.assign(w->b1_host, w->b1_host + size_t(L) * M);
+  m->host.b2.assign(w->b2_host, w->b2_host + size_t(L) * H);
+  m->host.ln_g.assign(w->ln_g_host, w->ln_g_host + size_t(L) * H);
+  m->host.ln_b.assign(w->ln_b_host, w->ln_b_host + size_t(L) * H);
+  m->host.ba.assign(w->ba_host, w->ba_host + H);
+  m->host.bb.assign(w->bb_host, w->bb_host + H);
   cudaError_t err = cudaGetDevice(&m->device);
   if (err == cudaSuccess) err = cudaMalloc(&m->arena, ab.bytes.size());
   if (err == cudaSuccess)

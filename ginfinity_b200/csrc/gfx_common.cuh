@@ -6,6 +6,7 @@
 
 #include <cstdio>
 #include <string>
+#include <vector>
 
 #include "gfx.h"
 
@@ -54,6 +55,12 @@ class StageScope {
 
 }  // namespace gfx
 
+// Host copies of the per-channel vectors: the lean tcgen05 kernels take them
+// as kernel parameters (constant bank) instead of loading them on the device.
+struct gfx_host_vectors {
+  std::vector<float> b1, b2, ln_g, ln_b, ba, bb;
+};
+
 // Device-side weights.  One allocation ("arena") holds everything.
 struct gfx_model {
   int hidden, layers, out_dim, feature_dim, edge_dim;
@@ -82,4 +89,5 @@ struct gfx_model {
   const __half *wa_img;   //       (2 kblocks x 128 rows x 64)   = 32 KB
   const __half *wb_img;   //       (2 kblocks x 128 rows x 64)   = 32 KB
   const __half *table16;  // [L][edge_dim][H] fp16 (fused layer kernel)
+  gfx_host_vectors host;
 };

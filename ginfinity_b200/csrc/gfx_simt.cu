@@ -132,6 +132,84 @@ aggregate_kernel(const T *__restrict__ h, const int32_t *__restrict__ row_ptr,
 }
 
 // ---------------------------------------------------------------------------
+// K1, fp16 storage: the same half-warp-per-node scheme with packed math.  The
+// message relu(h_src + table[type]) is one HFMA2.RELU per channel pair
+// (rounded to fp16, which is what the reference's own fp16 path does,
+// _model.py:43); the sum stays fp32 via the mixed-precision add
+// (add.rn.f32.f16 -> FHADD), in CSR order.  1.5 instructions per channel and
+// edge instead of 4, and the fp16 table row is one conflict-free 128-bit
+// shared-memory load per edge.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t hfma2_relu_add(uint32_t x, uint32_t t) {
+  uint32_t r;
+  asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(0x3c003c00u), "r"(t));
+  return r;
+}
+__device__ __forceinline__ void add_pair(float &a0, float &a1, uint32_t m) {
+  asm("{\n.reg .b16 lo, hi;\nmov.b32 {lo, hi}, %2;\nadd.rn.f32.f16 %0, lo, %0;\n"
+      "add.rn.f32.f16 %1, hi, %1;\n}"
+      : "+f"(a0), "+f"(a1)
+      : "r"(m));
+}
+__device__ __forceinline__ void add_message(float *acc, const uint4 &nb, const uint4 &tb) {
+  add_pair(acc[0], acc[1], hfma2_relu_add(nb.x, tb.x));
+  add_pair(acc[2], acc[3], hfma2_relu_add(nb.y, tb.y));
+  add_pair(acc[4], acc[5], hfma2_relu_add(nb.z, tb.z));
+  add_pair(acc[6], acc[7], hfma2_relu_add(nb.w, tb.w));
+}
+
+__global__ void __launch_bounds__(256)
+aggregate_f16_kernel(const __half *__restrict__ h, const int32_t *__restrict__ row_ptr,
+                     const int32_t *__restrict__ col_src, const uint8_t *__restrict__ col_type,
+                     const __half *__restrict__ table16, int edge_dim, float eps1, int64_t n,
+                     __half *__restrict__ z) {
+  __shared__ __align__(16) __half tab[kMaxEdgeDim * kHidden];
+  for (int i = threadIdx.x; i < edge_dim * kHidden / 8; i += blockDim.x)
+    reinterpret_cast<uint4 *>(tab)[i] = reinterpret_cast<const uint4 *>(table16)[i];
+  __syncthreads();
+  const int sub = threadIdx.x & 15;
+  const uint4 *hv = reinterpret_cast<const uint4 *>(h) + sub;      // row r -> hv[r * 16]
+  const uint4 *tv = reinterpret_cast<const uint4 *>(tab) + sub;
+  const int64_t rows_per_pass = int64_t(gridDim.x) * (blockDim.x >> 4);
+  for (int64_t i = int64_t(blockIdx.x) * (blockDim.x >> 4) + (threadIdx.x >> 4); i < n;
+       i += rows_per_pass) {
+    const int beg = row_ptr[i], end = row_ptr[i + 1];
+    const uint4 self = hv[i * 16];
+    float acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+    int e = beg;
+    for (; e + 4 <= end; e += 4) {
+      int s[4], t[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        s[u] = col_src[e + u];
+        t[u] = col_type[e + u];
+      }
+      uint4 nb[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) nb[u] = hv[int64_t(s[u]) * 16];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) add_message(acc, nb[u], tv[t[u] * 16]);
+    }
+    for (; e < end; ++e) {
+      const int s = col_src[e], t = col_type[e];
+      add_message(acc, hv[int64_t(s) * 16], tv[t * 16]);
+    }
+    const __half2 *sh = reinterpret_cast<const __half2 *>(&self);
+    uint4 out;
+    uint32_t *o = reinterpret_cast<uint32_t *>(&out);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float2 f = __half22float2(sh[c]);
+      const __half2 r = __floats2half2_rn(fmaf(eps1, f.x, acc[2 * c]), fmaf(eps1, f.y, acc[2 * c + 1]));
+      o[c] = *reinterpret_cast<const uint32_t *>(&r);
+    }
+    reinterpret_cast<uint4 *>(z)[i * 16 + sub] = out;
+  }
+}
+
+// ---------------------------------------------------------------------------
 // SIMT MLP.  One warp owns 8 node rows end to end (both GEMMs, LayerNorm or
 // L2 norm), so nothing but weights is shared between warps and only
 // __syncwarp is needed.  Stage 1: lane owns HID/32 hidden columns of its 8
@@ -324,6 +402,8 @@ int umma1_head_l2norm(const gfx_model *m, const __half *h, const int32_t *out_ro
                       void *out, int out_dtype, cudaStream_t st);
 int umma3_mlp_ln_residual(const gfx_model *m, int layer, const __half *z, const __half *h,
                           int64_t n, __half *h_out, cudaStream_t st);
+int umma4_mlp_ln_residual(const gfx_model *m, int layer, const __half *z, const __half *h,
+                          int64_t n, __half *h_out, cudaStream_t st);
 
 }  // namespace gfx
 
@@ -357,8 +437,8 @@ extern "C" int gfx_aggregate(const gfx_model *m, int layer, const void *h, const
   StageScope scope(GFX_STAGE_AGGREGATE, st, 1);
   const size_t toff = size_t(layer) * m->edge_dim * kHidden;
   if (dtype == GFX_F16)
-    aggregate_kernel<__half><<<row_grid(n), 256, 0, st>>>(
-        static_cast<const __half *>(h), row_ptr, col_src, col_type, m->table[1] + toff,
+    aggregate_f16_kernel<<<row_grid(n), 256, 0, st>>>(
+        static_cast<const __half *>(h), row_ptr, col_src, col_type, m->table16 + toff,
         m->edge_dim, m->eps1[layer], n, static_cast<__half *>(z));
   else if (dtype == GFX_F32)
     aggregate_kernel<float><<<row_grid(n), 256, 0, st>>>(
@@ -379,10 +459,12 @@ extern "C" int gfx_mlp_ln_residual(const gfx_model *m, int layer, const void *z,
   const int H = kHidden, M = kMlpHidden;
   StageScope scope(GFX_STAGE_MLP, st, 1);
   if (impl == GFX_IMPL_AUTO) impl = dtype == GFX_F16 ? GFX_IMPL_UMMA_TMA : GFX_IMPL_SIMT;
-  if (impl == GFX_IMPL_UMMA || impl == GFX_IMPL_UMMA_SERIAL || impl == GFX_IMPL_UMMA_TMA) {
+  if (impl == GFX_IMPL_UMMA || impl == GFX_IMPL_UMMA_SERIAL || impl == GFX_IMPL_UMMA_TMA ||
+      impl == GFX_IMPL_UMMA_LEAN) {
     if (dtype != GFX_F16)
       return fail(GFX_ERR_UNSUPPORTED, "tcgen05 MLP exists for GFX_F16 only");
-    auto fn = impl == GFX_IMPL_UMMA_TMA ? umma3_mlp_ln_residual
+    auto fn = impl == GFX_IMPL_UMMA_LEAN ? umma4_mlp_ln_residual
+              : impl == GFX_IMPL_UMMA_TMA ? umma3_mlp_ln_residual
               : impl == GFX_IMPL_UMMA   ? umma_mlp_ln_residual
                                         : umma1_mlp_ln_residual;
     return fn(m, layer, static_cast<const __half *>(z), static_cast<const __half *>(h), n,
@@ -413,7 +495,7 @@ extern "C" int gfx_head_l2norm(const gfx_model *m, const void *h, const int32_t 
   cudaStream_t st = as_stream(stream);
   StageScope scope(GFX_STAGE_HEAD, st, 1);
   if (impl == GFX_IMPL_AUTO) impl = dtype == GFX_F16 ? GFX_IMPL_UMMA : GFX_IMPL_SIMT;
-  if (impl == GFX_IMPL_UMMA_TMA) impl = GFX_IMPL_UMMA;      // the head has no TMA-I/O variant yet
+  if (impl == GFX_IMPL_UMMA_TMA || impl == GFX_IMPL_UMMA_LEAN) impl = GFX_IMPL_UMMA;  // head: v2 kernel
   if (impl == GFX_IMPL_UMMA || impl == GFX_IMPL_UMMA_SERIAL) {
     if (dtype != GFX_F16)
       return fail(GFX_ERR_UNSUPPORTED, "tcgen05 head exists for GFX_F16 only");

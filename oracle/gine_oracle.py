@@ -227,8 +227,9 @@ def forward_folded(fw, x, row_ptr, col_src, col_type, *, half_storage=False,
 
     ``half_storage=True`` models the device fp16 path: weights, tables and
     every tensor that the kernels store between stages (h, z, the hidden
-    activation fed to the second GEMM, the head's hidden activation) are
-    rounded to fp16; all sums are float32.
+    activation fed to the second GEMM, the head's hidden activation) and the
+    per-edge message relu(h_src + table) (as in the reference's own fp16
+    path, _model.py:43) are rounded to fp16; all sums are float32.
     """
     q = _h if half_storage else (lambda a: a)
     n = x.shape[0]
@@ -240,7 +241,7 @@ def forward_folded(fw, x, row_ptr, col_src, col_type, *, half_storage=False,
     h = q(x.astype(np.float32) @ q(fw["w_in"]).T + fw["b_in"])
     keep["h0"] = h
     for l in range(layers):
-        m = np.maximum(h[src] + q(fw["table"][l])[typ], 0)
+        m = q(np.maximum(h[src] + q(fw["table"][l])[typ], 0))
         agg = np.zeros_like(h)
         np.add.at(agg, dst, m)                       # CSR order per row
         z = q(fw["eps1"][l] * h + agg)
