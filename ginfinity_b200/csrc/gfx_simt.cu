@@ -75,6 +75,54 @@ input_linear_kernel(const float *__restrict__ x, const float *__restrict__ w_in,
   }
 }
 
+// Four consecutive nodes per half-warp and iteration: their 28 features are
+// seven 128-bit loads issued up front (x must be 16-byte aligned), so the
+// kernel runs at the speed of its 256 B/node of stores instead of waiting on
+// seven dependent scalar loads per node.
+template <typename T>
+__global__ void __launch_bounds__(256)
+input_linear4_kernel(const float *__restrict__ x, const float *__restrict__ w_in,
+                     const float *__restrict__ b_in, int64_t n, T *__restrict__ h) {
+  const int sub = threadIdx.x & 15;
+  float w[8][kFeat], b[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    b[c] = b_in[sub * 8 + c];
+#pragma unroll
+    for (int f = 0; f < kFeat; ++f) w[c][f] = w_in[(sub * 8 + c) * kFeat + f];
+  }
+  const int64_t groups = (n + 3) / 4;
+  const int64_t per_pass = int64_t(gridDim.x) * (blockDim.x >> 4);
+  for (int64_t g = int64_t(blockIdx.x) * (blockDim.x >> 4) + (threadIdx.x >> 4); g < groups;
+       g += per_pass) {
+    const int64_t i0 = g * 4;
+    float xf[4 * kFeat];
+    if (i0 + 4 <= n) {
+      const float4 *xv = reinterpret_cast<const float4 *>(x + i0 * kFeat);
+#pragma unroll
+      for (int q = 0; q < kFeat; ++q) {
+        const float4 v = xv[q];
+        xf[4 * q] = v.x; xf[4 * q + 1] = v.y; xf[4 * q + 2] = v.z; xf[4 * q + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4 * kFeat; ++q) xf[q] = i0 * kFeat + q < n * kFeat ? x[i0 * kFeat + q] : 0.f;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      Row8 o;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float acc = b[c];
+#pragma unroll
+        for (int f = 0; f < kFeat; ++f) acc = fmaf(xf[r * kFeat + f], w[c][f], acc);
+        o.v[c] = acc;
+      }
+      if (i0 + r < n) store8(h + (i0 + r) * kHidden + sub * 8, o);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------
 // K1  z_i = eps1 * h_i + sum_{e in row i} relu(h[col_src[e]] + table[col_type[e]])
 // One half-warp per destination node, edges of a row taken four at a time so
@@ -158,6 +206,27 @@ __device__ __forceinline__ void add_message(float *acc, const uint4 &nb, const u
   add_pair(acc[6], acc[7], hfma2_relu_add(nb.w, tb.w));
 }
 
+// The per-node chain row_ptr -> col_src/col_type -> neighbour rows is three
+// dependent memory latencies; run naively a half-warp spends two thirds of its
+// time with ~100 bytes in flight.  The loop below is software-pipelined two
+// nodes deep: while node i's rows are in flight, node i+1's edge indices and
+// node i+2's row_ptr entries are being fetched, so every resident half-warp
+// always has its ~1.5 KB of row loads outstanding.  kWin edges per node are
+// covered by the pipeline (the builder's graphs have in-degree <= 5); longer
+// rows finish in a plain loop.
+constexpr int kWin = 5;
+
+__device__ __forceinline__ void load_window(const int32_t *__restrict__ col_src,
+                                            const uint8_t *__restrict__ col_type, int beg, int end,
+                                            int *s, int *t) {
+#pragma unroll
+  for (int u = 0; u < kWin; ++u) {
+    const bool ok = beg + u < end;
+    s[u] = ok ? col_src[beg + u] : 0;
+    t[u] = ok ? int(col_type[beg + u]) : 0;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 aggregate_f16_kernel(const __half *__restrict__ h, const int32_t *__restrict__ row_ptr,
                      const int32_t *__restrict__ col_src, const uint8_t *__restrict__ col_type,
@@ -170,32 +239,40 @@ aggregate_f16_kernel(const __half *__restrict__ h, const int32_t *__restrict__ r
   const int sub = threadIdx.x & 15;
   const uint4 *hv = reinterpret_cast<const uint4 *>(h) + sub;      // row r -> hv[r * 16]
   const uint4 *tv = reinterpret_cast<const uint4 *>(tab) + sub;
-  const int64_t rows_per_pass = int64_t(gridDim.x) * (blockDim.x >> 4);
-  for (int64_t i = int64_t(blockIdx.x) * (blockDim.x >> 4) + (threadIdx.x >> 4); i < n;
-       i += rows_per_pass) {
-    const int beg = row_ptr[i], end = row_ptr[i + 1];
-    const uint4 self = hv[i * 16];
+  const int64_t stride = int64_t(gridDim.x) * (blockDim.x >> 4);
+  int64_t i = int64_t(blockIdx.x) * (blockDim.x >> 4) + (threadIdx.x >> 4);
+  if (i >= n) return;
+  int beg = row_ptr[i], end = row_ptr[i + 1];
+  int64_t i1 = i + stride;
+  int beg1 = 0, end1 = 0;
+  if (i1 < n) {
+    beg1 = row_ptr[i1];
+    end1 = row_ptr[i1 + 1];
+  }
+  int s[kWin], t[kWin];
+  load_window(col_src, col_type, beg, end, s, t);
+  while (true) {
+    const int64_t i2 = i1 + stride;
+    int beg2 = 0, end2 = 0;
+    if (i2 < n) {                                   // stage 1: row_ptr two nodes ahead
+      beg2 = row_ptr[i2];
+      end2 = row_ptr[i2 + 1];
+    }
+    int s1[kWin], t1[kWin];
+    load_window(col_src, col_type, beg1, end1, s1, t1);   // stage 2: indices one node ahead
+    const uint4 self = hv[i * 16];                  // stage 3: this node's rows
+    const int deg = end - beg;
+    uint4 nb[kWin];
+#pragma unroll
+    for (int u = 0; u < kWin; ++u) nb[u] = u < deg ? hv[int64_t(s[u]) * 16] : make_uint4(0, 0, 0, 0);
     float acc[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) acc[c] = 0.f;
-    int e = beg;
-    for (; e + 4 <= end; e += 4) {
-      int s[4], t[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        s[u] = col_src[e + u];
-        t[u] = col_type[e + u];
-      }
-      uint4 nb[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) nb[u] = hv[int64_t(s[u]) * 16];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) add_message(acc, nb[u], tv[t[u] * 16]);
-    }
-    for (; e < end; ++e) {
-      const int s = col_src[e], t = col_type[e];
-      add_message(acc, hv[int64_t(s) * 16], tv[t * 16]);
-    }
+    for (int u = 0; u < kWin; ++u)
+      if (u < deg) add_message(acc, nb[u], tv[t[u] * 16]);
+    for (int e = beg + kWin; e < end; ++e)          // rows longer than the window
+      add_message(acc, hv[int64_t(col_src[e]) * 16], tv[int(col_type[e]) * 16]);
     const __half2 *sh = reinterpret_cast<const __half2 *>(&self);
     uint4 out;
     uint32_t *o = reinterpret_cast<uint32_t *>(&out);
@@ -206,6 +283,14 @@ aggregate_f16_kernel(const __half *__restrict__ h, const int32_t *__restrict__ r
       o[c] = *reinterpret_cast<const uint32_t *>(&r);
     }
     reinterpret_cast<uint4 *>(z)[i * 16 + sub] = out;
+    if (i1 >= n) break;
+    i = i1; beg = beg1; end = end1;
+    i1 = i2; beg1 = beg2; end1 = end2;
+#pragma unroll
+    for (int u = 0; u < kWin; ++u) {
+      s[u] = s1[u];
+      t[u] = t1[u];
+    }
   }
 }
 
@@ -385,6 +470,14 @@ static int launch_mlp(const TIn *a, const TIn *res, const float *w1t, const floa
   return GFX_OK;
 }
 
+// grid-stride kernels with a software pipeline: exactly the blocks that are
+// resident at once (per_sm blocks of 256 threads per SM)
+static inline int resident_grid(int64_t n, int per_sm) {
+  int64_t b = (n + 15) / 16;
+  int64_t cap = int64_t(kNumSMs) * per_sm;
+  return int(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
 static inline int row_grid(int64_t n) {
   int64_t b = (n + 15) / 16;
   int64_t cap = int64_t(kNumSMs) * 8;
@@ -415,14 +508,27 @@ extern "C" int gfx_input_linear(const gfx_model *m, const float *x, int64_t n, v
   if (n <= 0) return GFX_OK;
   cudaStream_t st = as_stream(stream);
   StageScope scope(GFX_STAGE_INPUT, st, 1);
-  if (dtype == GFX_F16)
-    input_linear_kernel<__half><<<row_grid(n), 256, 0, st>>>(x, m->w_in[1], m->b_in, n,
-                                                             static_cast<__half *>(h));
-  else if (dtype == GFX_F32)
-    input_linear_kernel<float><<<row_grid(n), 256, 0, st>>>(x, m->w_in[0], m->b_in, n,
-                                                            static_cast<float *>(h));
-  else
+  if (dtype != GFX_F16 && dtype != GFX_F32)
     return fail(GFX_ERR_ARGUMENT, "gfx_input_linear: unknown dtype");
+  // nodes before the first 16-byte aligned feature row (at most 3) take the
+  // scalar kernel, the rest the vectorised one
+  int64_t lead = 0;
+  while (lead < n && lead < 4 && (reinterpret_cast<uintptr_t>(x + lead * kFeat) & 15)) ++lead;
+  if (lead == 4) lead = n;                          // x is not even 4-byte aligned: scalar only
+  const int64_t rest = n - lead;
+  if (dtype == GFX_F16) {
+    __half *hh = static_cast<__half *>(h);
+    if (lead) input_linear_kernel<__half><<<row_grid(lead), 256, 0, st>>>(x, m->w_in[1], m->b_in, lead, hh);
+    if (rest)
+      input_linear4_kernel<__half><<<row_grid((rest + 3) / 4), 256, 0, st>>>(
+          x + lead * kFeat, m->w_in[1], m->b_in, rest, hh + lead * kHidden);
+  } else {
+    float *hf = static_cast<float *>(h);
+    if (lead) input_linear_kernel<float><<<row_grid(lead), 256, 0, st>>>(x, m->w_in[0], m->b_in, lead, hf);
+    if (rest)
+      input_linear4_kernel<float><<<row_grid((rest + 3) / 4), 256, 0, st>>>(
+          x + lead * kFeat, m->w_in[0], m->b_in, rest, hf + lead * kHidden);
+  }
   GFX_LAUNCH_CHECK();
   return GFX_OK;
 }
@@ -437,7 +543,7 @@ extern "C" int gfx_aggregate(const gfx_model *m, int layer, const void *h, const
   StageScope scope(GFX_STAGE_AGGREGATE, st, 1);
   const size_t toff = size_t(layer) * m->edge_dim * kHidden;
   if (dtype == GFX_F16)
-    aggregate_f16_kernel<<<row_grid(n), 256, 0, st>>>(
+    aggregate_f16_kernel<<<resident_grid(n, 3), 256, 0, st>>>(
         static_cast<const __half *>(h), row_ptr, col_src, col_type, m->table16 + toff,
         m->edge_dim, m->eps1[layer], n, static_cast<__half *>(z));
   else if (dtype == GFX_F32)
@@ -458,7 +564,7 @@ extern "C" int gfx_mlp_ln_residual(const gfx_model *m, int layer, const void *z,
   cudaStream_t st = as_stream(stream);
   const int H = kHidden, M = kMlpHidden;
   StageScope scope(GFX_STAGE_MLP, st, 1);
-  if (impl == GFX_IMPL_AUTO) impl = dtype == GFX_F16 ? GFX_IMPL_UMMA_TMA : GFX_IMPL_SIMT;
+  if (impl == GFX_IMPL_AUTO) impl = dtype == GFX_F16 ? GFX_IMPL_UMMA_LEAN : GFX_IMPL_SIMT;
   if (impl == GFX_IMPL_UMMA || impl == GFX_IMPL_UMMA_SERIAL || impl == GFX_IMPL_UMMA_TMA ||
       impl == GFX_IMPL_UMMA_LEAN) {
     if (dtype != GFX_F16)

@@ -210,6 +210,23 @@ def test_input_linear(nat, dev, problem):
             assert np.abs(got - want).max() <= tol * max(1.0, np.abs(want).max())
 
 
+@pytest.mark.parametrize("skip,count", [(1, 1), (1, 2), (2, 5), (3, 1001), (0, 1003), (5, 4096)])
+def test_input_linear_unaligned_views_and_tails(nat, dev, problem, skip, count):
+    """The vectorised kernel needs 16-byte aligned feature rows; a view that
+    starts at an arbitrary node (what a chunk of a shard is) goes through the
+    scalar lead-in, and sizes that are not a multiple of 4 through the tail."""
+    x = _up(problem["shard"].node_features, dev)
+    for code in (0, 1):
+        full = _buf(x.shape[0], code, dev)
+        nat.check(nat.lib.gfx_input_linear(problem["handle"], x.data_ptr(), x.shape[0],
+                                           full.data_ptr(), code, _stream()))
+        part = _buf(count, code, dev)
+        nat.check(nat.lib.gfx_input_linear(problem["handle"], x[skip:].data_ptr(), count,
+                                           part.data_ptr(), code, _stream()))
+        torch.cuda.synchronize()
+        assert torch.equal(part, full[skip:skip + count])
+
+
 @pytest.mark.parametrize("code", [1, 0])
 def test_aggregate_layer0(nat, dev, problem, code):
     """K1 against the oracle's z0 given the oracle's h0 as input."""
