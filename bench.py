@@ -29,7 +29,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 from pathlib import Path
 
@@ -56,40 +55,62 @@ def measured_peaks():
                 source="fallback (B200_PROFILING.md: 6.65 TB/s, ~1.4 PFLOP/s sustained)")
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi SM clock / throttle reasons every 200 ms while running."""
+class ClockSampler:
+    """One `nvidia-smi -lms 50` process for the whole timed span (device-timed
+    steps and end-to-end steps): SM clock and throttle reasons every 50 ms."""
     QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        super().__init__(daemon=True)
-        self.index, self.rows, self._halt = index, [], threading.Event()
+        self.index, self.proc = index, None
 
-    def run(self):
-        while not self._halt.is_set():
-            try:
-                out = subprocess.run(
-                    ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}",
-                     "--format=csv,noheader,nounits"], capture_output=True, text=True,
-                    timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
-            except Exception:
-                pass
-            self._halt.wait(0.2)
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}",
+                 "--format=csv,noheader,nounits", "-lms", "50"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            time.sleep(0.3)                      # let the first samples arrive
+        except OSError:
+            self.proc = None
 
     def finish(self) -> dict:
-        self._halt.set()
-        self.join(timeout=6)
-        if not self.rows:
+        rows = []
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                out, _ = self.proc.communicate(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+                out, _ = self.proc.communicate()
+            for line in out.splitlines():
+                cells = [c.strip() for c in line.split(",")]
+                if len(cells) == 6:
+                    try:
+                        float(cells[0])
+                    except ValueError:
+                        continue
+                    rows.append(cells)
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(float(r[0]) for r in self.rows)
+        sm = sorted(float(r[0]) for r in rows)
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
         reasons = [n for k, n in enumerate(names)
-                   if any(r[2 + k].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]),
+                   if any(r[2 + k].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": float(rows[0][1]),
                 "reasons": reasons, "samples": len(sm)}
+
+
+def ncu_traffic(stage: str, nodes_per_launch: float):
+    """DRAM bytes per launch of a stage's kernel, from the committed ncu
+    capture (profiles/ncu_traffic.json: bytes per node of that capture, scaled
+    to this run's nodes per launch); None when no capture is recorded."""
+    path = ROOT / "profiles" / "ncu_traffic.json"
+    if not path.is_file():
+        return None
+    entry = json.loads(path.read_text()).get(stage)
+    return None if entry is None else entry["bytes_per_node"] * nodes_per_launch
 
 
 def build_workload(records: int, seed: int):
@@ -177,6 +198,8 @@ def main() -> None:
     ap.add_argument("--sample-records", type=int, default=3_000,
                     help="records per step of the CPU reference arm / cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--chunk-nodes", type=int, default=0,
+                    help="nodes per device chunk (0 = the encoder's default)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -203,6 +226,8 @@ def main() -> None:
     state, label = load_weights()
     shard, gen_s = build_workload(args.records, seed=rank)   # weak scaling: a shard per GPU
     encoder = Ginfinity.from_state(state, device=device)
+    if args.chunk_nodes > 0:
+        encoder.chunk_nodes = args.chunk_nodes
     nodes, edges = shard.node_count, shard.edge_count
 
     # ---------------- device-resident throughput (`value`) --------------------
@@ -210,13 +235,13 @@ def main() -> None:
     out = torch.empty((nodes, 128), dtype=torch.float16, device=device)
     step = lambda: encoder.encode_device_shard(  # noqa: E731
         dshard, max_batch_nodes=MAX_BATCH_NODES, max_batch_edges=MAX_BATCH_EDGES, out=out)
+    sampler = ClockSampler(local_rank)
+    sampler.start()                               # samples cover warm-up + timed steps (GPU busy)
     for _ in range(args.warmup):
         step()
     barrier()
     nat.launch_counts(reset=True)
     nat.profile_enable("mlp", "aggregate")
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
@@ -244,6 +269,8 @@ def main() -> None:
     d2h = nodes * 128 * 2
     run = lambda: encoder.encode_graphs(  # noqa: E731
         pinned, max_batch_nodes=MAX_BATCH_NODES, max_batch_edges=MAX_BATCH_EDGES)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(max(1, args.warmup - 1)):
         result = run()
     assert len(result) == shard.record_count and result[0].dtype == np.float16
@@ -254,6 +281,7 @@ def main() -> None:
         run()
     torch.cuda.synchronize()
     e2e_s = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
+    clocks_e2e = sampler.finish()
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = total_nodes.item() * args.steps / e2e_s.item()
@@ -265,16 +293,18 @@ def main() -> None:
         mlp_tflops = node_layers * FLOP_PER_NODE_MLP / (mlp_ms * 1e-3) / 1e12 if mlp_ms else 0.0
         agg_gbs = node_layers * BYTES_PER_NODE_AGG / (agg_ms * 1e-3) / 1e9 if agg_ms else 0.0
         step_ms_rank = ev0.elapsed_time(ev1) / args.steps
-        roofline_mlp = {"kernel": "umma_mlp_kernel (K2: MLP + LayerNorm + residual, tcgen05)",
+        roofline_mlp = {"kernel": "umma4_mlp_kernel (K2: MLP + LayerNorm + residual, tcgen05 + TMA)",
                         "bound": "tensor", "achieved": mlp_tflops, "peak": peaks["tflops"],
                         "unit": "TFLOP/s", "frac": mlp_tflops / peaks["tflops"],
-                        "traffic": None, "launches": mlp_calls,
+                        "traffic": ncu_traffic("mlp", node_layers / max(mlp_calls, 1)),
+                        "launches": mlp_calls,
                         "avg_launch_ms": mlp_ms / max(mlp_calls, 1),
                         "share_of_step": mlp_ms / args.steps / step_ms_rank,
                         "peak_source": peaks["source"]}
-        roofline_agg = {"kernel": "aggregate_kernel (K1: CSR gather + table + ReLU + self term)",
+        roofline_agg = {"kernel": "aggregate_f16_kernel (K1: CSR gather + table + ReLU + self term)",
                         "bound": "hbm", "achieved": agg_gbs, "peak": peaks["hbm_gbs"],
-                        "unit": "GB/s", "frac": agg_gbs / peaks["hbm_gbs"], "traffic": None,
+                        "unit": "GB/s", "frac": agg_gbs / peaks["hbm_gbs"],
+                        "traffic": ncu_traffic("aggregate", node_layers / max(agg_calls, 1)),
                         "launches": agg_calls, "avg_launch_ms": agg_ms / max(agg_calls, 1),
                         "share_of_step": agg_ms / args.steps / step_ms_rank,
                         "peak_source": peaks["source"]}
@@ -289,7 +319,7 @@ def main() -> None:
                        "nodes_per_gpu": nodes, "edges_per_gpu": edges,
                        "microbatches_per_step": microbatches,
                        "chunk_nodes": encoder.chunk_nodes},
-            "clocks": clocks,
+            "clocks": clocks, "clocks_e2e": clocks_e2e,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s.item() / args.steps * 1e3},
             "gpu_launches": int(sum(launches.values())),

@@ -51,7 +51,7 @@ struct Smem {
   static constexpr int off_bar = off_d2 + kD2Slots * kDbTile * 4;
   static constexpr int off_tmem = off_bar + kNumBars * 8;
   static constexpr int off_list = (off_tmem + 8 + 15) & ~15;
-  static constexpr int total(int kc) { return off_list + kc * kQTile * 8; }
+  static constexpr int total(int kc) { return off_list + kc * kQTile * 8; }   // per-thread sorted lists
 };
 static_assert(Smem::total(kMaxCand) <= 232448, "exceeds the 227 KB shared-memory limit of sm_100");
 
@@ -111,6 +111,12 @@ __device__ __noinline__ float list_insert(float *ls, int32_t *li, int kc, float 
   return ls[(kc - 1) * kQTile];
 }
 
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
 template <int METRIC>
 __global__ void __launch_bounds__(kWarps * 32, 1)
 topk_scan_kernel(const __grid_constant__ Maps maps, const Args p) {
@@ -121,7 +127,6 @@ topk_scan_kernel(const __grid_constant__ Maps maps, const Args p) {
   uint64_t *bar = reinterpret_cast<uint64_t *>(smem + L::off_bar);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::off_tmem);
   float *list_s = reinterpret_cast<float *>(smem + L::off_list);
-  int32_t *list_i = reinterpret_cast<int32_t *>(list_s + p.kc * kQTile);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (warp == kMmaWarp) {
@@ -213,9 +218,10 @@ topk_scan_kernel(const __grid_constant__ Maps maps, const Args p) {
     const int quad = warp & 3, half = warp >> 2;
     const int row = half * 128 + quad * 32 + lane;          // query inside the item
     const uint32_t tbase = tmem + (uint32_t(quad * 32) << 16) + half * 128;
-    float *ls = list_s + tid;
-    int32_t *li = list_i + tid;
     const int kc = p.kc;
+    const int32_t rows = int32_t(p.num_rows);
+    float *ls = list_s + tid;
+    int32_t *li = reinterpret_cast<int32_t *>(list_s + kc * kQTile) + tid;
     const float ninf = -INFINITY;
     uint32_t it = 0;
     for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
@@ -251,24 +257,32 @@ topk_scan_kernel(const __grid_constant__ Maps maps, const Args p) {
             v[4 * c4 + 3] = fmaf(2.f, v[4 * c4 + 3], -n.w);
           }
         }
-        const int64_t left = p.num_rows - int64_t(base);
-        if (METRIC == 1 || left >= kDbTile) {
-          // rows past the end carry |d|^2 = +inf in the L2 case, so no mask is needed
+        // hot path: the maximum of the 128 scores as four independent chains of
+        // 3-input maxima.  (Rows past the end of the database -- zero-filled by
+        // TMA -- may raise it in the last tile; offer() drops them by index.)
+        float t4[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          t4[q] = fmaxf(v[32 * q], v[32 * q + 1]);
+#pragma unroll
+          for (int c = 2; c < 32; c += 2) t4[q] = max3(t4[q], v[32 * q + c], v[32 * q + c + 1]);
+        }
+        const float top = fmaxf(fmaxf(t4[0], t4[1]), fmaxf(t4[2], t4[3]));
+        const bool hit = top > thr;
+        if (hit) {
+          // rare once the list has warmed up: find the values above the threshold
 #pragma unroll
           for (int g = 0; g < kDbTile / 8; ++g) {
-            const float m = fmaxf(fmaxf(fmaxf(v[8 * g], v[8 * g + 1]), fmaxf(v[8 * g + 2], v[8 * g + 3])),
-                                  fmaxf(fmaxf(v[8 * g + 4], v[8 * g + 5]), fmaxf(v[8 * g + 6], v[8 * g + 7])));
-            if (m > thr) {
+            const float gm = fmaxf(max3(v[8 * g], v[8 * g + 1], v[8 * g + 2]),
+                                   max3(v[8 * g + 3], v[8 * g + 4],
+                                        max3(v[8 * g + 5], v[8 * g + 6], v[8 * g + 7])));
+            if (gm > thr) {
 #pragma unroll
               for (int j = 0; j < 8; ++j)
-                if (v[8 * g + j] > thr) thr = list_insert(ls, li, kc, v[8 * g + j], base + 8 * g + j);
+                if (v[8 * g + j] > thr && base + 8 * g + j < rows)
+                  thr = list_insert(ls, li, kc, v[8 * g + j], base + 8 * g + j);
             }
           }
-        } else {
-          const int valid = int(left);
-#pragma unroll
-          for (int c = 0; c < kDbTile; ++c)
-            if (c < valid && v[c] > thr) thr = list_insert(ls, li, kc, v[c], base + c);
         }
       }
       // hand the segment's candidates to the finish kernel
@@ -450,7 +464,7 @@ template <int METRIC>
 static int launch_scan(const Maps &maps, const Args &a, int64_t items, cudaStream_t st) {
   const int smem = Smem::total(a.kc);
   GFX_CUDA(cudaFuncSetAttribute(topk_scan_kernel<METRIC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                Smem::total(kMaxCand)));
+                                232448));
   const int grid = int(items < kNumSMs ? items : kNumSMs);
   topk_scan_kernel<METRIC><<<grid, kWarps * 32, smem, st>>>(maps, a);
   GFX_LAUNCH_CHECK();
