@@ -198,6 +198,8 @@ def main() -> None:
     ap.add_argument("--sample-records", type=int, default=3_000,
                     help="records per step of the CPU reference arm / cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-records-e2e", dest="records_e2e", action="store_false",
+                    help="skip the encode_many (records -> embeddings) measurement")
     ap.add_argument("--chunk-nodes", type=int, default=0,
                     help="nodes per device chunk (0 = the encoder's default)")
     args = ap.parse_args()
@@ -286,6 +288,33 @@ def main() -> None:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = total_nodes.item() * args.steps / e2e_s.item()
 
+    # ------------- records -> embeddings (`encode_many`, graphs built on the GPU) ---------
+    from_records = None
+    if args.records_e2e:
+        from ginfinity_b200.synthetic import synthetic_records
+        recs = synthetic_records(rank, args.records)          # the same RNAs the shard was built from
+        assert sum(len(r.sequence) for r in recs) == nodes
+        run_many = lambda: encoder.encode_many(  # noqa: E731
+            recs, max_batch_nodes=MAX_BATCH_NODES, max_batch_edges=MAX_BATCH_EDGES)
+        res = run_many()
+        assert len(res) == len(recs)
+        del res
+        barrier()
+        nat.launch_counts(reset=True)
+        t0 = time.perf_counter()
+        for _ in range(2):
+            run_many()
+        torch.cuda.synchronize()
+        many_s = torch.tensor([(time.perf_counter() - t0) / 2], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(many_s, op=dist.ReduceOp.MAX)
+        from_records = {"value": total_nodes.item() / many_s.item(), "unit": UNIT,
+                        "ms_per_step": many_s.item() * 1e3,
+                        "h2d_bytes_per_step": 2 * nodes + 8 * (shard.record_count + 1),
+                        "d2h_bytes_per_step": d2h,
+                        "what": "Ginfinity.encode_many(records): dot-bracket strings in, host "
+                                "arrays out; graphs built by gfx_graph_count/fill on the GPU"}
+
     if rank == 0:
         peaks = measured_peaks()
         # per-launch algorithmic work / average launch duration == totals ratio
@@ -324,6 +353,7 @@ def main() -> None:
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s.item() / args.steps * 1e3},
             "gpu_launches": int(sum(launches.values())),
             "gpu_launches_by_stage": launches,
+            "e2e_from_records": from_records,
             "roofline": dominant, "roofline_other": other,
             "setup": {"workload_generation_s": gen_s, "host_cpus": os.cpu_count()},
         }

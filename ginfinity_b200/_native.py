@@ -51,6 +51,10 @@ _SIGNATURES = {
     "gfx_pack_microbatches": (C.c_int, [_p, _p, _i64, _i64, _i64, _p, _p, _p, _p]),
     "gfx_csr_workspace_bytes": (_sz, [_i64, _i64]),
     "gfx_csr_build": (C.c_int, [_p, _p, _p, _i64, _i64, _i32, _p, _p, _p, _p, _sz, _p]),
+    "gfx_graph_workspace_bytes": (_sz, [_i64, _i64]),
+    "gfx_graph_count": (C.c_int, [_p, _p, _i64, _i64, C.c_int, _p, _p, _p, _sz, _p]),
+    "gfx_graph_fill": (C.c_int, [_p, _p, _p, _p, _i64, _i64, _i64, C.c_int, _p, _p, _p, _p, _p,
+                                 _p, _p, _p, _p, _sz, _p]),
     "gfx_core_rows_workspace_bytes": (_sz, [_i64]),
     "gfx_core_rows": (C.c_int, [_p, _i64, _p, _p, _p, _sz, _p]),
     "gfx_input_linear": (C.c_int, [_p, _p, _i64, _p, C.c_int, _p]),
@@ -71,7 +75,7 @@ _SIGNATURES = {
 }
 
 STAGES = ("pack", "csr", "core_rows", "input", "aggregate", "mlp", "head",
-          "fused_layer", "topk")
+          "fused_layer", "topk", "build")
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

@@ -39,6 +39,13 @@ int fail(int code, const std::string &msg);
 
 inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// gfx_graph.cu: out[i] = sum(in[0..i)); block_sums holds scan_blocks(n) ints;
+// *grand_total (optional, device) receives the sum of all n inputs.
+int scan_blocks(int64_t n);
+int exclusive_scan(const int *in, int *out, int64_t n, int *block_sums, int64_t *grand_total,
+                   cudaStream_t st);
+inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
+
 // Counts `launches` kernel launches for `stage`; if the stage is being
 // profiled, brackets the enclosing scope with CUDA events on `st`.
 class StageScope {

@@ -90,11 +90,11 @@ scan_add_kernel(int *__restrict__ out, const int *__restrict__ block_sums, int64
     if (base + i < n) out[base + i] += add;
 }
 
-static inline int scan_blocks(int64_t n) { return int((n + kScanTile - 1) / kScanTile); }
+int scan_blocks(int64_t n) { return int((n + kScanTile - 1) / kScanTile); }
 
 // out[i] = sum(in[0..i)) for i in [0,n).  block_sums: scan_blocks(n) ints.
-static int exclusive_scan(const int *in, int *out, int64_t n, int *block_sums,
-                          int64_t *grand_total, cudaStream_t st) {
+int exclusive_scan(const int *in, int *out, int64_t n, int *block_sums,
+                   int64_t *grand_total, cudaStream_t st) {
   if (n == 0) return GFX_OK;
   int nb = scan_blocks(n);
   scan_local_kernel<<<nb, kScanThreads, 0, st>>>(in, out, block_sums, n);
@@ -245,7 +245,6 @@ static inline int grid_for(int64_t n, int threads) {
   return int(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
-static inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 
 }  // namespace gfx
 

@@ -120,6 +120,42 @@ int gfx_csr_build(const int32_t *edge_src, const int32_t *edge_dst,
                   size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------
+ * K6  graph construction on the device, for full-molecule records of the
+ * bundled graph specification.  Replaces GraphBuilder._build_full,
+ * _pair_table and GraphShard.from_graphs (graph.py:494-561, 737-747,
+ * 376-412); every output array is bit-identical to the reference's.
+ *   sequences / structures: the records' strings concatenated, one ASCII
+ *     byte per nucleotide ('A','C','G','U' / '(', ')', '.'), uint8 [N]
+ *   node_ptr: int64 [B+1] prefix sums of the record lengths
+ *   pos_table: float32 [T,2] (sin, cos) rows tabulated ON THE HOST with NumPy
+ *     for every distinct record length (the reference's float32 expression,
+ *     graph.py:510-514, is not correctly rounded, so it cannot be recomputed
+ *     on the device bit for bit); pos_offset: int64 [B], first table row of
+ *     each record
+ * Two phases, because the edge total is only known after pairing:
+ *   gfx_graph_count  -> edge_ptr int64 [B+1] (edge_ptr[B] = E) and *status
+ *   (host reads E and allocates edge_index int32 [2,E], edge_types uint8 [E])
+ *   gfx_graph_fill   -> node_features float32 [N,7], edge_index (global node
+ *     indices), edge_types, optional residue_index int32 [N] / node_roles
+ *     uint8 [N] (may be NULL)
+ * Both calls take the same workspace.  *status (device int32) collects
+ * GFX_GRAPH_BAD_BASE / UNBALANCED / BAD_STRUCTURE bits.
+ * ------------------------------------------------------------------------ */
+enum { GFX_GRAPH_BAD_BASE = 1, GFX_GRAPH_UNBALANCED = 2, GFX_GRAPH_BAD_STRUCTURE = 4 };
+size_t gfx_graph_workspace_bytes(int64_t num_nodes, int64_t num_records);
+int gfx_graph_count(const uint8_t *structures, const int64_t *node_ptr,
+                    int64_t num_records, int64_t num_nodes, int skip2,
+                    int64_t *edge_ptr, int32_t *status, void *workspace,
+                    size_t workspace_bytes, void *stream);
+int gfx_graph_fill(const uint8_t *sequences, const uint8_t *structures,
+                   const int64_t *node_ptr, const int64_t *edge_ptr,
+                   int64_t num_records, int64_t num_nodes, int64_t num_edges,
+                   int skip2, const float *pos_table, const int64_t *pos_offset,
+                   float *node_features, int32_t *edge_index, uint8_t *edge_types,
+                   int32_t *residue_index, uint8_t *node_roles, int32_t *status,
+                   void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------
  * Core-row map.  Replaces the per-record boolean masks of api.py:253-259:
  * out_row[i] = rank of node i among nodes with node_roles == 0, or -1 for
  * context nodes; n_core receives the number of core nodes (device int64).
@@ -212,7 +248,8 @@ enum {
   GFX_STAGE_HEAD = 6,
   GFX_STAGE_FUSED_LAYER = 7,
   GFX_STAGE_TOPK = 8,
-  GFX_NUM_STAGES = 9
+  GFX_STAGE_BUILD = 9,
+  GFX_NUM_STAGES = 10
 };
 int gfx_profile_enable(uint32_t stage_mask);
 int gfx_profile_read(int stage, double *total_ms, int64_t *timed_calls, int reset);

@@ -207,3 +207,53 @@ def test_simt_and_tcgen05_paths_agree(gb, syn16):
     b = np.concatenate(syn16.encode_graphs(shard, embedding_dtype=np.float32))
     syn16.impl = nat.IMPL_AUTO
     assert np.abs(a - b).max() <= 2e-3
+
+
+# ---- BASELINE configs[2]: long RNAs, dense long-range pairs, big microbatches -----
+def test_long_rna_shard_matches_oracle_across_microbatch_limits(gb, syn16, synthetic_state):
+    """1-10 knt records (past RNA's 4096-nt cap, built from duck-typed records
+    the way SURVEY 8d C3 prescribes): irregular aggregation with pairs that
+    span thousands of rows, and microbatch limits from one graph per batch to
+    the whole shard in one."""
+    from ginfinity_b200.synthetic import synthetic_records
+    recs = synthetic_records(1, 6, lo=1000, hi=10000, log_uniform=True, workers=1)
+    shard = gb.GraphBuilder().build_shard(recs)
+    longest, most_edges = int(np.diff(shard.node_ptr).max()), int(np.diff(shard.edge_ptr).max())
+    assert longest > 4096
+    span = np.abs(shard.edge_index[0].astype(np.int64) - shard.edge_index[1])
+    assert span.max() > 1000                       # genuinely long-range pairs
+    fw = O.fold_state(synthetic_state)
+    want = np.concatenate(O.encode_shard(fw, shard, max_batch_nodes=1 << 20,
+                                         max_batch_edges=1 << 23,
+                                         embedding_dtype=np.float32, half_storage=True))
+    outs = []
+    for nodes, edges in ((longest, most_edges), (60_000, 300_000), (1 << 20, 1 << 23)):
+        outs.append(np.concatenate(syn16.encode_graphs(
+            shard, max_batch_nodes=nodes, max_batch_edges=edges, embedding_dtype=np.float32)))
+        lengths, ecounts = np.diff(shard.node_ptr).tolist(), np.diff(shard.edge_ptr).tolist()
+        assert np.array_equal(syn16.last_microbatch_bounds,
+                              O.pack_microbatches(lengths, ecounts, nodes, edges))
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[1], outs[2])
+    assert np.abs(outs[0] - want).max() <= 3e-3
+    assert _cos(outs[0], want).min() >= 0.9999
+    assert np.abs(np.linalg.norm(outs[0].astype(np.float64), axis=1) - 1).max() <= 1e-6
+    with pytest.raises(ValueError, match="max_batch_nodes"):
+        syn16.encode_graphs(shard, max_batch_nodes=longest - 1)
+
+
+def test_maximum_length_record_and_tiny_records(gb, syn16, synthetic_state):
+    """RNA's own limits: one 4096-nt record next to 1-, 2- and 3-nt records
+    (0, 2 and 8 edges) in the same shard."""
+    rng = np.random.default_rng(5)
+    from ginfinity_b200.synthetic import random_structure
+    big = "".join(rng.choice(list("ACGU"), 4096))
+    recs = [gb.RNA("big", big, random_structure(rng, 4096)), gb.RNA("one", "A", "."),
+            gb.RNA("two", "AC", ".."), gb.RNA("three", "GAC", "(.)")]
+    shard = gb.GraphBuilder().build_shard(recs)
+    assert np.diff(shard.edge_ptr).tolist()[1:] == [0, 2, 8]
+    got = syn16.encode_graphs(shard, embedding_dtype=np.float32)
+    want = O.encode_shard(O.fold_state(synthetic_state), shard, embedding_dtype=np.float32,
+                          half_storage=True)
+    assert [g.shape for g in got] == [(4096, 128), (1, 128), (2, 128), (3, 128)]
+    for g, w in zip(got, want):
+        assert np.abs(g - w).max() <= 3e-3
