@@ -56,8 +56,17 @@ def position_table(lengths: np.ndarray):
     return table, starts[:-1][inverse]
 
 
+def _pinned_bytes(text: str) -> torch.Tensor:
+    """ASCII characters of `text` in page-locked memory (so the copy to the
+    device is a real asynchronous DMA)."""
+    raw = text.encode("ascii")
+    t = torch.empty(len(raw), dtype=torch.uint8, pin_memory=True)
+    t.numpy()[:] = np.frombuffer(raw, np.uint8)
+    return t
+
+
 def build_device_shard(records: Sequence, device, spec: GraphSpec = None,
-                       *, with_node_metadata: bool = False) -> DeviceShard:
+                       *, with_node_metadata: bool = False, lengths=None) -> DeviceShard:
     """Device-resident shard of full-molecule graphs for `records` (objects
     with `.sequence` and `.structure`).  Raises GraphValidationError for
     characters outside ACGU / ().  and for unbalanced structures."""
@@ -72,16 +81,19 @@ def build_device_shard(records: Sequence, device, spec: GraphSpec = None,
     sequences = [r.sequence for r in records]
     structures = [r.structure for r in records]
     B = len(records)
-    lengths = np.fromiter((len(s) for s in sequences), np.int64, B)
-    if np.any(lengths < 1) or any(len(t) != n for t, n in zip(structures, lengths.tolist())):
+    if lengths is None:
+        lengths = np.fromiter(map(len, sequences), np.int64, B)
+    if np.any(lengths < 1) or list(map(len, structures)) != lengths.tolist():
         raise GraphValidationError("sequence and structure lengths must match and be positive")
     node_ptr = np.zeros(B + 1, np.int64)
     np.cumsum(lengths, out=node_ptr[1:])
     N = int(node_ptr[-1])
     if N > 1 << 30:
         raise GraphValidationError("shard exceeds 2^30 nucleotides")
-    seq = np.frombuffer(bytearray("".join(sequences), "ascii"), np.uint8)
-    dbn = np.frombuffer(bytearray("".join(structures), "ascii"), np.uint8)
+    try:
+        seq, dbn = _pinned_bytes("".join(sequences)), _pinned_bytes("".join(structures))
+    except UnicodeEncodeError as exc:
+        raise GraphValidationError("sequence contains characters outside ACGU") from exc
     table, offset = position_table(lengths)
     skip2 = 1 if "skip2" in spec.extra_edges else 0
 
@@ -89,7 +101,8 @@ def build_device_shard(records: Sequence, device, spec: GraphSpec = None,
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream().cuda_stream
         up = lambda a: torch.from_numpy(a).to(dev, non_blocking=True)  # noqa: E731
-        seq_d, dbn_d, node_ptr_d = up(seq), up(dbn), up(node_ptr)
+        seq_d, dbn_d = seq.to(dev, non_blocking=True), dbn.to(dev, non_blocking=True)
+        node_ptr_d = up(node_ptr)
         table_d, offset_d = up(table), up(offset)
         edge_ptr_d = torch.empty(B + 1, dtype=torch.int64, device=dev)
         status = torch.empty(1, dtype=torch.int32, device=dev)

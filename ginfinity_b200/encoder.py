@@ -43,7 +43,7 @@ from .weights import (BUNDLED_CONFIG, EncoderConfig, FoldedWeights,
                       ModelIntegrityError, default_model_dir, fold,
                       load_checkpoint, parameter_count)
 
-DEFAULT_CHUNK_NODES = 1 << 19
+DEFAULT_CHUNK_NODES = 1 << 20
 
 
 def _embedding_dtype(value) -> np.dtype:
@@ -248,22 +248,11 @@ class Ginfinity:
             return []
         from . import device_builder
         if self.device_builder and device_builder.supports(self._graph_spec, records):
-            # full-molecule records: build the graphs on the GPU (2 B/nt over
-            # PCIe instead of 69 B/nt) and stream the embeddings out
-            _check_unique_ids(records)
-            dtype = _embedding_dtype(embedding_dtype)
-            with torch.cuda.device(self._torch_device), torch.inference_mode():
-                ds = device_builder.build_device_shard(records, self._torch_device,
-                                                       self._graph_spec)
-                self._check_request(ds.spec, ds.max_nodes_per_record, ds.max_edges_per_record,
-                                    max_batch_nodes, max_batch_edges, dtype)
-                out_code = nat.GFX_F16 if dtype == np.float16 else nat.GFX_F32
-                table, core_ptr, rows = self._encode_resident(
-                    ds, int(max_batch_nodes), int(max_batch_edges), out_code,
-                    presplit=(dtype.itemsize <= 4))
-            if table.dtype != dtype:
-                return split_rows(table.astype(dtype), core_ptr)
-            return rows
+            # full-molecule records: graphs are built on the GPU (2 B/nt over PCIe
+            # instead of 69 B/nt) group by group, the host preparing group g+1
+            # while the device encodes group g and copies out group g-1
+            return self._encode_records(records, int(max_batch_nodes), int(max_batch_edges),
+                                        _embedding_dtype(embedding_dtype))
         shard = GraphBuilder(
             self._graph_spec, keep_paired_neighbours=keep_paired_neighbours,
             context_hops=context_hops).build_shard(records)
@@ -320,7 +309,7 @@ class Ginfinity:
 
     # -- host shard -> host embeddings, copies overlapped with compute -----------
     def _plan(self, node_ptr_d, edge_ptr_d, B, max_batch_nodes, max_batch_edges,
-              stream) -> np.ndarray:
+              stream) -> np.ndarray:  # `stream`: raw handle of the CURRENT torch stream
         """K4 on the device, then one small read-back: rows of (record stop,
         node offset, edge offset) per microbatch boundary."""
         dev = self._torch_device
@@ -471,32 +460,93 @@ class Ginfinity:
         main.synchronize()
         return table, core_ptr, rows
 
-    def _encode_resident(self, ds: "DeviceShard", max_batch_nodes: int, max_batch_edges: int,
-                         out_code: int, presplit=True):
-        """`_encode_streaming` for a shard that is already in HBM: no input
-        copies; chunk c's embeddings are copied out while chunk c+1 runs."""
+    records_group_nodes = 1 << 22      # nucleotides per host-prep / device-build group
+
+    def _encode_records(self, records: list, max_batch_nodes: int, max_batch_edges: int,
+                        dtype: np.dtype) -> list:
+        """records -> embeddings with the graphs built on the device.
+
+        The node limit is checked before any device work, like the reference
+        (api.py:196-210); the edge limit as soon as a group's edge counts exist
+        (they come out of the device builder's pairing pass)."""
+        from . import device_builder as dbuild
+        if max_batch_nodes <= 0 or max_batch_edges <= 0:
+            raise ValueError("batch node and edge limits must be positive")
+        ids = [r.identifier for r in records]
+        if len(set(ids)) != len(ids):
+            from .graph import GraphValidationError
+            raise GraphValidationError("duplicate identifiers in graph shard")
+        B = len(records)
+        lengths = np.fromiter(map(len, (r.sequence for r in records)), np.int64, B)
+        if int(lengths.max()) > max_batch_nodes:
+            raise ValueError("max_batch_nodes is smaller than the longest graph")
+        node_ptr = np.zeros(B + 1, np.int64)
+        np.cumsum(lengths, out=node_ptr[1:])
+        N = int(node_ptr[-1])
+        out_code = nat.GFX_F16 if dtype == np.float16 else nat.GFX_F32
+        tdtype = torch.float16 if out_code == nat.GFX_F16 else torch.float32
+        # groups of whole records, about records_group_nodes nucleotides each
+        cuts = [0]
+        while cuts[-1] < B:
+            target = node_ptr[cuts[-1]] + self.records_group_nodes
+            nxt = int(np.searchsorted(node_ptr, target, side="right")) - 1
+            cuts.append(min(B, max(nxt, cuts[-1] + 1)))
         dev = self._torch_device
+        with torch.cuda.device(dev), torch.inference_mode():
+            host = torch.empty((N, 128), dtype=tdtype, pin_memory=True)
+            main = torch.cuda.current_stream()
+            if not hasattr(self, "_streams"):
+                self._streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+            s_build, s_out = self._streams
+            s_build.wait_stream(main)
+            s_out.wait_stream(main)
+            state = dict(out_free=[None, None], turn=0, keep=[])
+            bounds = [0]
+            table = host.numpy()
+            presplit = dtype.itemsize <= 4
+            rows = []
+            for a, b in zip(cuts[:-1], cuts[1:]):
+                with torch.cuda.stream(s_build):
+                    ds = dbuild.build_device_shard(records[a:b], dev, self._graph_spec,
+                                                   lengths=lengths[a:b])
+                    if ds.max_edges_per_record > max_batch_edges:
+                        torch.cuda.synchronize()
+                        raise ValueError("max_batch_edges is smaller than the largest graph")
+                    plan = self._plan(ds.node_ptr, ds.edge_ptr, b - a, max_batch_nodes,
+                                      max_batch_edges, s_build.cuda_stream)
+                    built = torch.cuda.Event()
+                    built.record(s_build)
+                bounds.extend((plan[0][1:] + a).tolist())
+                main.wait_event(built)
+                self._enqueue_resident(ds, plan, host[int(node_ptr[a]):int(node_ptr[b])],
+                                       out_code, state)
+                if presplit:        # per-record views, made while the device is busy
+                    rows.extend(split_rows(table, node_ptr[a:b + 1]))
+            self.last_microbatch_bounds = np.asarray(bounds, np.int64)
+            main.wait_stream(s_out)
+            main.synchronize()
+            state["keep"].clear()
+        if table.dtype != dtype:
+            return split_rows(table.astype(dtype), node_ptr)
+        return rows
+
+    def _enqueue_resident(self, ds: "DeviceShard", plan: np.ndarray, host: torch.Tensor,
+                          out_code: int, state: dict) -> None:
+        """Enqueue the forward of a device-resident shard of full molecules on
+        the current stream, chunk by chunk; each chunk's embeddings are copied
+        into `host` ([nodes, 128], pinned) on the copy-out stream while the
+        next chunk runs.  Does not synchronise."""
         lib = nat.lib
-        B, N = ds.record_count, ds.node_count
         act = nat.GFX_F32 if self.full_precision else nat.GFX_F16
         tdtype = torch.float16 if out_code == nat.GFX_F16 else torch.float32
         esize = 2 if out_code == nat.GFX_F16 else 4
-        if ds.node_roles is not None:
-            raise ValueError("_encode_resident expects a shard of full molecules")
-        core_ptr = ds.core_ptr_host
-        host = torch.empty((N, 128), dtype=tdtype, pin_memory=True)
         main = torch.cuda.current_stream()
-        if not hasattr(self, "_streams"):
-            self._streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
         s_out = self._streams[1]
-        plan = self._plan(ds.node_ptr, ds.edge_ptr, B, max_batch_nodes, max_batch_edges,
-                          main.cuda_stream)
         chunks = self._chunks(plan)
         node_at, edge_at = plan[1], plan[2]
         max_n = max(int(node_at[b] - node_at[a]) for a, b in chunks)
         max_e = max(int(edge_at[b] - edge_at[a]) for a, b in chunks)
         outs = [self._scratch.get(f"out{k}", 128 * esize * max_n) for k in range(2)]
-        out_free = [torch.cuda.Event(), torch.cuda.Event()]
         row_ptr = self._scratch.get("row_ptr", 4 * (max_n + 1))
         col_src = self._scratch.get("col_src", 4 * max(max_e, 1))
         col_type = self._scratch.get("col_type", max(max_e, 1))
@@ -504,15 +554,17 @@ class Ginfinity:
         enc_ws_bytes = lib.gfx_encode_workspace_bytes(max_n, act)
         csr_ws = self._scratch.get("csr_ws", csr_ws_bytes)
         enc_ws = self._scratch.get("enc_ws", enc_ws_bytes)
-        s_out.wait_stream(main)
+        state["keep"].append((ds, outs, row_ptr, col_src, col_type, csr_ws, enc_ws))
         ei = ds.edge_index
-        for c, (a, b) in enumerate(chunks):
+        for a, b in chunks:
             n0, n1 = int(node_at[a]), int(node_at[b])
             e0, e1 = int(edge_at[a]), int(edge_at[b])
             n, e = n1 - n0, e1 - e0
-            out = outs[c & 1]
-            if c >= 2:
-                main.wait_event(out_free[c & 1])
+            turn = state["turn"]
+            state["turn"] = turn ^ 1
+            out = outs[turn]
+            if state["out_free"][turn] is not None:
+                main.wait_event(state["out_free"][turn])
             nat.check(lib.gfx_csr_build(
                 ei[0, e0:].data_ptr() if e else None, ei[1, e0:].data_ptr() if e else None,
                 ds.edge_types[e0:].data_ptr() if e else None, n, e, n0, row_ptr.data_ptr(),
@@ -529,12 +581,9 @@ class Ginfinity:
                 s_out.wait_event(ready)
                 src = out[:n * 128 * esize].view(tdtype).view(n, 128)
                 host[n0:n1].copy_(src, non_blocking=True)
-                out_free[c & 1].record(s_out)
-        main.wait_stream(s_out)
-        table = host.numpy()
-        rows = split_rows(table, core_ptr) if presplit else None
-        main.synchronize()
-        return table, core_ptr, rows
+                free = torch.cuda.Event()
+                free.record(s_out)
+                state["out_free"][turn] = free
 
     def encode_device_shard(self, ds: DeviceShard, *, max_batch_nodes=60_000,
                             max_batch_edges=300_000, out_dtype=nat.GFX_F16,

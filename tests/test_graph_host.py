@@ -329,3 +329,28 @@ def test_record_partitioning_respects_record_and_node_limits():
         list(g.partition_records(records, max_records=2, max_nodes=3))
     with pytest.raises(ValueError, match="positive"):
         list(g.partition_records(records, max_records=0))
+
+
+# ---- host side of the device graph builder (K6) ---------------------------------------
+def test_position_table_reproduces_the_builder_columns_bit_for_bit():
+    """The device builder gathers sin/cos from a per-length table made on the
+    host; it must hold exactly what the host builder (and the reference,
+    graph.py:510-514) computes per record."""
+    pytest.importorskip("torch")
+    import ginfinity_b200 as g
+    try:
+        from ginfinity_b200 import device_builder as db
+    except ImportError as exc:                      # libgfx.so not built
+        pytest.skip(str(exc))
+    records = random_records(11, 300) + [g.RNA("one", "A", "."), g.RNA("two", "AC", "..")]
+    shard = g.GraphBuilder().build_shard(records)
+    lengths = np.diff(shard.node_ptr)
+    table, offset = db.position_table(lengths)
+    assert table.dtype == np.float32 and offset.dtype == np.int64
+    assert table.shape[0] == int(np.unique(lengths).sum())
+    rows = np.concatenate([np.arange(o, o + n) for o, n in zip(offset.tolist(), lengths.tolist())])
+    assert np.array_equal(table[rows].view(np.uint32),
+                          np.ascontiguousarray(shard.node_features[:, 5:7]).view(np.uint32))
+    assert db.supports(g.GraphSpec(), records)
+    assert not db.supports(g.GraphSpec(), records + [g.RNA("w", "ACGUACGU", "((....))", start=2, end=5)])
+    assert not db.supports(g.GraphSpec(positional=False), records)
