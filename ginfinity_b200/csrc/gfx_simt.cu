@@ -216,16 +216,14 @@ __device__ __forceinline__ void add_message(float *acc, const uint4 &nb, const u
 // rows finish in a plain loop.
 constexpr int kWin = 5;
 
-// Edge types of the window are kept packed, 4 bits each (edge_dim <= 16).
 __device__ __forceinline__ void load_window(const int32_t *__restrict__ col_src,
                                             const uint8_t *__restrict__ col_type, int beg, int end,
-                                            int *s, uint32_t &types) {
-  types = 0;
+                                            int *s, int *t) {
 #pragma unroll
   for (int u = 0; u < kWin; ++u) {
     const bool ok = beg + u < end;
     s[u] = ok ? col_src[beg + u] : 0;
-    types |= (ok ? uint32_t(col_type[beg + u]) : 0u) << (4 * u);
+    t[u] = ok ? int(col_type[beg + u]) : 0;
   }
 }
 
@@ -251,8 +249,7 @@ aggregate_f16_kernel(const __half *__restrict__ h, const int32_t *__restrict__ r
     beg1 = row_ptr[i1];
     end1 = row_ptr[i1 + 1];
   }
-  int s[kWin];
-  uint32_t t;
+  int s[kWin], t[kWin];
   load_window(col_src, col_type, beg, end, s, t);
   while (true) {
     const int64_t i2 = i1 + stride;
@@ -261,8 +258,7 @@ aggregate_f16_kernel(const __half *__restrict__ h, const int32_t *__restrict__ r
       beg2 = row_ptr[i2];
       end2 = row_ptr[i2 + 1];
     }
-    int s1[kWin];
-    uint32_t t1;
+    int s1[kWin], t1[kWin];
     load_window(col_src, col_type, beg1, end1, s1, t1);   // stage 2: indices one node ahead
     const uint4 self = hv[i * 16];                  // stage 3: this node's rows
     const int deg = end - beg;
@@ -274,7 +270,7 @@ aggregate_f16_kernel(const __half *__restrict__ h, const int32_t *__restrict__ r
     for (int c = 0; c < 8; ++c) acc[c] = 0.f;
 #pragma unroll
     for (int u = 0; u < kWin; ++u)
-      if (u < deg) add_message(acc, nb[u], tv[((t >> (4 * u)) & 15u) * 16]);
+      if (u < deg) add_message(acc, nb[u], tv[t[u] * 16]);
     for (int e = beg + kWin; e < end; ++e)          // rows longer than the window
       add_message(acc, hv[int64_t(col_src[e]) * 16], tv[int(col_type[e]) * 16]);
     const __half2 *sh = reinterpret_cast<const __half2 *>(&self);
@@ -290,9 +286,11 @@ aggregate_f16_kernel(const __half *__restrict__ h, const int32_t *__restrict__ r
     if (i1 >= n) break;
     i = i1; beg = beg1; end = end1;
     i1 = i2; beg1 = beg2; end1 = end2;
-    t = t1;
 #pragma unroll
-    for (int u = 0; u < kWin; ++u) s[u] = s1[u];
+    for (int u = 0; u < kWin; ++u) {
+      s[u] = s1[u];
+      t[u] = t1[u];
+    }
   }
 }
 

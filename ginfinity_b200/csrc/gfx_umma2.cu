@@ -1,9 +1,8 @@
-// K2 / K3 / fused layer on tcgen05: warp-specialised, software-pipelined.
+// K2 / K3 on tcgen05: warp-specialised, software-pipelined (second version; K2's
+// current kernel is gfx_umma4.cu, the fused layer is gfx_fused5.cu).
 //
 //   K2     h_out = h + LayerNorm(W2 relu(W1' z + b1') + b2)          HID = 256
 //   K3     out   = l2norm(Wb relu(Wa h + ba) + bb)                   HID = 128
-//   FUSED  K1 + K2: z is produced by aggregation warps straight into the
-//          swizzled shared-memory A operand and never touches HBM
 //
 // One persistent CTA per SM.  Roles (warps):
 //   0-3   epilogue A   D1 (TMEM) -> bias + ReLU -> fp16 -> A2 (TMEM)
@@ -11,8 +10,7 @@
 //   8     MMA issuer   one thread issues every tcgen05.mma; also owns TMEM
 //                      allocation and the one-time weight fetch (TMA bulk copy)
 //   9..   producers    fill the A1 ring (2 stages x 128 rows x 128 fp16,
-//                      K-major, 128-byte swizzle): cp.async of z rows (K2/K3)
-//                      or CSR aggregation (FUSED)
+//                      K-major, 128-byte swizzle): cp.async of the input rows
 //
 // Tensor-pipe schedule per 128-node tile (H = HID/2):
 //     MMA1a  D1[:, :H]  = A1 * W1[:H]^T      | epilogue A on the previous half
@@ -43,18 +41,17 @@ constexpr int kEpiAWarp0 = 0, kEpiBWarp0 = 4, kMmaWarp = 8, kProdWarp0 = 9;
 enum Bar {
   kBarW = 0, kBarA1Full = 1, kBarA1Empty = 3, kBarD1aFull = 5, kBarD1bFull = 6,
   kBarA2aFull = 7, kBarA2bFull = 8, kBarD2Full = 9, kBarD2Empty = 10,
-  kBarHsFull = 11, kBarHsEmpty = 13, kNumBars = 15
+  kNumBars = 11
 };
 
-template <int HID, bool FUSED>
+template <int HID>
 struct Smem {
   static constexpr int w1_bytes = HID * kHidden * 2;
   static constexpr int w2_bytes = kHidden * HID * 2;
   static constexpr int off_w1 = 0;
   static constexpr int off_w2 = off_w1 + w1_bytes;
   static constexpr int off_a1 = off_w2 + w2_bytes;                 // kStages x 32 KB
-  static constexpr int off_hs = off_a1 + kStages * kA1Bytes;       // FUSED: 2 x 64 rows of h
-  static constexpr int off_b1 = off_hs + (FUSED ? kA1Bytes : 0);   // float[HID]
+  static constexpr int off_b1 = off_a1 + kStages * kA1Bytes;       // float[HID]
   static constexpr int off_vec = off_b1 + HID * 4;                 // float[3][128]
   static constexpr int off_bar = off_vec + 3 * kHidden * 4;
   static constexpr int off_tmem = off_bar + kNumBars * 8;
@@ -62,18 +59,13 @@ struct Smem {
 };
 
 struct Args {
-  const __half *a_in;     // K2/K3: the GEMM-1 input rows; FUSED: h (aggregation input)
+  const __half *a_in;     // the GEMM-1 input rows
   const __half *res;      // residual rows (MODE 0)
   const __half *w1_img, *w2_img;
   const float *b1, *b2, *ln_g, *ln_b;
   const int32_t *out_row;
   int64_t n;
   void *out;
-  // FUSED only
-  const int32_t *row_ptr, *col_src;
-  const uint8_t *col_type;
-  const __half *table16;  // [edge_dim][128]
-  float eps1;
 };
 
 __device__ __forceinline__ uint32_t a_chunk_offset(int r, int c16) {
@@ -99,56 +91,13 @@ __device__ __forceinline__ void unpack8(const uint4 &raw, float *f) {
   }
 }
 
-// ---------------------------------------------------------------------------
-// FUSED producer: one half-warp per destination node, lane l owns channels
-// [8l, 8l+8).  In-tile neighbours (87 % of edges are within +-2 rows) are read
-// from the shared-memory copy of the current 64-row block of h; the others
-// come from global memory.  z = eps1*h_i + sum relu(h_src + table[type]) is
-// written as fp16 into the swizzled A1 stage.
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ void aggregate_block(const Args &p, const uint8_t *hs, int64_t blk_row0,
-                                                uint8_t *a1, int a1_row0, int hw, int n_hw,
-                                                int sub) {
-  for (int r = hw; r < 64; r += n_hw) {
-    const int64_t i = blk_row0 + r;
-    float acc[8];
-#pragma unroll
-    for (int c = 0; c < 8; ++c) acc[c] = 0.f;
-    float self[8];
-    if (i < p.n) {
-      unpack8(*reinterpret_cast<const uint4 *>(hs + r * 256 + sub * 16), self);
-      const int beg = p.row_ptr[i], end = p.row_ptr[i + 1];
-      for (int e = beg; e < end; ++e) {
-        const int64_t s = p.col_src[e];
-        const int t = p.col_type[e];
-        const int64_t local = s - blk_row0;
-        uint4 raw;
-        if (local >= 0 && local < 64)
-          raw = *reinterpret_cast<const uint4 *>(hs + local * 256 + sub * 16);
-        else
-          raw = __ldg(reinterpret_cast<const uint4 *>(p.a_in + s * kHidden + sub * 8));
-        const uint4 traw = __ldg(reinterpret_cast<const uint4 *>(p.table16 + t * kHidden + sub * 8));
-        float nb[8], tb[8];
-        unpack8(raw, nb);
-        unpack8(traw, tb);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) acc[c] += fmaxf(nb[c] + tb[c], 0.f);
-      }
-#pragma unroll
-      for (int c = 0; c < 8; ++c) acc[c] = fmaf(p.eps1, self[c], acc[c]);
-    }
-    *reinterpret_cast<uint4 *>(a1 + a_chunk_offset(a1_row0 + r, sub)) = pack8(acc);
-  }
-}
-
-template <int HID, int MODE, typename TOut, int NPROD, bool FUSED>
+template <int HID, int MODE, typename TOut, int NPROD>
 __global__ void __launch_bounds__((kProdWarp0 + NPROD) * 32, 1)
 umma2_kernel(const Args p) {
-  using L = Smem<HID, FUSED>;
+  using L = Smem<HID>;
   constexpr int H = HID / 2;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t *w1s = smem + L::off_w1, *w2s = smem + L::off_w2, *a1s = smem + L::off_a1;
-  uint8_t *hss = smem + L::off_hs;
   float *b1s = reinterpret_cast<float *>(smem + L::off_b1);
   float *b2s = reinterpret_cast<float *>(smem + L::off_vec);
   float *gs = b2s + kHidden, *bs = gs + kHidden;
@@ -163,8 +112,6 @@ umma2_kernel(const Args p) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(bar + kBarA1Full + s, NPROD);
       mbar_init(bar + kBarA1Empty + s, 1);
-      mbar_init(bar + kBarHsFull + s, 1);
-      mbar_init(bar + kBarHsEmpty + s, NPROD);
     }
     mbar_init(bar + kBarD1aFull, 1);
     mbar_init(bar + kBarD1bFull, 1);
@@ -354,61 +301,22 @@ umma2_kernel(const Args p) {
     const int pw = warp - kProdWarp0;
     const int ptid = pw * 32 + lane;
     uint32_t it = 0;
-    if (!FUSED) {
-      for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
-        const uint32_t s = it & 1, ph2 = (it >> 1) & 1;
-        const int64_t row0 = tile * kTileM;
-        uint8_t *a1 = a1s + s * kA1Bytes;
-        mbar_wait(bar + kBarA1Empty + s, ph2 ^ 1);
-        for (int q = ptid; q < kTileM * 16; q += NPROD * 32) {
-          const int r = q >> 4, c16 = q & 15;
-          const bool ok = row0 + r < p.n;
-          const __half *src = p.a_in + (ok ? (row0 + r) : 0) * kHidden + c16 * 8;
-          cp_async16(a1 + a_chunk_offset(r, c16), src, ok ? 16u : 0u);
-        }
-        cp_async_commit();
-        cp_async_wait<0>();
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar + kBarA1Full + s);
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+      const uint32_t s = it & 1, ph2 = (it >> 1) & 1;
+      const int64_t row0 = tile * kTileM;
+      uint8_t *a1 = a1s + s * kA1Bytes;
+      mbar_wait(bar + kBarA1Empty + s, ph2 ^ 1);
+      for (int q = ptid; q < kTileM * 16; q += NPROD * 32) {
+        const int r = q >> 4, c16 = q & 15;
+        const bool ok = row0 + r < p.n;
+        const __half *src = p.a_in + (ok ? (row0 + r) : 0) * kHidden + c16 * 8;
+        cp_async16(a1 + a_chunk_offset(r, c16), src, ok ? 16u : 0u);
       }
-    } else {
-      // 64-row blocks of h are double-buffered in shared memory (TMA bulk copy
-      // issued one block ahead by producer thread 0); two blocks make one tile.
-      const int hw = ptid >> 4, n_hw = NPROD * 2, sub = ptid & 15;
-      const int64_t my_tiles = tiles > blockIdx.x ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-      const int64_t blocks = my_tiles * 2;
-      auto block_row0 = [&](int64_t b) {
-        return (int64_t(blockIdx.x) + (b >> 1) * gridDim.x) * kTileM + (b & 1) * 64;
-      };
-      auto issue_load = [&](int64_t b) {
-        const int hb = b & 1;
-        const int64_t r0 = block_row0(b);
-        int64_t rows = p.n - r0;
-        rows = rows > 64 ? 64 : (rows < 0 ? 0 : rows);
-        mbar_wait(bar + kBarHsEmpty + hb, ((b >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(bar + kBarHsFull + hb, uint32_t(rows * 256));
-        if (rows > 0)
-          bulk_g2s(hss + hb * (64 * 256), p.a_in + r0 * kHidden, uint32_t(rows * 256),
-                   bar + kBarHsFull + hb);
-      };
-      if (ptid == 0 && blocks > 0) issue_load(0);
-      for (int64_t b = 0; b < blocks; ++b) {
-        const int hb = b & 1;
-        const uint32_t s = (b >> 1) & 1, ph2 = (b >> 2) & 1;
-        if (ptid == 0 && b + 1 < blocks) issue_load(b + 1);
-        if ((b & 1) == 0) mbar_wait(bar + kBarA1Empty + s, ph2 ^ 1);
-        mbar_wait(bar + kBarHsFull + hb, (b >> 1) & 1);
-        aggregate_block(p, hss + hb * (64 * 256), block_row0(b), a1s + s * kA1Bytes, (b & 1) * 64,
-                        hw, n_hw, sub);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar + kBarHsEmpty + hb);
-        if (b & 1) {
-          fence_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar + kBarA1Full + s);
-        }
-      }
+      cp_async_commit();
+      cp_async_wait<0>();
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar + kBarA1Full + s);
     }
   }
   tc_fence_before();
@@ -416,10 +324,10 @@ umma2_kernel(const Args p) {
   if (warp == kMmaWarp) tmem_dealloc(tmem, kTmemCols);
 }
 
-template <int HID, int MODE, typename TOut, int NPROD, bool FUSED>
+template <int HID, int MODE, typename TOut, int NPROD>
 static int launch(const Args &args, cudaStream_t st) {
-  auto kern = umma2_kernel<HID, MODE, TOut, NPROD, FUSED>;
-  constexpr int smem = Smem<HID, FUSED>::total;
+  auto kern = umma2_kernel<HID, MODE, TOut, NPROD>;
+  constexpr int smem = Smem<HID>::total;
   static_assert(smem <= 232448, "exceeds the 227 KB shared-memory limit of sm_100");
   GFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int64_t tiles = (args.n + kTileM - 1) / kTileM;
@@ -439,7 +347,7 @@ int umma_mlp_ln_residual(const gfx_model *m, int layer, const __half *z, const _
   a.b1 = m->b1 + size_t(layer) * kMlpHidden; a.b2 = m->b2 + size_t(layer) * kHidden;
   a.ln_g = m->ln_g + size_t(layer) * kHidden; a.ln_b = m->ln_b + size_t(layer) * kHidden;
   a.n = n; a.out = h_out;
-  return v2::launch<kMlpHidden, 0, __half, 4, false>(a, st);
+  return v2::launch<kMlpHidden, 0, __half, 4>(a, st);
 }
 
 int umma_head_l2norm(const gfx_model *m, const __half *h, const int32_t *out_row, int64_t n,
@@ -447,11 +355,17 @@ int umma_head_l2norm(const gfx_model *m, const __half *h, const int32_t *out_row
   v2::Args a{};
   a.a_in = h; a.w1_img = m->wa_img; a.w2_img = m->wb_img; a.b1 = m->ba; a.b2 = m->bb;
   a.out_row = out_row; a.n = n; a.out = out;
-  if (out_dtype == GFX_F16) return v2::launch<kHidden, 1, __half, 4, false>(a, st);
-  return v2::launch<kHidden, 1, float, 4, false>(a, st);
+  if (out_dtype == GFX_F16) return v2::launch<kHidden, 1, __half, 4>(a, st);
+  return v2::launch<kHidden, 1, float, 4>(a, st);
 }
 
 }  // namespace gfx
+
+namespace gfx {
+int fused5_layer(const gfx_model *m, int layer, const __half *h, const int32_t *row_ptr,
+                 const int32_t *col_src, const uint8_t *col_type, int64_t n, __half *h_out,
+                 cudaStream_t st);
+}
 
 extern "C" int gfx_layer_fused(const gfx_model *m, int layer, const void *h,
                                const int32_t *row_ptr, const int32_t *col_src,
@@ -462,14 +376,6 @@ extern "C" int gfx_layer_fused(const gfx_model *m, int layer, const void *h,
   if (n <= 0) return GFX_OK;
   cudaStream_t st = as_stream(stream);
   StageScope scope(GFX_STAGE_FUSED_LAYER, st, 1);
-  const size_t wi = size_t(layer) * kMlpHidden * kHidden;
-  v2::Args a{};
-  a.a_in = static_cast<const __half *>(h); a.res = a.a_in;
-  a.w1_img = m->w1_img + wi; a.w2_img = m->w2_img + wi;
-  a.b1 = m->b1 + size_t(layer) * kMlpHidden; a.b2 = m->b2 + size_t(layer) * kHidden;
-  a.ln_g = m->ln_g + size_t(layer) * kHidden; a.ln_b = m->ln_b + size_t(layer) * kHidden;
-  a.n = n; a.out = h_out;
-  a.row_ptr = row_ptr; a.col_src = col_src; a.col_type = col_type;
-  a.table16 = m->table16 + size_t(layer) * m->edge_dim * kHidden; a.eps1 = m->eps1[layer];
-  return v2::launch<kMlpHidden, 0, __half, 10, true>(a, st);
+  return fused5_layer(m, layer, static_cast<const __half *>(h), row_ptr, col_src, col_type, n,
+                      static_cast<__half *>(h_out), st);
 }
