@@ -217,7 +217,12 @@ def main() -> None:
 
     torch.cuda.set_device(local_rank)
     device = f"cuda:{local_rank}"
+    from ginfinity_b200.multi_gpu import bind_to_gpu_numa_node
+    numa = bind_to_gpu_numa_node(local_rank)       # before any pinned allocation
     if world > 1:
+        # NCCL prints its version banner on stdout when NCCL_DEBUG=VERSION/INFO; the
+        # contract is ONE JSON line there
+        os.environ["NCCL_DEBUG"] = os.environ.get("GFX_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=torch.device(device))
 
     def barrier():
@@ -355,7 +360,7 @@ def main() -> None:
             "gpu_launches_by_stage": launches,
             "e2e_from_records": from_records,
             "roofline": dominant, "roofline_other": other,
-            "setup": {"workload_generation_s": gen_s, "host_cpus": os.cpu_count()},
+            "setup": {"workload_generation_s": gen_s, "host_cpus": os.cpu_count(), "numa_binding": numa},
         }
         if world == 1 and not args.no_cpu_baseline:
             rate, sub, threads, secs = cpu_port_rate(state, shard, args.sample_records)

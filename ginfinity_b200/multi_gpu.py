@@ -18,6 +18,57 @@ def rank_info() -> Tuple[int, int, int]:
             int(os.environ.get("WORLD_SIZE", "1")))
 
 
+def _cpu_list(text: str) -> set:
+    """'0-15,64-79' -> {0..15, 64..79}"""
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(device_index: int) -> dict:
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off.
+
+    The end-to-end encode moves 325 B per nucleotide between pinned host memory
+    and the GPU.  Pinned pages are placed on the node of the allocating thread;
+    if that is the other socket every copy crosses the inter-socket link, which
+    the ranks of that socket then share (measured on an 8-GPU box: 41 instead
+    of ~190 M nt/s per GPU).  Call this before the first pinned allocation.
+    Returns what was done ({"node": .., "cpus": ..}) or {"node": None, ...} when
+    the topology cannot be read; never raises."""
+    info = {"node": None, "cpus": None, "reason": None}
+    try:
+        import torch
+        props = torch.cuda.get_device_properties(device_index)
+        if hasattr(props, "pci_bus_id"):
+            bus = "%04x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        else:                                      # older torch: ask NVML
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            index = int(visible.split(",")[device_index]) if visible else device_index
+            raw = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+            raw = raw.decode() if isinstance(raw, bytes) else raw
+            bus = raw.lower()[-12:]                # 00000000:1b:00.0 -> 0000:1b:00.0
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            info["reason"] = "the platform reports no NUMA node for the GPU"
+            return info
+        cpus = _cpu_list(open(f"/sys/devices/system/node/node{node}/cpulist").read())
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            info["reason"] = "no allowed CPU on the GPU's node"
+            return info
+        os.sched_setaffinity(0, allowed)
+        info.update(node=node, cpus=len(allowed))
+    except Exception as exc:                       # topology files missing, permissions, ...
+        info["reason"] = f"{type(exc).__name__}: {exc}"
+    return info
+
+
 def assign_shards(node_counts: Sequence[int], world_size: int) -> List[List[int]]:
     """Deterministic longest-first greedy assignment of shards to ranks,
     balanced by node count (ties: lower shard index first, lower rank first).

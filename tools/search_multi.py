@@ -35,6 +35,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("GFX_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=dev)
     rows_per_gpu = int(sys.argv[1]) if len(sys.argv) > 1 else 12_500_000
     Q, k = 100_000, 10
