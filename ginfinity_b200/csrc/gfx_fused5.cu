@@ -9,17 +9,24 @@
 // (DESIGN.md section 9); fused it moves ~512 B and the tensor pipe (2,048
 // cycles per 128-node tile) becomes the floor.
 //
-// One persistent CTA per SM, 128-node tiles, 24 warps (80 registers each; with 16
-// producer warps the register budget drops to 64 and the producers spill, which
-// costs an L2 round trip per access here because shared memory leaves no L1):
+// Status (603k-node chunk, B200): 0.243 ms per layer against 0.195 ms for
+// K1 + K2, so the pair stays the default and this kernel is selected by the
+// `fused` argument of gfx_encode.  Measured break-down: everything but the
+// producers 0.144 ms (bound by the life cycle of the two stage buffers, which
+// couples the producers to the store of two tiles earlier), producers working
+// from shared memory only +0.06 ms, out-of-block neighbour rows +0.04 ms.  The
+// way forward is a CTA pair sharing the weights (64 KB per CTA instead of 128),
+// which buys a third and fourth stage buffer.
+//
+// One persistent CTA per SM, 128-node tiles, 32 warps of 64 registers:
 //    0-3   epilogue A   D1 (TMEM) -> + b1, ReLU, fp16 -> A2 (TMEM)
 //    4-11  epilogue B   D2 (TMEM) -> + b2, LayerNorm, + residual -> stage buffer
-//   12-19  producers    half-warp per node: CSR row -> messages -> z row, written
+//   12-27  producers    half-warp per node: CSR row -> messages -> z row, written
 //                       in the UMMA K-major swizzled layout into the A1 stage
-//   20     MMA issuer   (also fetches the weights once)
-//   21     store        TMA store of finished stage buffers
-//   22     residual     TMA load of the tile's h rows into the stage buffer
-//   23     h blocks     bulk copies of 32-row blocks of h into a 3-deep ring
+//   28     MMA issuer   (also fetches the weights once)
+//   29     store        TMA store of finished stage buffers
+//   30     residual     TMA load of the tile's h rows into the stage buffer
+//   31     h blocks     bulk copies of 32-row blocks of h into a 3-deep ring
 //
 // Shared memory (227 KB): W1, W2 operand images (128 KB, resident); two A1
 // stage buffers of 32 KB whose life is  z tile -> (MMA-1 done) -> residual
@@ -27,7 +34,10 @@
 // h rows from which the producers take the in-block neighbours (the graphs
 // are near-banded: ~80 % of edges stay inside a 32-row block), the rest come
 // from global memory; the fp16 edge table; LayerNorm partial sums.
-// Edge indices are prefetched two rows ahead as in the stand-alone K1.
+// The block loader also stages the block's slice of row_ptr / col_src /
+// col_type (it is contiguous) in shared memory, so a producer's only global
+// accesses are the out-of-block neighbour rows, and those are issued for both
+// of its rows of a block before either is summed.
 #include "gfx_common.cuh"
 #include "gfx_tma.cuh"
 #include "gfx_umma.cuh"
@@ -43,11 +53,16 @@ constexpr int kTileM = 128;
 constexpr int kTileBytes = kTileM * 128;      // [128 x 64] fp16 box
 constexpr int kA1Bytes = 2 * kTileBytes;
 constexpr int kBlkRows = 32, kBlkBytes = kBlkRows * 256, kBlkBufs = 3, kBlksPerTile = kTileM / kBlkRows;
-constexpr int kWin = 5;                       // edges per row covered by the index prefetch
+constexpr int kWin = 5;                       // edges per row whose rows are loaded up front
+// the block's slice of the CSR arrays, staged next to its h rows
+constexpr int kRpBytes = 144;                 // row_ptr[r0 .. r0+32] (33 ints) rounded to 16 bytes
+constexpr int kCapSrc = 176 + 4;              // col_src ints per block (avg 145) incl. alignment slack
+constexpr int kCapTyp = 176 + 16;             // col_type bytes per block incl. alignment slack
+constexpr int kIdxBytes = kRpBytes + kCapSrc * 4 + kCapTyp + 16;   // + 16 bytes of meta
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kA2Col = 256, kD2Col = 384;
-constexpr int kEpiBWarp0 = 4, kProdWarp0 = 12, kProdWarps = 8, kMmaWarp = 20, kStoreWarp = 21,
-              kResWarp = 22, kBlkWarp = 23, kWarps = 24;
+constexpr int kEpiBWarp0 = 4, kProdWarp0 = 12, kProdWarps = 16, kMmaWarp = 28, kStoreWarp = 29,
+              kResWarp = 30, kBlkWarp = 31, kWarps = 32;
 constexpr int kHalfWarps = kProdWarps * 2;            // one node row per half-warp at a time
 constexpr int kRowsPerBlk = kBlkRows / kHalfWarps;    // rows of a 32-row block per half-warp
 static_assert(kRowsPerBlk >= 1 && kRowsPerBlk * kHalfWarps == kBlkRows, "block rows must divide evenly");
@@ -67,7 +82,8 @@ struct Smem {
   static constexpr int off_tab = off_hs + kBlkBufs * kBlkBytes;     // fp16 [16][128]
   static constexpr int off_xs = off_tab + kMaxEdgeDim * kHidden * 2;
   static constexpr int off_vec = off_xs + 2 * kTileM * 8;           // float b2[128], g[128], b[128]
-  static constexpr int off_bar = off_vec + 3 * kHidden * 4;
+  static constexpr int off_idx = off_vec + 3 * kHidden * 4;         // 3 x CSR slice of a block
+  static constexpr int off_bar = off_idx + kBlkBufs * kIdxBytes;
   static constexpr int off_tmem = off_bar + kNumBars * 8;
   static constexpr int total = off_tmem + 8;
 };
@@ -229,18 +245,6 @@ __device__ __forceinline__ void epi_b(const float *vec, uint32_t trow, uint64_t 
   if (lane == 0) mbar_arrive(bar + kBarOReady + s);
 }
 
-__device__ __forceinline__ void load_window(const int32_t *__restrict__ col_src,
-                                            const uint8_t *__restrict__ col_type, int beg, int end,
-                                            int *s, uint32_t &types) {
-  types = 0;
-#pragma unroll
-  for (int u = 0; u < kWin; ++u) {
-    const bool ok = beg + u < end;
-    s[u] = ok ? col_src[beg + u] : 0;
-    types |= (ok ? uint32_t(col_type[beg + u]) : 0u) << (4 * u);
-  }
-}
-
 __global__ void __launch_bounds__(kWarps * 32, 1)
 fused_layer_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Consts c, const Args p) {
   using L = Smem;
@@ -250,6 +254,7 @@ fused_layer_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Co
   uint4 *tab = reinterpret_cast<uint4 *>(smem + L::off_tab);
   float2 *xs = reinterpret_cast<float2 *>(smem + L::off_xs);
   float *vec = reinterpret_cast<float *>(smem + L::off_vec);
+  uint8_t *idxs = smem + L::off_idx;
   uint64_t *bar = reinterpret_cast<uint64_t *>(smem + L::off_bar);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::off_tmem);
 
@@ -316,29 +321,13 @@ fused_layer_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Co
     const int hw = ptid >> 4, sub = ptid & 15;
     const uint4 *hv = reinterpret_cast<const uint4 *>(p.h) + sub;        // row r -> hv[r * 16]
     const uint4 *tv = tab + sub;
-    constexpr int kSteps = kTileM / kHalfWarps;                           // rows per half-warp and tile
     const int n = int(p.n), ntiles = int(tiles), grid = int(gridDim.x);
-    auto row_at = [&](int q) -> int {                    // node of step q of this half-warp, or n
-      const int tile = int(blockIdx.x) + (q / kSteps) * grid;
-      if (tile >= ntiles) return n;
-      const int w = q % kSteps;
-      const int i = tile * kTileM + (w / kRowsPerBlk) * kBlkRows + hw + kHalfWarps * (w % kRowsPerBlk);
-      return i < n ? i : n;
+
+    struct Row {              // one node row in flight
+      uint4 nb[kWin];
+      int beg, end;
+      uint32_t types;
     };
-    int q = 0;
-    int i0 = row_at(0), i1 = row_at(1);
-    int beg = 0, end = 0, beg1 = 0, end1 = 0;
-    if (i0 < n) {
-      beg = p.row_ptr[i0];
-      end = p.row_ptr[i0 + 1];
-    }
-    if (i1 < n) {
-      beg1 = p.row_ptr[i1];
-      end1 = p.row_ptr[i1 + 1];
-    }
-    int sidx[kWin];
-    uint32_t types;
-    load_window(p.col_src, p.col_type, beg, end, sidx, types);
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += grid, ++it) {
       const int s = it & 1;
@@ -349,40 +338,62 @@ fused_layer_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Co
         const uint32_t b = it * kBlksPerTile + blk;
         const uint32_t hb = b % kBlkBufs;
         const uint8_t *hblk = hss + hb * kBlkBytes + sub * 16;
+        const uint8_t *idx = idxs + hb * kIdxBytes;
         const int blk_row0 = tile * kTileM + blk * kBlkRows;
         mbar_wait(bar + kBarHFull + hb, (b / kBlkBufs) & 1);
-#pragma unroll 1
-        for (int k = 0; k < kRowsPerBlk; ++k, ++q) {
-          const int i2 = row_at(q + 2);
-          int beg2 = 0, end2 = 0;
-          if (i2 < n) {                                  // row_ptr two rows ahead
-            beg2 = p.row_ptr[i2];
-            end2 = p.row_ptr[i2 + 1];
+        // meta: {staged?, first staged col_src index, first staged col_type index}
+        const int4 meta = *reinterpret_cast<const int4 *>(idx + kIdxBytes - 16);
+        const int32_t *rp = reinterpret_cast<const int32_t *>(idx);
+        const int32_t *cs = reinterpret_cast<const int32_t *>(idx + kRpBytes) - meta.y;
+        const uint8_t *ct = idx + kRpBytes + kCapSrc * 4 - meta.z;
+        const bool staged = meta.x != 0;
+
+        auto edge = [&](int e, int &src, int &typ) {
+          if (staged) {
+            src = cs[e];
+            typ = ct[e];
+          } else {
+            src = p.col_src[e];
+            typ = p.col_type[e];
           }
-          int s1[kWin];
-          uint32_t t1;
-          load_window(p.col_src, p.col_type, beg1, end1, s1, t1);   // indices one row ahead
-          const int lr = hw + kHalfWarps * k;
+        };
+        auto neighbour = [&](int src) -> uint4 {
+          const uint32_t local = uint32_t(src - blk_row0);
+          return local < uint32_t(kBlkRows) ? *reinterpret_cast<const uint4 *>(hblk + local * 256)
+                                            : hv[int64_t(src) * 16];
+        };
+        auto fetch = [&](int lr, Row &r) {          // indices, then the neighbour-row loads
+          const int i = blk_row0 + lr;
+          r.beg = r.end = 0;
+          r.types = 0;
+          if (i < n) {
+            r.beg = staged ? rp[lr] : p.row_ptr[i];
+            r.end = staged ? rp[lr + 1] : p.row_ptr[i + 1];
+          }
+#pragma unroll
+          for (int u = 0; u < kWin; ++u) {
+            if (r.beg + u < r.end) {
+              int src, typ;
+              edge(r.beg + u, src, typ);
+              r.types |= uint32_t(typ) << (4 * u);
+              r.nb[u] = neighbour(src);
+            }
+          }
+        };
+        auto finish = [&](int lr, const Row &r) {   // messages, self term, z row into A1
           uint4 out = make_uint4(0, 0, 0, 0);
-          if (i0 < n) {
+          if (blk_row0 + lr < n) {
             float acc[8];
 #pragma unroll
             for (int ch = 0; ch < 8; ++ch) acc[ch] = 0.f;
-            const int deg = end - beg;
-            uint4 nb[kWin];
-#pragma unroll
-            for (int u = 0; u < kWin; ++u) {
-              const uint32_t local = uint32_t(sidx[u] - blk_row0);
-              if (u < deg)
-                nb[u] = local < uint32_t(kBlkRows)
-                            ? *reinterpret_cast<const uint4 *>(hblk + local * 256)
-                            : hv[int64_t(sidx[u]) * 16];
-            }
 #pragma unroll
             for (int u = 0; u < kWin; ++u)
-              if (u < deg) add_message(acc, nb[u], tv[((types >> (4 * u)) & 15u) * 16]);
-            for (int e = beg + kWin; e < end; ++e)
-              add_message(acc, hv[int64_t(p.col_src[e]) * 16], tv[int(p.col_type[e]) * 16]);
+              if (r.beg + u < r.end) add_message(acc, r.nb[u], tv[((r.types >> (4 * u)) & 15u) * 16]);
+            for (int e = r.beg + kWin; e < r.end; ++e) {   // rows longer than the window
+              int src, typ;
+              edge(e, src, typ);
+              add_message(acc, neighbour(src), tv[typ * 16]);
+            }
             const uint4 self = *reinterpret_cast<const uint4 *>(hblk + lr * 256);
             const __half2 *sh = reinterpret_cast<const __half2 *>(&self);
             uint32_t *o = reinterpret_cast<uint32_t *>(&out);
@@ -393,11 +404,17 @@ fused_layer_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Co
             }
           }
           *reinterpret_cast<uint4 *>(a1 + a_chunk_offset(blk * kBlkRows + lr, sub)) = out;
-          i0 = i1; beg = beg1; end = end1;
-          i1 = i2; beg1 = beg2; end1 = end2;
-          types = t1;
-#pragma unroll
-          for (int u = 0; u < kWin; ++u) sidx[u] = s1[u];
+        };
+        if (kRowsPerBlk == 2) {
+          Row r0, r1;
+          fetch(hw, r0);
+          fetch(hw + kHalfWarps, r1);                // both rows' loads are in flight
+          finish(hw, r0);
+          finish(hw + kHalfWarps, r1);
+        } else {
+          Row r0;
+          fetch(hw, r0);
+          finish(hw, r0);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(bar + kBarHEmpty + hb);
@@ -414,7 +431,7 @@ fused_layer_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Co
         bulk_g2s(w1s + off, reinterpret_cast<const uint8_t *>(p.w1_img) + off, 16384, bar + kBarW);
         bulk_g2s(w2s + off, reinterpret_cast<const uint8_t *>(p.w2_img) + off, 16384, bar + kBarW);
       }
-      mbar_wait(bar + kBarW, 0);
+      mbar_wait_parked(bar + kBarW, 0);
       constexpr uint32_t idesc1 = idesc_f16(kTileM, H);
       constexpr uint32_t idesc2 = idesc_f16(kTileM, kHidden);
       const uint32_t w1a = smem_u32(w1s), w2a = smem_u32(w2s);
@@ -422,7 +439,7 @@ fused_layer_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Co
       for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
         const uint32_t s = it & 1, ph2 = (it >> 1) & 1, ph = it & 1;
         const uint32_t a1a = smem_u32(a1s) + s * kA1Bytes;
-        mbar_wait(bar + kBarA1Full + s, ph2);
+        mbar_wait_parked(bar + kBarA1Full + s, ph2);
         tc_fence_after();
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
@@ -436,13 +453,13 @@ fused_layer_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Co
           mma_commit(bar + (half ? kBarD1bFull : kBarD1aFull));
         }
         mma_commit(bar + kBarA1Empty + s);      // z has been consumed: the stage can take the residual
-        mbar_wait(bar + kBarA2aFull, ph);
-        mbar_wait(bar + kBarD2Empty, ph ^ 1);
+        mbar_wait_parked(bar + kBarA2aFull, ph);
+        mbar_wait_parked(bar + kBarD2Empty, ph ^ 1);
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < HID / 16; ++kk) {
           if (kk == H / 16) {
-            mbar_wait(bar + kBarA2bFull, ph);
+            mbar_wait_parked(bar + kBarA2bFull, ph);
             tc_fence_after();
           }
           const uint64_t db = smem_desc_sw128(w2a + (kk >> 2) * kTileBytes + (kk & 3) * 32);
@@ -460,7 +477,7 @@ fused_layer_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Co
       for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
         const int s = it & 1;
         const int row0 = int(tile * kTileM);
-        mbar_wait(bar + kBarOReady + s, (it >> 1) & 1);
+        mbar_wait_parked(bar + kBarOReady + s, (it >> 1) & 1);
         tma_store_2d(&maps.out, 0, row0, a1s + s * kA1Bytes);
         tma_store_2d(&maps.out, 64, row0, a1s + s * kA1Bytes + kTileBytes);
         bulk_commit();
@@ -478,7 +495,7 @@ fused_layer_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Co
       for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
         const int s = it & 1;
         const int row0 = int(tile * kTileM);
-        mbar_wait(bar + kBarA1Empty + s, (it >> 1) & 1);
+        mbar_wait_parked(bar + kBarA1Empty + s, (it >> 1) & 1);
         mbar_arrive_expect_tx(bar + kBarRFull + s, kA1Bytes);
         tma_load_2d(a1s + s * kA1Bytes, &maps.res, 0, row0, bar + kBarRFull + s);
         tma_load_2d(a1s + s * kA1Bytes + kTileBytes, &maps.res, 64, row0, bar + kBarRFull + s);
@@ -486,19 +503,44 @@ fused_layer_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Co
     }
     __syncwarp();
   } else {
-    // ============================ h block ring (bulk copies) =======================
+    // ============== h rows + CSR slice of every 32-row block (bulk copies) ============
     if (lane == 0) {
+      const int n = int(p.n);
+      const int num_edges = p.row_ptr[n];
       uint32_t b = 0;
       for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         for (int blk = 0; blk < kBlksPerTile; ++blk, ++b) {
           const uint32_t hb = b % kBlkBufs;
-          const int64_t r0 = tile * kTileM + blk * kBlkRows;
-          int64_t rows = p.n - r0;
+          const int r0 = int(tile) * kTileM + blk * kBlkRows;
+          int rows = n - r0;
           rows = rows > kBlkRows ? kBlkRows : (rows < 0 ? 0 : rows);
-          mbar_wait(bar + kBarHEmpty + hb, ((b / kBlkBufs) & 1) ^ 1);
-          mbar_arrive_expect_tx(bar + kBarHFull + hb, uint32_t(rows * 256));
+          uint8_t *idx = idxs + hb * kIdxBytes;
+          // the CSR slice: every copy must start and end on 16 bytes inside the arrays
+          int e0 = 0, e1 = 0;
+          if (rows > 0) {
+            e0 = p.row_ptr[r0];
+            e1 = p.row_ptr[r0 + rows];
+          }
+          const int s0 = e0 & ~3, s1 = (e1 + 3) & ~3;          // col_src window (ints)
+          const int t0 = e0 & ~15, t1 = (e1 + 15) & ~15;       // col_type window (bytes)
+          const bool staged = rows > 0 && r0 + kRpBytes / 4 <= n + 1 && s1 <= num_edges &&
+                              t1 <= num_edges && s1 - s0 <= kCapSrc && t1 - t0 <= kCapTyp;
+          mbar_wait_parked(bar + kBarHEmpty + hb, ((b / kBlkBufs) & 1) ^ 1);
+          *reinterpret_cast<int4 *>(idx + kIdxBytes - 16) = make_int4(staged ? 1 : 0, s0, t0, 0);
+          uint32_t bytes = uint32_t(rows * 256);
+          if (staged) bytes += kRpBytes + uint32_t(s1 - s0) * 4 + uint32_t(t1 - t0);
+          mbar_arrive_expect_tx(bar + kBarHFull + hb, bytes);
           if (rows > 0)
-            bulk_g2s(hss + hb * kBlkBytes, p.h + r0 * kHidden, uint32_t(rows * 256), bar + kBarHFull + hb);
+            bulk_g2s(hss + hb * kBlkBytes, p.h + int64_t(r0) * kHidden, uint32_t(rows * 256),
+                     bar + kBarHFull + hb);
+          if (staged) {
+            bulk_g2s(idx, p.row_ptr + r0, kRpBytes, bar + kBarHFull + hb);
+            if (s1 > s0)
+              bulk_g2s(idx + kRpBytes, p.col_src + s0, uint32_t(s1 - s0) * 4, bar + kBarHFull + hb);
+            if (t1 > t0)
+              bulk_g2s(idx + kRpBytes + kCapSrc * 4, p.col_type + t0, uint32_t(t1 - t0),
+                       bar + kBarHFull + hb);
+          }
         }
       }
     }
