@@ -240,14 +240,19 @@ aggregate_f16_kernel(const __half *__restrict__ h, const int32_t *__restrict__ r
   const uint4 *hv = reinterpret_cast<const uint4 *>(h) + sub;      // row r -> hv[r * 16]
   const uint4 *tv = reinterpret_cast<const uint4 *>(tab) + sub;
   const int64_t stride = int64_t(gridDim.x) * (blockDim.x >> 4);
+  // Nodes are visited from the END of the chunk towards its start: K2 (ascending)
+  // wrote the last rows of h most recently, and the z rows written last here (the
+  // start of the chunk) are the first ones K2 reads -- both while still in L2.
+  // `i` counts visits; the node is n-1-i.
   int64_t i = int64_t(blockIdx.x) * (blockDim.x >> 4) + (threadIdx.x >> 4);
   if (i >= n) return;
-  int beg = row_ptr[i], end = row_ptr[i + 1];
+  const int64_t last = n - 1;
+  int beg = row_ptr[last - i], end = row_ptr[last - i + 1];
   int64_t i1 = i + stride;
   int beg1 = 0, end1 = 0;
   if (i1 < n) {
-    beg1 = row_ptr[i1];
-    end1 = row_ptr[i1 + 1];
+    beg1 = row_ptr[last - i1];
+    end1 = row_ptr[last - i1 + 1];
   }
   int s[kWin], t[kWin];
   load_window(col_src, col_type, beg, end, s, t);
@@ -255,12 +260,12 @@ aggregate_f16_kernel(const __half *__restrict__ h, const int32_t *__restrict__ r
     const int64_t i2 = i1 + stride;
     int beg2 = 0, end2 = 0;
     if (i2 < n) {                                   // stage 1: row_ptr two nodes ahead
-      beg2 = row_ptr[i2];
-      end2 = row_ptr[i2 + 1];
+      beg2 = row_ptr[last - i2];
+      end2 = row_ptr[last - i2 + 1];
     }
     int s1[kWin], t1[kWin];
     load_window(col_src, col_type, beg1, end1, s1, t1);   // stage 2: indices one node ahead
-    const uint4 self = hv[i * 16];                  // stage 3: this node's rows
+    const uint4 self = hv[(last - i) * 16];         // stage 3: this node's rows
     const int deg = end - beg;
     uint4 nb[kWin];
 #pragma unroll
@@ -282,7 +287,7 @@ aggregate_f16_kernel(const __half *__restrict__ h, const int32_t *__restrict__ r
       const __half2 r = __floats2half2_rn(fmaf(eps1, f.x, acc[2 * c]), fmaf(eps1, f.y, acc[2 * c + 1]));
       o[c] = *reinterpret_cast<const uint32_t *>(&r);
     }
-    reinterpret_cast<uint4 *>(z)[i * 16 + sub] = out;
+    reinterpret_cast<uint4 *>(z)[(last - i) * 16 + sub] = out;
     if (i1 >= n) break;
     i = i1; beg = beg1; end = end1;
     i1 = i2; beg1 = beg2; end1 = end2;

@@ -18,6 +18,10 @@
 //
 // Warps: 0-7 epilogue A, 8-15 epilogue B, 16 MMA issuer, 17 z loader (TMA),
 // 18 residual / output manager (TMA).
+//
+// Tiles are taken in ascending row order; K1 walks the chunk in DESCENDING order
+// (gfx_simt.cu), so what either kernel touched last is what the other one reads
+// first while the 126 MB L2 still holds it.
 #include "gfx_common.cuh"
 #include "gfx_tma.cuh"
 #include "gfx_umma.cuh"
@@ -277,8 +281,9 @@ umma4_mlp_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Cons
         uint8_t *a1 = a1s + s * kA1Bytes;
         mbar_wait(bar + kBarA1Empty + s, ph2 ^ 1);
         mbar_arrive_expect_tx(bar + kBarA1Full + s, kA1Bytes);
-        tma_load_2d(a1, &maps.z, 0, int(tile * kTileM), bar + kBarA1Full + s);
-        tma_load_2d(a1 + kTileBytes, &maps.z, 64, int(tile * kTileM), bar + kBarA1Full + s);
+        const int row0 = int(tile * kTileM);
+        tma_load_2d(a1, &maps.z, 0, row0, bar + kBarA1Full + s);
+        tma_load_2d(a1 + kTileBytes, &maps.z, 64, row0, bar + kBarA1Full + s);
       }
     }
     __syncwarp();

@@ -85,12 +85,60 @@ def assign_shards(node_counts: Sequence[int], world_size: int) -> List[List[int]
     return [sorted(m) for m in mine]
 
 
+class ShardPrefetcher:
+    """Iterate over shard files with the NEXT file being read (and, when
+    `pin` is set, copied into page-locked memory) on a background thread while
+    the caller works on the current one (shard I/O that
+    keeps a GPU fed).  At most `depth` loaded shards wait in the queue."""
+
+    def __init__(self, paths: Sequence, *, pin: bool = True, depth: int = 1, load=None,
+                 device_index: int = None):
+        import queue
+        import threading
+        self._paths = [str(p) for p in paths]
+        self._pin, self._load, self._device_index = pin, load, device_index
+        self._queue = queue.Queue(maxsize=max(1, int(depth)))
+        self._thread = threading.Thread(target=self._work, name="gfx-shard-prefetch", daemon=True)
+        self._thread.start()
+
+    def _work(self) -> None:
+        try:
+            load = self._load
+            if load is None:
+                from .graph import load_graph_shard as load
+            pin = None
+            if self._pin:
+                import torch
+                from .encoder import pin_shard as pin
+                if self._device_index is not None:
+                    torch.cuda.set_device(self._device_index)
+            for path in self._paths:
+                shard = load(path)
+                self._queue.put((path, pin(shard) if pin else shard, None))
+        except BaseException as exc:                  # surfaced on the consumer's thread
+            self._queue.put((None, None, exc))
+            return
+        self._queue.put((None, None, None))
+
+    def __iter__(self):
+        while True:
+            path, shard, exc = self._queue.get()
+            if exc is not None:
+                raise exc
+            if path is None:
+                return
+            yield path, shard
+
+
 def encode_shard_files(encoder, paths: Sequence, *, rank: int, world_size: int,
-                       node_counts: Sequence[int] = None, **encode_kwargs) -> Dict[str, list]:
+                       node_counts: Sequence[int] = None, prefetch: bool = True,
+                       **encode_kwargs) -> Dict[str, list]:
     """Encode this rank's share of a list of graph-shard files (the
     reference's `embed-graphs` unit of work, cli.py:139-197).  Every rank must
     pass the same `paths`; when `node_counts` is not given the JSON sidecars
-    are read for the node totals.  Returns {path: [embeddings per record]}."""
+    are read for the node totals.  With `prefetch` the next file is loaded and
+    pinned while the current one is on the GPU.  Returns {path: [embeddings
+    per record]}."""
     import json
 
     from .graph import graph_metadata_path, load_graph_shard
@@ -98,7 +146,13 @@ def encode_shard_files(encoder, paths: Sequence, *, rank: int, world_size: int,
     if node_counts is None:
         node_counts = [int(json.loads(graph_metadata_path(p).read_text())["node_count"])
                        for p in paths]
+    mine = [paths[i] for i in assign_shards(node_counts, world_size)[rank]]
     out = {}
-    for i in assign_shards(node_counts, world_size)[rank]:
-        out[paths[i]] = encoder.encode_graphs(load_graph_shard(paths[i]), **encode_kwargs)
+    if prefetch:
+        index = getattr(getattr(encoder, "_torch_device", None), "index", None)
+        for path, shard in ShardPrefetcher(mine, device_index=index):
+            out[path] = encoder.encode_graphs(shard, **encode_kwargs)
+    else:
+        for path in mine:
+            out[path] = encoder.encode_graphs(load_graph_shard(path), **encode_kwargs)
     return out

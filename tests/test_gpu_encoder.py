@@ -257,3 +257,30 @@ def test_maximum_length_record_and_tiny_records(gb, syn16, synthetic_state):
     assert [g.shape for g in got] == [(4096, 128), (1, 128), (2, 128), (3, 128)]
     for g, w in zip(got, want):
         assert np.abs(g - w).max() <= 3e-3
+
+
+def test_encode_shard_files_with_prefetch_matches_direct_encoding(gb, syn16, tmp_path):
+    """The C4 unit of work: shard files assigned to ranks by node count, the
+    next file loaded and pinned while the current one is encoded."""
+    from ginfinity_b200.multi_gpu import assign_shards, encode_shard_files
+    paths, shards = [], []
+    for k in range(4):
+        shard = gb.GraphBuilder().build_shard(random_records(40 + k, 30 + 10 * k, prefix=f"f{k}-"))
+        path = tmp_path / f"part-{k}.safetensors"
+        gb.save_graph_shard(shard, path)
+        paths.append(str(path))
+        shards.append(shard)
+    counts = [s.node_count for s in shards]
+    seen = {}
+    for rank in range(2):
+        seen.update(encode_shard_files(syn16, paths, rank=rank, world_size=2))
+        seen_plain = encode_shard_files(syn16, paths, rank=rank, world_size=2, prefetch=False,
+                                        node_counts=counts)
+        for p, arrays in seen_plain.items():
+            assert all(np.array_equal(a, b) for a, b in zip(arrays, seen[p]))
+    assert sorted(seen) == sorted(paths)
+    assert sorted(sum(assign_shards(counts, 2), [])) == [0, 1, 2, 3]
+    for p, shard in zip(paths, shards):
+        want = syn16.encode_graphs(shard)
+        assert len(want) == len(seen[p])
+        assert all(np.array_equal(a, b) for a, b in zip(want, seen[p]))

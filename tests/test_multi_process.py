@@ -97,3 +97,55 @@ def test_shard_bounds_cover_the_database_exactly():
             assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         shard_bounds(10, 2, 2)
+
+
+def test_numa_binding_helper_never_raises_and_reports():
+    """On a box without a GPU (this runner) the helper must say why it did
+    nothing instead of failing; the CPU-list parser is exercised directly."""
+    sys.path.insert(0, str(ROOT))
+    from ginfinity_b200.multi_gpu import _cpu_list, bind_to_gpu_numa_node
+    assert _cpu_list("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert _cpu_list("") == set()
+    before = os.sched_getaffinity(0)
+    info = bind_to_gpu_numa_node(0)
+    assert set(info) == {"node", "cpus", "reason"}
+    if info["node"] is None:
+        assert info["reason"] and os.sched_getaffinity(0) == before
+
+
+def test_shard_prefetcher_order_errors_and_overlap():
+    """The prefetcher yields every file once, in order, loads ahead of the
+    consumer, and re-raises a loader failure on the consumer's thread."""
+    import time
+    sys.path.insert(0, str(ROOT))
+    from ginfinity_b200.multi_gpu import ShardPrefetcher
+    loaded = []
+
+    def load(path):
+        loaded.append(path)
+        time.sleep(0.05)
+        return {"path": path}
+
+    paths = [f"shard-{i}" for i in range(5)]
+    seen = []
+    t0 = time.perf_counter()
+    for path, shard in ShardPrefetcher(paths, pin=False, load=load):
+        if len(seen) == 1:
+            time.sleep(0.15)
+            assert len(loaded) >= 3          # the loader ran ahead while the consumer was busy
+        time.sleep(0.05)
+        seen.append((path, shard["path"]))
+    assert seen == [(p, p) for p in paths]
+    assert time.perf_counter() - t0 < 5 * 0.1 + 0.15 + 0.2   # overlapped, not serial
+
+    def broken(path):
+        if path.endswith("2"):
+            raise OSError("truncated file")
+        return path
+
+    got = []
+    with pytest.raises(OSError, match="truncated"):
+        for path, _ in ShardPrefetcher(paths, pin=False, load=broken):
+            got.append(path)
+    assert got == paths[:2]
+    assert list(ShardPrefetcher([], pin=False, load=load)) == []
