@@ -151,6 +151,8 @@ def run_reference(args, rank: int, world: int) -> None:
     if rank != 0:
         return
     import torch
+    # torchrun exports OMP_NUM_THREADS=1; the reference arm uses every host core it is given
+    torch.set_num_threads(len(os.sched_getaffinity(0)))
     state, label = load_weights()
     shard, _ = build_workload(args.sample_records, seed=0)
     from oracle.cpu_port import CpuPort

@@ -38,6 +38,7 @@ constexpr int kEpiWarps = 8, kMmaWarp = 8, kLoadWarp = 9, kWarps = 10;
 constexpr int kD2Slots = 8;                       // loader runs <= 5 tiles ahead of the epilogue
 constexpr int kMaxCand = 28, kMaxK = 24;
 constexpr int kWaves = 8;                         // work items per CTA aimed for
+constexpr int kSampleTiles = 128;                 // database tiles of the threshold-seeding pre-pass
 
 enum Bar {
   kBarQFull = 0, kBarQEmpty = 1, kBarBFull = 2, kBarBEmpty = 5, kBarDFull = 8, kBarDEmpty = 10,
@@ -62,7 +63,8 @@ struct alignas(64) Maps {
 struct Plan {
   int64_t tiles_q, tiles_db, segs, tiles_per_seg, qp;
   int kc;
-  size_t off_scores, off_index, off_d2, total;
+  int64_t sample_tiles;       // 0 = no seeding pre-pass
+  size_t off_scores, off_index, off_d2, off_seed_scores, off_seed_index, total;
 };
 
 static Plan make_plan(int64_t Q, int64_t D, int k) {
@@ -85,6 +87,11 @@ static Plan make_plan(int64_t Q, int64_t D, int k) {
   p.off_index = up(cand * 4);
   p.off_d2 = p.off_index + up(cand * 4);
   p.total = p.off_d2 + up(size_t(p.tiles_db) * kDbTile * 4);
+  // Seeding pays when the sample is a small part of the scan.
+  p.sample_tiles = p.tiles_db >= 8 * kSampleTiles ? kSampleTiles : 0;
+  p.off_seed_scores = p.total;
+  p.off_seed_index = p.off_seed_scores + up(size_t(p.qp) * p.kc * 4);
+  if (p.sample_tiles) p.total = p.off_seed_index + up(size_t(p.qp) * p.kc * 4);
   return p;
 }
 
@@ -94,6 +101,11 @@ struct Args {
   int32_t *part_index;
   int64_t tiles_q, tiles_db, segs, tiles_per_seg, qp, num_rows;
   int kc;
+  // [qp][kc] lists of a pre-pass over the first kSampleTiles tiles, or NULL.  The
+  // kc-th best score of ANY subset of the database is a lower bound of the
+  // kc-th best overall, so a scan may start from it instead of -inf: it skips
+  // the warm-up in which every value is inserted.
+  const float *seed;
 };
 
 // Insert (v, idx) into the thread's descending list (column `ls`/`li`, stride
@@ -232,7 +244,12 @@ topk_scan_kernel(const __grid_constant__ Maps maps, const Args p) {
         ls[j * kQTile] = ninf;
         li[j * kQTile] = INT_MAX;
       }
-      float thr = ninf;
+      float seed = ninf;
+      if (p.seed) {
+        seed = p.seed[(size_t(qt) * kQTile + row) * kc + kc - 1];
+        seed -= fabsf(seed) * 2.4e-7f + 1e-30f;     // strictly below: ties with the seed still enter
+      }
+      float thr = seed;
       for (int64_t t = t0; t < t1; ++t, ++it) {
         const uint32_t a = it & 1, pha = (it >> 1) & 1;
         mbar_wait(bar + kBarDFull + a, pha);
@@ -280,7 +297,7 @@ topk_scan_kernel(const __grid_constant__ Maps maps, const Args p) {
 #pragma unroll
               for (int j = 0; j < 8; ++j)
                 if (v[8 * g + j] > thr && base + 8 * g + j < rows)
-                  thr = list_insert(ls, li, kc, v[8 * g + j], base + 8 * g + j);
+                  thr = fmaxf(seed, list_insert(ls, li, kc, v[8 * g + j], base + 8 * g + j));
             }
           }
         }
@@ -520,20 +537,31 @@ extern "C" int gfx_topk(const void *queries, int64_t num_queries, const void *da
   int rc = tma::make_rows128_map(&maps.q, q, num_queries, 128);
   if (!rc) rc = tma::make_rows128_map(&maps.db, db, num_rows, 128);
   if (rc) return rc;
-  StageScope scope(GFX_STAGE_TOPK, st, metric == 1 ? 3 : 2);
+  StageScope scope(GFX_STAGE_TOPK, st, (metric == 1 ? 3 : 2) + (plan.sample_tiles ? 1 : 0));
   const int64_t items = plan.tiles_q * plan.segs;
+  topk::Args pre = a;                      // seeding pre-pass over the first rows, one segment
+  if (plan.sample_tiles) {
+    pre.part_scores = reinterpret_cast<float *>(ws + plan.off_seed_scores);
+    pre.part_index = reinterpret_cast<int32_t *>(ws + plan.off_seed_index);
+    pre.tiles_db = pre.tiles_per_seg = plan.sample_tiles;
+    pre.segs = 1;
+    pre.num_rows = plan.sample_tiles * topk::kDbTile;
+    a.seed = pre.part_scores;
+  }
   if (metric == 1) {
     const int64_t padded = plan.tiles_db * topk::kDbTile;
     int64_t blocks = (padded + 15) / 16;
     if (blocks > int64_t(kNumSMs) * 8) blocks = int64_t(kNumSMs) * 8;
     topk::row_sqnorm_kernel<<<int(blocks), 256, 0, st>>>(db, num_rows, padded, const_cast<float *>(a.d2));
     GFX_LAUNCH_CHECK();
+    if (plan.sample_tiles && (rc = topk::launch_scan<1>(maps, pre, plan.tiles_q, st))) return rc;
     rc = topk::launch_scan<1>(maps, a, items, st);
     if (rc) return rc;
     topk::topk_finish_kernel<1><<<finish_blocks, topk::kFinishWarps * 32, 0, st>>>(
         q, db, a.part_scores, a.part_index, plan.segs, plan.qp, plan.kc, num_queries, k, index_base,
         out_scores, out_index);
   } else {
+    if (plan.sample_tiles && (rc = topk::launch_scan<0>(maps, pre, plan.tiles_q, st))) return rc;
     rc = topk::launch_scan<0>(maps, a, items, st);
     if (rc) return rc;
     topk::topk_finish_kernel<0><<<finish_blocks, topk::kFinishWarps * 32, 0, st>>>(

@@ -145,3 +145,25 @@ def test_search_over_real_embeddings(search, synthetic_state):
     want_s, want_i = O.topk_exact(emb[:500], emb, 3, "cosine")
     np.testing.assert_array_equal(i.cpu().numpy(), want_i)
     assert np.all(np.abs(s.cpu().numpy()[:, 0] - 1.0) < 2e-3)
+
+
+@pytest.mark.parametrize("metric", ["cosine", "l2"])
+def test_seeded_scan_on_a_large_database_with_ties(search, metric):
+    """Databases of >= 131,072 rows take the threshold-seeding pre-pass (kc-th
+    best of the first 16,384 rows).  Built so that it matters: the best rows
+    are duplicated inside AND outside the sample, so scores equal to the seed
+    must still enter, and ties must come out in index order."""
+    rng = np.random.default_rng(15)
+    D, Q, k = 140_000, 40, 10
+    db = unit_rows(16, D, scale=(0.7, 1.3) if metric == "l2" else None)
+    q = unit_rows(17, Q)
+    hot = db[rng.integers(0, 16_384, 6)]                   # six rows of the sample ...
+    for pos in (20_000, 77_777, 139_990):                  # ... repeated far outside it
+        db[pos:pos + 6] = hot
+    q[:6] = hot                                            # and used as queries: exact ties at the top
+    got_s, got_i = run(search, q, db, k, metric)
+    want_s, want_i = O.topk_exact(q, db, k, metric)
+    np.testing.assert_array_equal(got_i, want_i)
+    np.testing.assert_allclose(got_s, want_s, rtol=1e-6, atol=1e-7)
+    assert np.all(got_s[:6, 0] == got_s[:6, 3])            # four copies of each hot row tie
+    assert np.all(np.diff(got_i[:6, :4], axis=1) > 0)
