@@ -110,7 +110,9 @@ struct Args {
 
 // Insert (v, idx) into the thread's descending list (column `ls`/`li`, stride
 // kQTile).  Strict comparisons: among equal scores the earlier (lower) index
-// stays ahead.  Returns the new threshold (the list's last score).
+// stays ahead.  Returns the new threshold (the list's last score).  (An
+// unsorted set with a tracked eviction slot was tried: its full rescan per
+// insert costs more than the average shift here.)
 __device__ __noinline__ float list_insert(float *ls, int32_t *li, int kc, float v, int32_t idx) {
   int j = kc - 1;
   while (j > 0 && ls[(j - 1) * kQTile] < v) {
@@ -245,7 +247,7 @@ topk_scan_kernel(const __grid_constant__ Maps maps, const Args p) {
         li[j * kQTile] = INT_MAX;
       }
       float seed = ninf;
-      if (p.seed) {
+      if (p.seed) {                                 // kc-th best of the sample (lists are sorted)
         seed = p.seed[(size_t(qt) * kQTile + row) * kc + kc - 1];
         seed -= fabsf(seed) * 2.4e-7f + 1e-30f;     // strictly below: ties with the seed still enter
       }
