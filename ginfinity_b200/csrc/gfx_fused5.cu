@@ -559,6 +559,12 @@ int fused5_layer(const gfx_model *m, int layer, const __half *h, const int32_t *
   if ((reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(h_out)) & 15)
     return fail(GFX_ERR_ARGUMENT, "fused layer: activation buffers must be 16-byte aligned");
   if (h == h_out) return fail(GFX_ERR_ARGUMENT, "fused layer: h and h_out must not alias");
+  if ((reinterpret_cast<uintptr_t>(row_ptr) | reinterpret_cast<uintptr_t>(col_src) |
+       reinterpret_cast<uintptr_t>(col_type)) & 15)
+    return fail(GFX_ERR_ARGUMENT,
+                "fused layer: row_ptr, col_src and col_type must be 16-byte aligned (their block "
+                "slices are fetched with bulk copies)");
+  if (n >= (int64_t(1) << 31) - 256) return fail(GFX_ERR_ARGUMENT, "fused layer: too many nodes");
   v5::Maps maps;
   int rc = tma::make_rows128_map(&maps.res, h, n, v5::kTileM);
   if (!rc) rc = tma::make_rows128_map(&maps.out, h_out, n, v5::kTileM);

@@ -485,12 +485,14 @@ class Ginfinity:
         N = int(node_ptr[-1])
         out_code = nat.GFX_F16 if dtype == np.float16 else nat.GFX_F32
         tdtype = torch.float16 if out_code == nat.GFX_F16 else torch.float32
-        # groups of whole records, about records_group_nodes nucleotides each
-        cuts = [0]
+        # groups of whole records: small first (nothing overlaps the first group's host
+        # preparation), then doubling up to records_group_nodes nucleotides
+        cuts, size = [0], max(1, self.records_group_nodes >> 3)
         while cuts[-1] < B:
-            target = node_ptr[cuts[-1]] + self.records_group_nodes
+            target = node_ptr[cuts[-1]] + size
             nxt = int(np.searchsorted(node_ptr, target, side="right")) - 1
             cuts.append(min(B, max(nxt, cuts[-1] + 1)))
+            size = min(2 * size, self.records_group_nodes)
         dev = self._torch_device
         with torch.cuda.device(dev), torch.inference_mode():
             host = torch.empty((N, 128), dtype=tdtype, pin_memory=True)
