@@ -337,7 +337,7 @@ def main() -> None:
                         "avg_launch_ms": mlp_ms / max(mlp_calls, 1),
                         "share_of_step": mlp_ms / args.steps / step_ms_rank,
                         "peak_source": peaks["source"]}
-        roofline_agg = {"kernel": "aggregate_f16_kernel (K1: CSR gather + table + ReLU + self term)",
+        roofline_agg = {"kernel": "aggregate_f16_q_kernel (K1: CSR gather + table + ReLU + self term, quarter-warp per node)",
                         "bound": "hbm", "achieved": agg_gbs, "peak": peaks["hbm_gbs"],
                         "unit": "GB/s", "frac": agg_gbs / peaks["hbm_gbs"],
                         "traffic": ncu_traffic("aggregate", node_layers / max(agg_calls, 1)),

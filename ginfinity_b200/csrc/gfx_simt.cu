@@ -1,6 +1,8 @@
 // CUDA-core kernels: input projection, K1 neighbour aggregation (the HBM-bound
 // kernel of the path) and an fp32-accumulate MLP / head used for the
 // full-precision model and as the on-device cross-check of the tcgen05 path.
+#include <cstdlib>
+
 #include "gfx_common.cuh"
 
 namespace gfx {
@@ -300,6 +302,132 @@ aggregate_f16_kernel(const __half *__restrict__ h, const int32_t *__restrict__ r
 }
 
 // ---------------------------------------------------------------------------
+// K1, fp16 storage, quarter-warp per node.  ncu of the half-warp kernel above
+// (profiles/r01_f): 71 % of the issue slots busy at 39 % of DRAM throughput,
+// 120 warp instructions per node -- it is bound by instruction issue, and half
+// of what it issues is per-node bookkeeping (index loads with their address
+// arithmetic, divergent `u < deg` regions) that costs the same for 16 lanes
+// as for 8.  Here 8 lanes own a node (lane q: channels [8q, 8q+8) and
+// [64+8q, 64+8q+8), i.e. two 128-bit accesses, each instruction covering a
+// contiguous 128-byte line per node), so a warp retires 4 nodes per pass
+// through the same bookkeeping:
+//   * lane q fetches edge `beg + q` (source and type, packed into one
+//     register) and the 8 lanes exchange them by shuffle: 2 loads + 5 SHFL
+//     instead of 10 loads;
+//   * a missing edge (u >= deg) points at the node itself with a table row of
+//     -65504, so its message is relu(h - 65504) = +0 and nothing is
+//     predicated or divergent; the extra row read is an L1 hit (the self row
+//     is loaded anyway);
+//   * the software pipeline is the same (row_ptr two nodes ahead, indices one
+//     node ahead, rows now).
+// Rows with more than 8 edges finish in a plain loop.  Sources must fit 27
+// bits (the caller falls back to the half-warp kernel above 2^27 nodes).
+// ---------------------------------------------------------------------------
+constexpr int kWinQ = 5;              // edges per node covered by the straight-line code
+constexpr int kSrcBits = 27;
+constexpr uint32_t kSrcMask = (1u << kSrcBits) - 1u;
+
+__global__ void __launch_bounds__(256, 2)
+aggregate_f16_q_kernel(const __half *__restrict__ h, const int32_t *__restrict__ row_ptr,
+                       const int32_t *__restrict__ col_src, const uint8_t *__restrict__ col_type,
+                       const __half *__restrict__ table16, int edge_dim, float eps1, int64_t n,
+                       __half *__restrict__ z) {
+  __shared__ __align__(16) __half tab[(kMaxEdgeDim + 1) * kHidden];
+  for (int i = threadIdx.x; i < edge_dim * kHidden / 8; i += blockDim.x)
+    reinterpret_cast<uint4 *>(tab)[i] = reinterpret_cast<const uint4 *>(table16)[i];
+  for (int i = threadIdx.x; i < kHidden / 8; i += blockDim.x)       // the "no edge" row
+    reinterpret_cast<uint4 *>(tab)[edge_dim * kHidden / 8 + i] =
+        make_uint4(0xFBFFFBFFu, 0xFBFFFBFFu, 0xFBFFFBFFu, 0xFBFFFBFFu);
+  __syncthreads();
+  const int sub = threadIdx.x & 7;
+  const int qbase = threadIdx.x & 24;                               // first lane of this quarter
+  const uint4 *hv = reinterpret_cast<const uint4 *>(h) + sub;       // row r -> hv[r*16], hv[r*16+8]
+  const uint4 *tv = reinterpret_cast<const uint4 *>(tab) + sub;
+  const uint32_t none = uint32_t(edge_dim) << kSrcBits;
+  const int64_t stride = int64_t(gridDim.x) * (blockDim.x >> 3);
+  // descending node order, as in the half-warp kernel (L2 hand-over with K2)
+  int64_t i = int64_t(blockIdx.x) * (blockDim.x >> 3) + (threadIdx.x >> 3);
+  const int64_t last = n - 1;
+  // Out-of-range quarters keep running with an empty row (every shuffle below
+  // is executed by the full warp) and skip only the store.
+  auto rp = [&](int64_t v, int &b, int &e) {
+    b = e = 0;
+    if (v < n) {
+      b = row_ptr[last - v];
+      e = row_ptr[last - v + 1];
+    }
+  };
+  auto fetch_edge = [&](int64_t v, int b, int e) -> uint32_t {       // this lane's edge of node v
+    uint32_t pk = (uint32_t(v < n ? last - v : 0) & kSrcMask) | none;
+    if (b + sub < e) pk = uint32_t(col_src[b + sub]) | (uint32_t(col_type[b + sub]) << kSrcBits);
+    return pk;
+  };
+  int beg, end, beg1, end1;
+  rp(i, beg, end);
+  int64_t i1 = i + stride;
+  rp(i1, beg1, end1);
+  uint32_t pk = fetch_edge(i, beg, end);
+  while (true) {                                                     // warp-uniform trip count
+    const int64_t i2 = i1 + stride;
+    int beg2, end2;
+    rp(i2, beg2, end2);                                              // stage 1
+    const uint32_t pk1 = fetch_edge(i1, beg1, end1);                 // stage 2
+    const int64_t node = i < n ? last - i : 0;                       // stage 3
+    const uint4 self0 = hv[node * 16], self1 = hv[node * 16 + 8];
+    uint32_t e[kWinQ];
+    uint4 nb0[kWinQ], nb1[kWinQ];
+#pragma unroll
+    for (int u = 0; u < kWinQ; ++u) {
+      e[u] = __shfl_sync(0xffffffffu, pk, qbase + u);
+      const uint4 *src = hv + int64_t(e[u] & kSrcMask) * 16;
+      nb0[u] = src[0];
+      nb1[u] = src[8];
+    }
+    float acc[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[c] = 0.f;
+#pragma unroll
+    for (int u = 0; u < kWinQ; ++u) {
+      const uint4 *t = tv + (e[u] >> kSrcBits) * 16;
+      add_message(acc, nb0[u], t[0]);
+      add_message(acc + 8, nb1[u], t[8]);
+    }
+    const int deg = end - beg;
+    if (deg > kWinQ) {                                               // rare: longer rows
+      for (int u = kWinQ; u < deg; ++u) {
+        const int s = col_src[beg + u], ty = col_type[beg + u];
+        const uint4 *src = hv + int64_t(s) * 16;
+        const uint4 *t = tv + ty * 16;
+        add_message(acc, src[0], t[0]);
+        add_message(acc + 8, src[8], t[8]);
+      }
+    }
+    if (i < n) {
+      uint4 o0, o1;
+      uint32_t *p0 = reinterpret_cast<uint32_t *>(&o0), *p1 = reinterpret_cast<uint32_t *>(&o1);
+      const __half2 *s0 = reinterpret_cast<const __half2 *>(&self0);
+      const __half2 *s1 = reinterpret_cast<const __half2 *>(&self1);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float2 f0 = __half22float2(s0[c]), f1 = __half22float2(s1[c]);
+        const __half2 r0 = __floats2half2_rn(fmaf(eps1, f0.x, acc[2 * c]), fmaf(eps1, f0.y, acc[2 * c + 1]));
+        const __half2 r1 =
+            __floats2half2_rn(fmaf(eps1, f1.x, acc[8 + 2 * c]), fmaf(eps1, f1.y, acc[8 + 2 * c + 1]));
+        p0[c] = *reinterpret_cast<const uint32_t *>(&r0);
+        p1[c] = *reinterpret_cast<const uint32_t *>(&r1);
+      }
+      uint4 *zr = reinterpret_cast<uint4 *>(z) + node * 16 + sub;
+      zr[0] = o0;
+      zr[8] = o1;
+    }
+    // the first node of the warp is the lowest visit index: all four are done when it is
+    if (__shfl_sync(0xffffffffu, int(i1 >= n), 0)) break;
+    i = i1; beg = beg1; end = end1; pk = pk1;
+    i1 = i2; beg1 = beg2; end1 = end2;
+  }
+}
+
+// ---------------------------------------------------------------------------
 // SIMT MLP.  One warp owns 8 node rows end to end (both GEMMs, LayerNorm or
 // L2 norm), so nothing but weights is shared between warps and only
 // __syncwarp is needed.  Stage 1: lane owns HID/32 hidden columns of its 8
@@ -547,11 +675,23 @@ extern "C" int gfx_aggregate(const gfx_model *m, int layer, const void *h, const
   cudaStream_t st = as_stream(stream);
   StageScope scope(GFX_STAGE_AGGREGATE, st, 1);
   const size_t toff = size_t(layer) * m->edge_dim * kHidden;
-  if (dtype == GFX_F16)
-    aggregate_f16_kernel<<<resident_grid(n, 4), 256, 0, st>>>(
-        static_cast<const __half *>(h), row_ptr, col_src, col_type, m->table16 + toff,
-        m->edge_dim, m->eps1[layer], n, static_cast<__half *>(z));
-  else if (dtype == GFX_F32)
+  if (dtype == GFX_F16) {
+    static const bool half_warp = [] {
+      const char *v = getenv("GFX_K1_HALFWARP");     // diagnostic: the previous kernel
+      return v && *v && *v != '0';
+    }();
+    if (!half_warp && n <= (int64_t(1) << kSrcBits)) {
+      int64_t b = (n + 31) / 32;
+      const int grid = int(b > 2 * kNumSMs ? 2 * kNumSMs : b);
+      aggregate_f16_q_kernel<<<grid, 256, 0, st>>>(
+          static_cast<const __half *>(h), row_ptr, col_src, col_type, m->table16 + toff,
+          m->edge_dim, m->eps1[layer], n, static_cast<__half *>(z));
+    } else {
+      aggregate_f16_kernel<<<resident_grid(n, 4), 256, 0, st>>>(
+          static_cast<const __half *>(h), row_ptr, col_src, col_type, m->table16 + toff,
+          m->edge_dim, m->eps1[layer], n, static_cast<__half *>(z));
+    }
+  } else if (dtype == GFX_F32)
     aggregate_kernel<float><<<row_grid(n), 256, 0, st>>>(
         static_cast<const float *>(h), row_ptr, col_src, col_type, m->table[0] + toff,
         m->edge_dim, m->eps1[layer], n, static_cast<float *>(z));

@@ -254,6 +254,45 @@ def test_aggregate_layer0(nat, dev, problem, code):
     assert torch.equal(z, z2)
 
 
+@pytest.mark.parametrize("n", [1, 3, 31, 33, 1000, 4099])
+def test_aggregate_irregular_rows(nat, dev, problem, n):
+    """K1 on rows the builder never produces: empty rows, rows longer than the
+    quarter-warp kernel's straight-line window (5) and than its 8 fetched
+    edges, self loops, duplicate edges, and node counts that leave quarters
+    of the last warp without a node.  fp16 storage: bit-identical to the
+    half-warp kernel's formula restated in NumPy (fp16 messages, fp32 sum in
+    CSR order, one rounding of the result)."""
+    rng = np.random.default_rng(100 + n)
+    deg = rng.choice([0, 1, 2, 4, 5, 6, 8, 9, 17, 40], size=n,
+                     p=[.1, .1, .1, .2, .2, .1, .05, .05, .05, .05])
+    dst = np.repeat(np.arange(n), deg)
+    src = rng.integers(0, n, size=dst.shape[0])
+    src[::7] = dst[::7]                                  # self loops
+    order = rng.permutation(dst.shape[0])                # unsorted input
+    ei = np.stack([src[order], dst[order]]).astype(np.int32)
+    et = rng.integers(0, 10, size=dst.shape[0]).astype(np.uint8)
+    rp, cs, ct = device_csr(nat, dev, ei, et, n)
+    erp, ecs, ect = O.csr_by_destination(ei, et, n)
+    h = (rng.standard_normal((n, 128)) * 3).astype(np.float16)
+    fw = problem["fw"]
+    q = lambda a: a.astype(np.float16).astype(np.float32)   # noqa: E731
+    hf = h.astype(np.float32)
+    m = q(np.maximum(hf[ecs.astype(np.int64)] + q(fw["table"][1])[ect.astype(np.int64)], 0))
+    agg = np.zeros_like(hf)
+    np.add.at(agg, np.repeat(np.arange(n), np.diff(erp)), m)
+    want = (np.float32(fw["eps1"][1]) * hf + agg).astype(np.float16)
+    hd = _up(h, dev)
+    z = _buf(n, 0, dev)
+    nat.check(nat.lib.gfx_aggregate(problem["handle"], 1, hd.data_ptr(), rp.data_ptr(),
+                                    cs.data_ptr(), ct.data_ptr(), n, z.data_ptr(), 0, _stream()))
+    torch.cuda.synchronize()
+    got = z.cpu().numpy()
+    # fma contraction of eps1*h + agg may differ from NumPy's two roundings by one fp16 ulp
+    err = np.abs(got.astype(np.float32) - want.astype(np.float32))
+    assert err.max() <= 2 ** -10 * max(1.0, np.abs(want.astype(np.float32)).max())
+    assert (got != want).mean() < 0.02
+
+
 @pytest.mark.parametrize("code,impl", [(1, 1), (0, 1), (0, 2), (0, 3), (0, 4), (0, 5)])
 def test_mlp_layernorm_residual_layer0(nat, dev, problem, code, impl):
     """K2 (SIMT fp32, SIMT fp16-storage, pipelined tcgen05, serial tcgen05) against the oracle's h1."""
