@@ -261,9 +261,17 @@ def main() -> None:
     elapsed_ms = torch.tensor([ev0.elapsed_time(ev1)], device=device, dtype=torch.float64)
     total_nodes = torch.tensor([float(nodes)], device=device, dtype=torch.float64)
     launches = nat.launch_counts(reset=True)
+    launches = {k: int(v) for k, v in launches.items()}
     mlp_ms, mlp_calls = nat.profile_read("mlp")
     agg_ms, agg_calls = nat.profile_read("aggregate")
+    # one more pass, untimed, with every stage bracketed: where the step goes
+    nat.profile_enable(*nat.STAGES)
+    step()
+    torch.cuda.synchronize()
+    stage_ms = {name: round(nat.profile_read(name)[0], 4) for name in nat.STAGES}
+    stage_ms = {k: v for k, v in stage_ms.items() if v > 0}
     nat.profile_enable()
+    nat.launch_counts(reset=True)
     if world > 1:
         dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(total_nodes, op=dist.ReduceOp.SUM)
@@ -360,6 +368,7 @@ def main() -> None:
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s.item() / args.steps * 1e3},
             "gpu_launches": int(sum(launches.values())),
             "gpu_launches_by_stage": launches,
+            "stage_ms_per_step": stage_ms,
             "e2e_from_records": from_records,
             "roofline": dominant, "roofline_other": other,
             "setup": {"workload_generation_s": gen_s, "host_cpus": os.cpu_count(), "numa_binding": numa},

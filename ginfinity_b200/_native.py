@@ -55,6 +55,11 @@ _SIGNATURES = {
     "gfx_graph_count": (C.c_int, [_p, _p, _i64, _i64, C.c_int, _p, _p, _p, _sz, _p]),
     "gfx_graph_fill": (C.c_int, [_p, _p, _p, _p, _i64, _i64, _i64, C.c_int, _p, _p, _p, _p, _p,
                                  _p, _p, _p, _p, _sz, _p]),
+    "gfx_slice_workspace_bytes": (_sz, [_i64, _i64]),
+    "gfx_slice_select": (C.c_int, [_p, _p, _p, _p, _i64, _i64, C.c_int, C.c_int, C.c_int, _p, _p,
+                                   _p, _p, _sz, _p]),
+    "gfx_slice_fill": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, C.c_int, _p,
+                                 _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "gfx_core_rows_workspace_bytes": (_sz, [_i64]),
     "gfx_core_rows": (C.c_int, [_p, _i64, _p, _p, _p, _sz, _p]),
     "gfx_input_linear": (C.c_int, [_p, _p, _i64, _p, C.c_int, _p]),

@@ -11,8 +11,12 @@ reference's.  The sin/cos position columns are tabulated on the host with
 NumPy once per distinct record length (NumPy's float32 sin/cos is not
 correctly rounded, so only NumPy reproduces it) and gathered on the device.
 
-Windowed (sliced) records keep the host path (`GraphBuilder`), and so does
-any graph specification other than the bundled one.
+Windowed (sliced) records go through `gfx_slice_select` / `gfx_slice_fill`
+(reference: graph.py:599-695): the full molecules' strings
+go up, the window, its pairing partners and the breadth-first context are
+selected per record on the device and only the induced subgraphs are written.
+Any graph specification other than the bundled one keeps the host path
+(`GraphBuilder`).
 """
 from __future__ import annotations
 
@@ -30,12 +34,16 @@ _BUNDLED = dict(struct_feature="A", positional=True)
 
 def supports(spec: GraphSpec, records: Sequence) -> bool:
     """True when the device builder covers this request: the bundled feature
-    layout and full-molecule records only."""
+    layout (full-molecule and windowed records alike)."""
     if spec.node_feature_dim != 7 or spec.struct_feature != "A" or not spec.positional:
         return False
     if any(e not in ("skip2",) for e in spec.extra_edges):
         return False
-    return not any(getattr(r, "sliced", False) for r in records)
+    return True
+
+
+def any_sliced(records: Sequence) -> bool:
+    return any(getattr(r, "sliced", False) for r in records)
 
 
 def position_table(lengths: np.ndarray):
@@ -66,17 +74,27 @@ def _pinned_bytes(text: str) -> torch.Tensor:
 
 
 def build_device_shard(records: Sequence, device, spec: GraphSpec = None,
-                       *, with_node_metadata: bool = False, lengths=None) -> DeviceShard:
-    """Device-resident shard of full-molecule graphs for `records` (objects
-    with `.sequence` and `.structure`).  Raises GraphValidationError for
-    characters outside ACGU / ().  and for unbalanced structures."""
+                       *, with_node_metadata: bool = False, lengths=None,
+                       keep_paired_neighbours: bool = False,
+                       context_hops: int = 1) -> DeviceShard:
+    """Device-resident shard of the graphs of `records` (objects with
+    `.sequence`, `.structure` and, for windowed records, `.start` / `.end`),
+    i.e. `GraphBuilder(spec, keep_paired_neighbours=..., context_hops=...)
+    .build_shard(records)` with the arrays born in HBM.  Raises
+    GraphValidationError for characters outside ACGU / ().  and for
+    unbalanced structures."""
     spec = spec if spec is not None else GraphSpec()
     records = list(records)
     if not records:
         raise GraphValidationError("a graph shard needs at least one record")
+    if context_hops < 1:
+        raise ValueError("context_hops must be >= 1")
     if not supports(spec, records):
-        raise GraphValidationError("the device builder covers full-molecule records of the "
-                                   "bundled graph specification only")
+        raise GraphValidationError("the device builder covers the bundled graph "
+                                   "specification only")
+    if any_sliced(records):
+        return _build_sliced(records, device, spec, bool(keep_paired_neighbours),
+                             int(context_hops))
     dev = torch.device(device)
     sequences = [r.sequence for r in records]
     structures = [r.structure for r in records]
@@ -138,4 +156,83 @@ def build_device_shard(records: Sequence, device, spec: GraphSpec = None,
                         core_count=N, spec=spec, core_ptr_host=node_ptr)
     shard.residue_index, shard.node_roles_full = residue, roles
     shard.edge_ptr_host = edge_ptr
+    return shard
+
+
+def _build_sliced(records: list, device, spec: GraphSpec, keep_paired: bool,
+                  hops: int) -> DeviceShard:
+    """Windowed records: selection and induced subgraphs on the device."""
+    dev = torch.device(device)
+    sequences = [r.sequence for r in records]
+    structures = [r.structure for r in records]
+    B = len(records)
+    lengths = np.fromiter(map(len, sequences), np.int64, B)
+    if np.any(lengths < 1) or list(map(len, structures)) != lengths.tolist():
+        raise GraphValidationError("sequence and structure lengths must match and be positive")
+    start = np.zeros(B, np.int32)
+    end = lengths.astype(np.int32)
+    for k, r in enumerate(records):
+        if getattr(r, "sliced", False):
+            if r.start is None or r.end is None:
+                raise GraphValidationError("sliced graph is missing start/end")
+            start[k], end[k] = r.start, r.end
+    if np.any(start < 0) or np.any(end > lengths) or np.any(start >= end):
+        raise GraphValidationError("slice window outside the molecule")
+    full_ptr = np.zeros(B + 1, np.int64)
+    np.cumsum(lengths, out=full_ptr[1:])
+    NF = int(full_ptr[-1])
+    if NF > 1 << 30:
+        raise GraphValidationError("shard exceeds 2^30 nucleotides")
+    try:
+        seq, dbn = _pinned_bytes("".join(sequences)), _pinned_bytes("".join(structures))
+    except UnicodeEncodeError as exc:
+        raise GraphValidationError("sequence contains characters outside ACGU") from exc
+    table, offset = position_table(lengths)
+    skip2 = 1 if "skip2" in spec.extra_edges else 0
+    lib = nat.lib
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream().cuda_stream
+        up = lambda a: torch.from_numpy(a).to(dev, non_blocking=True)  # noqa: E731
+        seq_d, dbn_d = seq.to(dev, non_blocking=True), dbn.to(dev, non_blocking=True)
+        full_ptr_d, start_d, end_d = up(full_ptr), up(start), up(end)
+        table_d, offset_d = up(table), up(offset)
+        ptrs = torch.empty((2, B + 1), dtype=torch.int64, device=dev)
+        status = torch.empty(1, dtype=torch.int32, device=dev)
+        need = lib.gfx_slice_workspace_bytes(NF, B)
+        ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        nat.check(lib.gfx_slice_select(
+            dbn_d.data_ptr(), full_ptr_d.data_ptr(), start_d.data_ptr(), end_d.data_ptr(), B, NF,
+            skip2, 1 if keep_paired else 0, hops, ptrs[0].data_ptr(), ptrs[1].data_ptr(),
+            status.data_ptr(), ws.data_ptr(), need, stream))
+        ptrs_h = ptrs.cpu().numpy()                         # one read-back: N, E and the limits
+        node_ptr, edge_ptr = ptrs_h[0], ptrs_h[1]
+        N, E = int(node_ptr[-1]), int(edge_ptr[-1])
+        feats = torch.empty((N, 7), dtype=torch.float32, device=dev)
+        edge_index = torch.empty((2, E), dtype=torch.int32, device=dev)
+        edge_types = torch.empty(E, dtype=torch.uint8, device=dev)
+        residue = torch.empty(N, dtype=torch.int32, device=dev)
+        roles = torch.empty(N, dtype=torch.uint8, device=dev)
+        nat.check(lib.gfx_slice_fill(
+            seq_d.data_ptr(), dbn_d.data_ptr(), full_ptr_d.data_ptr(), start_d.data_ptr(),
+            end_d.data_ptr(), ptrs[0].data_ptr(), ptrs[1].data_ptr(), B, NF, N, E, skip2,
+            table_d.data_ptr(), offset_d.data_ptr(), feats.data_ptr(),
+            edge_index.data_ptr() if E else None, edge_types.data_ptr() if E else None,
+            residue.data_ptr(), roles.data_ptr(), status.data_ptr(), ws.data_ptr(), need, stream))
+        flags = int(status.item())
+    if flags & 1:
+        raise GraphValidationError("sequence contains characters outside ACGU")
+    if flags & 6:
+        raise GraphValidationError("unbalanced or malformed dot-bracket structure")
+    if flags & 8:
+        raise GraphValidationError("slice window outside the molecule")
+    core_ptr = np.zeros(B + 1, np.int64)
+    np.cumsum((end - start).astype(np.int64), out=core_ptr[1:])
+    all_core = int(core_ptr[-1]) == N
+    shard = DeviceShard(feats, edge_index, edge_types, ptrs[0], ptrs[1],
+                        None if all_core else roles,
+                        max_nodes_per_record=int(np.diff(node_ptr).max()),
+                        max_edges_per_record=int(np.diff(edge_ptr).max()),
+                        core_count=int(core_ptr[-1]), spec=spec, core_ptr_host=core_ptr)
+    shard.residue_index, shard.node_roles_full = residue, roles
+    shard.node_ptr_host, shard.edge_ptr_host = node_ptr, edge_ptr
     return shard

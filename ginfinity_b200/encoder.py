@@ -248,6 +248,12 @@ class Ginfinity:
             return []
         from . import device_builder
         if self.device_builder and device_builder.supports(self._graph_spec, records):
+            if device_builder.any_sliced(records):
+                # windowed records: selection + induced subgraphs on the GPU (K7)
+                return self._encode_sliced_records(
+                    records, int(max_batch_nodes), int(max_batch_edges),
+                    bool(keep_paired_neighbours), int(context_hops),
+                    _embedding_dtype(embedding_dtype))
             # full-molecule records: graphs are built on the GPU (2 B/nt over PCIe
             # instead of 69 B/nt) group by group, the host preparing group g+1
             # while the device encodes group g and copies out group g-1
@@ -531,6 +537,41 @@ class Ginfinity:
         if table.dtype != dtype:
             return split_rows(table.astype(dtype), node_ptr)
         return rows
+
+    def _encode_sliced_records(self, records: list, max_batch_nodes: int, max_batch_edges: int,
+                               keep_paired: bool, hops: int, dtype: np.dtype) -> list:
+        """Windowed records -> embeddings of their core nucleotides, with the
+        selection (graph.py:599-646) and the induced subgraphs (graph.py:649-695)
+        made on the device.  Argument errors are raised before the encode, as in
+        the reference (api.py:196-210); the per-record sizes they need come out of
+        the selection pass."""
+        from . import device_builder as dbuild
+        from .graph import GraphValidationError
+        if hops < 1:
+            raise ValueError("context_hops must be >= 1")
+        if max_batch_nodes <= 0 or max_batch_edges <= 0:
+            raise ValueError("batch node and edge limits must be positive")
+        ids = [r.identifier for r in records]
+        if len(set(ids)) != len(ids):
+            raise GraphValidationError("duplicate identifiers in graph shard")
+        dev = self._torch_device
+        out_code = nat.GFX_F16 if dtype == np.float16 else nat.GFX_F32
+        with torch.cuda.device(dev), torch.inference_mode():
+            ds = dbuild.build_device_shard(records, dev, self._graph_spec,
+                                           keep_paired_neighbours=keep_paired,
+                                           context_hops=hops)
+            self._check_request(ds.spec, ds.max_nodes_per_record, ds.max_edges_per_record,
+                                max_batch_nodes, max_batch_edges, dtype)
+            out = self.encode_device_shard(ds, max_batch_nodes=max_batch_nodes,
+                                           max_batch_edges=max_batch_edges,
+                                           out_dtype=out_code, _checked=True)
+            host = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+            host.copy_(out, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        table = host.numpy()
+        if table.dtype != dtype:
+            table = table.astype(dtype)
+        return split_rows(table, ds.core_ptr_host)
 
     def _enqueue_resident(self, ds: "DeviceShard", plan: np.ndarray, host: torch.Tensor,
                           out_code: int, state: dict) -> None:

@@ -156,6 +156,48 @@ int gfx_graph_fill(const uint8_t *sequences, const uint8_t *structures,
                    void *workspace, size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------
+ * K7  windowed ("sliced") records on the device.  Replaces
+ * _select_slice_nodes, _extract_slice and GraphShard.from_graphs
+ * (graph.py:599-695, 376-412) for the bundled graph specification; every
+ * output array is bit-identical to the reference's.
+ *   sequences / structures / full_ptr: the FULL molecules, as for K6
+ *     (uint8 [NF], int64 [B+1])
+ *   win_start / win_end: int32 [B], the core window [start, end) of each
+ *     record in full-molecule coordinates; a record without a window is
+ *     [0, L) (everything kept, every node core)
+ *   keep_paired_neighbours / context_hops: GraphBuilder's arguments
+ *     (graph.py:471-476); hop 1 adds the pairing partners of core
+ *     nucleotides, hops 2.. the graph neighbours of the previous hop's
+ *     additions
+ * Two phases, because the sliced totals are only known after selection:
+ *   gfx_slice_select -> node_ptr, edge_ptr int64 [B+1] of the SLICED shard
+ *   (host reads N = node_ptr[B], E = edge_ptr[B] and allocates the outputs)
+ *   gfx_slice_fill   -> node_features float32 [N,7] (rows of the full
+ *     molecule's features), edge_index int32 [2,E] (shard-global indices,
+ *     full-graph edge order), edge_types, residue_index int32 [N] (position
+ *     in the full molecule), node_roles uint8 [N] (0 core, 1 context)
+ * pos_table / pos_offset as for K6, tabulated for the FULL lengths.
+ * *status additionally collects GFX_GRAPH_BAD_WINDOW.
+ * ------------------------------------------------------------------------ */
+enum { GFX_GRAPH_BAD_WINDOW = 8 };
+size_t gfx_slice_workspace_bytes(int64_t num_full_nodes, int64_t num_records);
+int gfx_slice_select(const uint8_t *structures, const int64_t *full_ptr,
+                     const int32_t *win_start, const int32_t *win_end,
+                     int64_t num_records, int64_t num_full_nodes, int skip2,
+                     int keep_paired_neighbours, int context_hops,
+                     int64_t *node_ptr, int64_t *edge_ptr, int32_t *status,
+                     void *workspace, size_t workspace_bytes, void *stream);
+int gfx_slice_fill(const uint8_t *sequences, const uint8_t *structures,
+                   const int64_t *full_ptr, const int32_t *win_start,
+                   const int32_t *win_end, const int64_t *node_ptr,
+                   const int64_t *edge_ptr, int64_t num_records,
+                   int64_t num_full_nodes, int64_t num_nodes, int64_t num_edges,
+                   int skip2, const float *pos_table, const int64_t *pos_offset,
+                   float *node_features, int32_t *edge_index, uint8_t *edge_types,
+                   int32_t *residue_index, uint8_t *node_roles, int32_t *status,
+                   void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------
  * Core-row map.  Replaces the per-record boolean masks of api.py:253-259:
  * out_row[i] = rank of node i among nodes with node_roles == 0, or -1 for
  * context nodes; n_core receives the number of core nodes (device int64).

@@ -352,5 +352,7 @@ def test_position_table_reproduces_the_builder_columns_bit_for_bit():
     assert np.array_equal(table[rows].view(np.uint32),
                           np.ascontiguousarray(shard.node_features[:, 5:7]).view(np.uint32))
     assert db.supports(g.GraphSpec(), records)
-    assert not db.supports(g.GraphSpec(), records + [g.RNA("w", "ACGUACGU", "((....))", start=2, end=5)])
+    windowed = records + [g.RNA("w", "ACGUACGU", "((....))", start=2, end=5)]
+    assert db.supports(g.GraphSpec(), windowed) and db.any_sliced(windowed)
+    assert not db.any_sliced(records)
     assert not db.supports(g.GraphSpec(positional=False), records)
