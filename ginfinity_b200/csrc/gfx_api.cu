@@ -256,8 +256,9 @@ extern "C" int gfx_encode(const gfx_model *model, const float *x, const int32_t 
   int rc = gfx_input_linear(model, x, n, h, dtype, stream);
   if (rc) return rc;
   for (int l = 0; l < model->layers; ++l) {
-    if (fused) {
-      rc = gfx_layer_fused(model, l, h, row_ptr, col_src, col_type, n, h2, stream);
+    if (fused) {   // 1: one CTA per SM (gfx_fused5.cu); 2: CTA pairs (gfx_fused6.cu)
+      rc = (fused == 2 ? gfx_layer_fused_pair : gfx_layer_fused)(model, l, h, row_ptr, col_src,
+                                                                 col_type, n, h2, stream);
       if (rc) return rc;
     } else {
       rc = gfx_aggregate(model, l, h, row_ptr, col_src, col_type, n, z, dtype, stream);

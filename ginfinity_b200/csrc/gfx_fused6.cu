@@ -1,0 +1,629 @@
+// One GINE layer in one kernel on CTA PAIRS (tcgen05 cta_group::2): K1 (the
+// aggregation) produces K2's GEMM-1 A operand in shared memory, so z never
+// exists in HBM and h is read once and written once per layer.
+//
+//   h_out = h + LayerNorm(W2 relu(W1' z + b1') + b2),
+//   z_i   = (1+eps) h_i + sum_{e: dst=i} relu(h[src_e] + table[type_e])
+//
+// Why pairs: gfx_fused5.cu (one CTA per SM) keeps 128 KB of weights resident
+// and has 99 KB left, i.e. two 32 KB buffers that each have to be z tile,
+// residual tile and output tile in turn; their life cycle, not the tensor
+// pipe, set its pace.  A CTA pair splits the B operands
+// (each CTA holds the half of W1 / W2 that produces half of the N columns:
+// 64 KB), runs M = 256 MMAs over both CTAs' 128-row tiles, and has 160 KB per
+// CTA for data:
+//   * 3 h-tile buffers (32 KB, TMA, 128-byte swizzle): the tile's own rows of
+//     h serve (i) the producers' self rows and in-tile neighbour rows (~97 % of
+//     the edges of RNA graphs stay inside a 128-row tile; the rest are read
+//     from global memory / L2), (ii) epilogue B's residual, (iii) the output
+//     staging for the TMA store -- loaded once, stored once;
+//   * 2 z stages (32 KB, the UMMA K-major swizzled A operand of GEMM 1).
+// TMEM (512 columns per CTA): D1 [0,256) fp32, overwritten IN PLACE by the
+// fp16 hidden activation A2 [0,128) (epilogue A walks the columns upwards, so
+// it only overwrites what it has already read), D2 double-buffered at
+// [256,384) and [384,512).
+//
+// Warps (32 x 64 registers), per CTA:
+//    0-3   epilogue A   D1 -> + b1, ReLU, fp16 -> A2 (in place)
+//    4-11  epilogue B   two groups of 4, alternating tiles: D2 -> + b2,
+//                       LayerNorm (two passes over TMEM, full rows: no
+//                       exchange between warps), + residual, in place in the
+//                       h-tile buffer
+//   12-27  producers    quarter-warp per node (as K1: shuffled edge fetch,
+//                       branch-free missing edges), rows from the h-tile
+//                       buffer, z row into the z stage; the CSR entries of the
+//                       NEXT tile are fetched before the current one is summed
+//   28     MMA issuer   (rank 0 of the pair issues for both CTAs; both fetch
+//                       their halves of the weights)
+//   29     h-tile loader (TMA)
+//   30     output store  (TMA)
+// Barriers that collect arrivals from both CTAs (z full, A2 full, D2 empty,
+// weights ready) live in rank 0 and are reached with mapa + a cluster-scope
+// arrive; completions of the MMAs are multicast to both CTAs by tcgen05.commit.
+#include "gfx_common.cuh"
+#include "gfx_tma.cuh"
+#include "gfx_umma.cuh"
+
+namespace gfx {
+
+using namespace ptx;
+
+namespace v6 {
+
+constexpr int HID = kMlpHidden, H = HID / 2;
+constexpr int kTileM = 128;
+constexpr int kKbBytes = kTileM * 128;        // one K block of a tile: [128 x 64] fp16
+constexpr int kTileBytes = 2 * kKbBytes;      // a whole [128 x 128] fp16 tile
+constexpr int kStages = 2, kHBufs = 3;
+constexpr int kWPiece = 64 * 128;             // 64 weight rows x 64 columns (one CTA's share)
+constexpr int kTabRows = 11;                  // edge types 0..9 + the "no edge" row
+constexpr uint32_t kTmemCols = 512, kD2Col = 256;
+constexpr int kEpiBWarp0 = 4, kProdWarp0 = 12, kProdWarps = 16, kMmaWarp = 28, kLoadWarp = 29,
+              kStoreWarp = 30, kWarps = 32;
+constexpr int kSrcBits = 27;
+constexpr uint32_t kSrcMask = (1u << kSrcBits) - 1u;
+constexpr int kWin = 5;
+
+enum Bar {
+  kBarWLocal = 0, kBarWReady = 1, kBarHFull = 2, kBarHEmpty = 5, kBarOReady = 8, kBarA1Full = 11,
+  kBarA1Empty = 13, kBarD1aFull = 15, kBarD1bFull = 16, kBarA2aFull = 17, kBarA2bFull = 18,
+  kBarD2Full = 19, kBarD2Empty = 21, kNumBars = 23
+};
+
+struct Smem {
+  static constexpr int off_w1 = 0;                                   // [kb 2][half 2] x 8 KB
+  static constexpr int off_w2 = off_w1 + 4 * kWPiece;                // [kb 4] x 8 KB
+  static constexpr int off_z = off_w2 + 4 * kWPiece;                 // 2 stages x 32 KB
+  static constexpr int off_h = off_z + kStages * kTileBytes;         // 3 tiles x 32 KB
+  static constexpr int off_tab = off_h + kHBufs * kTileBytes;        // fp16 [11][128]
+  static constexpr int off_bar = off_tab + kTabRows * kHidden * 2;
+  static constexpr int off_tmem = off_bar + kNumBars * 8;
+  static constexpr int total = off_tmem + 8;
+};
+static_assert(Smem::total <= 232448, "exceeds the 227 KB shared-memory limit of sm_100");
+
+struct alignas(64) Maps {
+  CUtensorMap h, out;        // [n, 128] fp16, box 64 x 128, SWIZZLE_128B
+};
+
+struct Consts {
+  float b1[HID];
+};
+
+struct Args {
+  const __half *h;
+  const int32_t *row_ptr, *col_src;
+  const uint8_t *col_type;
+  const __half *table16, *w1_img, *w2_img;
+  const float *b2, *g, *b;   // device vectors of this layer
+  int64_t n;
+  int edge_dim;
+  float eps1;
+};
+
+// ---- cluster / cta_group::2 wrappers ------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n"
+               "barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cta address -> shared::cluster address of the same location in CTA `rank`
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+// Arrive on a barrier of another CTA of the cluster.  Default semantics (release at CTA scope),
+// as CUTLASS's ClusterBarrier::arrive does: what the arrival publishes is consumed by the tensor
+// core (shared memory through the async proxy after fence.proxy.async, or TMEM after
+// tcgen05.fence), never through the waiting thread's L1.  The cluster-scope forms cost a
+// MEMBAR + ERRBAR per arrive and a CCTL.IVALL (L1 invalidate) per wait: 30 % of all stall
+// samples in the first version of this kernel.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// parked wait (suspend-time hint) on a local barrier
+__device__ __forceinline__ void mbar_wait_c(uint64_t *bar, uint32_t parity) {
+  mbar_wait_parked(bar, parity);
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t *dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+               "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void mma2_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma2_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on `bar` (same offset in both CTAs of the pair) when all MMAs issued so far are done
+__device__ __forceinline__ void mma2_commit(uint64_t *bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::
+          "r"(smem_u32(bar)),
+      "h"(uint16_t(3))
+      : "memory");
+}
+__device__ __forceinline__ void fence_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t relu_pack2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t hfma2_relu_add(uint32_t x, uint32_t t) {
+  uint32_t r;
+  asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(0x3c003c00u), "r"(t));
+  return r;
+}
+__device__ __forceinline__ void add_pair(float &a0, float &a1, uint32_t m) {
+  asm("{\n.reg .b16 lo, hi;\nmov.b32 {lo, hi}, %2;\nadd.rn.f32.f16 %0, lo, %0;\n"
+      "add.rn.f32.f16 %1, hi, %1;\n}"
+      : "+f"(a0), "+f"(a1)
+      : "r"(m));
+}
+__device__ __forceinline__ void add_message(float *acc, const uint4 &nb, const uint4 &tb) {
+  add_pair(acc[0], acc[1], hfma2_relu_add(nb.x, tb.x));
+  add_pair(acc[2], acc[3], hfma2_relu_add(nb.y, tb.y));
+  add_pair(acc[4], acc[5], hfma2_relu_add(nb.z, tb.z));
+  add_pair(acc[6], acc[7], hfma2_relu_add(nb.w, tb.w));
+}
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, const uint4 &v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w)
+               : "memory");
+}
+// byte offset of 16-byte chunk `c8` (0..7) of row `r` inside one swizzled K block
+__device__ __forceinline__ uint32_t sw_off(int r, int c8) {
+  return uint32_t(r) * 128u + (uint32_t((c8 ^ r) & 7) << 4);
+}
+
+// D1[:, HALF*128 .. +128) -> bias + ReLU -> fp16 -> A2[:, HALF*64 .. +64), 32 columns at a time
+template <int HALF>
+__device__ __forceinline__ void epi_a(const Consts &c, uint32_t trow, uint64_t *bar, uint32_t ph,
+                                      int lane, uint32_t leader_bar) {
+  constexpr int col0 = HALF * H;
+  mbar_wait_c(bar + (HALF ? kBarD1bFull : kBarD1aFull), ph);
+  tc_fence_after();
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float v[32];
+    tmem_ld32(trow + col0 + 32 * q, v);
+    tmem_ld_wait();
+    uint32_t pk[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      pk[j] = relu_pack2(v[2 * j] + c.b1[col0 + 32 * q + 2 * j],
+                         v[2 * j + 1] + c.b1[col0 + 32 * q + 2 * j + 1]);
+    tmem_st16(trow + col0 / 2 + 16 * q, pk);
+  }
+  tmem_st_wait();
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive_cluster(leader_bar);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWarps * 32, 1)
+fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Consts c, const Args p) {
+  using L = Smem;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t *w1s = smem + L::off_w1, *w2s = smem + L::off_w2, *zs = smem + L::off_z;
+  uint8_t *hs = smem + L::off_h;
+  uint4 *tab = reinterpret_cast<uint4 *>(smem + L::off_tab);
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smem + L::off_bar);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::off_tmem);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  if (warp == kMmaWarp) {
+    tmem_alloc2(tmem_slot, kTmemCols);
+  } else if (tid == 0) {
+    mbar_init(bar + kBarWLocal, 1);
+    mbar_init(bar + kBarWReady, 2);
+    for (int s = 0; s < kHBufs; ++s) {
+      mbar_init(bar + kBarHFull + s, 1);
+      mbar_init(bar + kBarHEmpty + s, 1);
+      mbar_init(bar + kBarOReady + s, 4);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar + kBarA1Full + s, 2 * kProdWarps);
+      mbar_init(bar + kBarA1Empty + s, 1);
+      mbar_init(bar + kBarD2Full + s, 1);
+      mbar_init(bar + kBarD2Empty + s, 8);
+    }
+    mbar_init(bar + kBarD1aFull, 1);
+    mbar_init(bar + kBarD1bFull, 1);
+    mbar_init(bar + kBarA2aFull, 8);
+    mbar_init(bar + kBarA2bFull, 8);
+    fence_mbar_init();
+  }
+  for (int i = tid; i < p.edge_dim * kHidden / 8; i += blockDim.x)
+    tab[i] = reinterpret_cast<const uint4 *>(p.table16)[i];
+  for (int i = tid; i < kHidden / 8; i += blockDim.x)               // the "no edge" row: -65504
+    tab[p.edge_dim * kHidden / 8 + i] = make_uint4(0xFBFFFBFFu, 0xFBFFFBFFu, 0xFBFFFBFFu, 0xFBFFFBFFu);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                          // both CTAs' barriers exist before any remote arrive
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  const int n = int(p.n);
+  const int tiles = (n + kTileM - 1) / kTileM;
+  const int pairs = (tiles + 1) / 2;
+  const int cluster_id = blockIdx.x >> 1, clusters = gridDim.x >> 1;
+  // barriers of rank 0 that collect arrivals from both CTAs
+  auto leader = [&](int b) { return map_to_cta(smem_u32(bar + b), 0); };
+
+  if (warp < kEpiBWarp0) {
+    // ================= epilogue A =================================================
+    const uint32_t trow = tmem + (uint32_t(warp * 32) << 16);
+    const uint32_t a2a = leader(kBarA2aFull), a2b = leader(kBarA2bFull);
+    uint32_t it = 0;
+    for (int pair = cluster_id; pair < pairs; pair += clusters, ++it) {
+      epi_a<0>(c, trow, bar, it & 1, lane, a2a);
+      epi_a<1>(c, trow, bar, it & 1, lane, a2b);
+    }
+  } else if (warp < kProdWarp0) {
+    // ================= epilogue B (group g takes iterations it % 2 == g) ===========
+    const int quad = warp & 3, g = (warp - kEpiBWarp0) >> 2;
+    const uint32_t trow = tmem + (uint32_t(quad * 32) << 16) + kD2Col + uint32_t(g) * kHidden;
+    const uint32_t d2e = leader(kBarD2Empty + g);
+    const float4 *b2v = reinterpret_cast<const float4 *>(p.b2);
+    const float4 *gv = reinterpret_cast<const float4 *>(p.g);
+    const float4 *bv = reinterpret_cast<const float4 *>(p.b);
+    const int r = quad * 32 + lane;
+    uint32_t it = 0;
+    for (int pair = cluster_id; pair < pairs; pair += clusters, ++it) {
+      if (int(it & 1) != g) continue;
+      const uint32_t hb = it % kHBufs;
+      mbar_wait_c(bar + kBarD2Full + g, (it >> 1) & 1);
+      tc_fence_after();
+      // 16 columns at a time, loops NOT unrolled: an unrolled body lets the compiler hoist the
+      // vector loads of several chunks and spill (64 registers per thread)
+      float s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};
+#pragma unroll 1
+      for (int q = 0; q < 8; ++q) {
+        float u[16];
+        tmem_ld16(trow + 16 * q, u);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 bb = __ldg(b2v + 4 * q + j4);
+          const float t0 = u[4 * j4] + bb.x, t1 = u[4 * j4 + 1] + bb.y;
+          const float t2 = u[4 * j4 + 2] + bb.z, t3 = u[4 * j4 + 3] + bb.w;
+          s1[0] += t0; s1[1] += t1; s1[0] += t2; s1[1] += t3;
+          s2[0] = fmaf(t0, t0, s2[0]); s2[1] = fmaf(t1, t1, s2[1]);
+          s2[0] = fmaf(t2, t2, s2[0]); s2[1] = fmaf(t3, t3, s2[1]);
+        }
+      }
+      const float mean = (s1[0] + s1[1]) * (1.f / kHidden);
+      const float var = fmaxf((s2[0] + s2[1]) * (1.f / kHidden) - mean * mean, 0.f);
+      const float rstd = rsqrtf(var + 1e-5f);
+      const float nm = -mean * rstd;
+      mbar_wait_c(bar + kBarHFull + hb, (it / kHBufs) & 1);      // long complete: visibility only
+      const uint32_t hrow = smem_u32(hs) + hb * kTileBytes;
+#pragma unroll 1
+      for (int q = 0; q < 8; ++q) {
+        float u[16];
+        tmem_ld16(trow + 16 * q, u);
+        tmem_ld_wait();
+        if (q == 7) {                                     // D2 fully read
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(d2e);
+        }
+#pragma unroll
+        for (int gi = 0; gi < 2; ++gi) {
+          const int c16 = q * 2 + gi;                     // 16-byte chunk of the 256-byte row
+          const uint32_t cell = hrow + uint32_t(c16 >> 3) * kKbBytes + sw_off(r, c16 & 7);
+          const uint4 raw = lds128(cell);
+          const __half2 *hp = reinterpret_cast<const __half2 *>(&raw);
+          float o[8];
+#pragma unroll
+          for (int w = 0; w < 2; ++w) {
+            const int j = gi * 8 + 4 * w, c4 = 4 * q + 2 * gi + w;
+            const float4 bb = __ldg(b2v + c4), gg = __ldg(gv + c4), be = __ldg(bv + c4);
+            const float2 ra = __half22float2(hp[2 * w]), rb = __half22float2(hp[2 * w + 1]);
+            o[4 * w] = fmaf(fmaf(u[j] + bb.x, rstd, nm), gg.x, ra.x + be.x);
+            o[4 * w + 1] = fmaf(fmaf(u[j + 1] + bb.y, rstd, nm), gg.y, ra.y + be.y);
+            o[4 * w + 2] = fmaf(fmaf(u[j + 2] + bb.z, rstd, nm), gg.z, rb.x + be.z);
+            o[4 * w + 3] = fmaf(fmaf(u[j + 3] + bb.w, rstd, nm), gg.w, rb.y + be.w);
+          }
+          sts128(cell, make_uint4(pack2(o[0], o[1]), pack2(o[2], o[3]), pack2(o[4], o[5]),
+                                  pack2(o[6], o[7])));
+        }
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar + kBarOReady + hb);
+    }
+  } else if (warp < kMmaWarp) {
+    // ================= producers: aggregation into the z stage ======================
+    const int ptid = (warp - kProdWarp0) * 32 + lane;
+    const int qid = ptid >> 3, sub = ptid & 7, qbase = lane & 24;
+    const uint4 *hv = reinterpret_cast<const uint4 *>(p.h) + sub;     // row r -> hv[r*16], hv[r*16+8]
+    const uint32_t tvs = smem_u32(tab) + uint32_t(sub) * 16u;          // type t -> tvs + t*256 (+128)
+    const uint32_t none = uint32_t(p.edge_dim) << kSrcBits;
+    const uint32_t a1f[2] = {leader(kBarA1Full), leader(kBarA1Full + 1)};
+
+    struct Idx {                      // CSR entries of this quarter's two rows of a tile
+      int deg[2];
+      uint32_t pk[2];                 // this lane's edge: source | type << 27
+    };
+    auto fetch_idx = [&](int tile, Idx &x) {
+      int beg[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int row = tile * kTileM + qid + 64 * k;
+        beg[k] = 0;
+        x.deg[k] = 0;
+        if (row < n) {
+          beg[k] = p.row_ptr[row];
+          x.deg[k] = p.row_ptr[row + 1] - beg[k];
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int row = tile * kTileM + qid + 64 * k;
+        uint32_t pk = (uint32_t(row < n ? row : 0) & kSrcMask) | none;
+        if (sub < x.deg[k])
+          pk = uint32_t(p.col_src[beg[k] + sub]) | (uint32_t(p.col_type[beg[k] + sub]) << kSrcBits);
+        x.pk[k] = pk;
+      }
+    };
+    Idx nxt;
+    if (cluster_id < pairs) fetch_idx(2 * cluster_id + int(rank), nxt);
+    uint32_t it = 0;
+    for (int pair = cluster_id; pair < pairs; pair += clusters, ++it) {
+      const int tile = 2 * pair + int(rank);
+      const int row0 = tile * kTileM;
+      const uint32_t s = it & 1, hb = it % kHBufs;
+      const Idx cur = nxt;
+      if (pair + clusters < pairs) fetch_idx(2 * (pair + clusters) + int(rank), nxt);
+      const uint32_t hbase = smem_u32(hs) + hb * kTileBytes;
+      const uint32_t zbase = smem_u32(zs) + s * kTileBytes;
+      mbar_wait_c(bar + kBarHFull + hb, (it / kHBufs) & 1);
+      mbar_wait_c(bar + kBarA1Empty + s, ((it >> 1) & 1) ^ 1);
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int lr = qid + 64 * k;
+        float acc[16];
+#pragma unroll
+        for (int ch = 0; ch < 16; ++ch) acc[ch] = 0.f;
+#pragma unroll
+        for (int u = 0; u < kWin; ++u) {
+          const uint32_t e = __shfl_sync(0xffffffffu, cur.pk[k], qbase + u);
+          const int src = int(e & kSrcMask);
+          const uint32_t local = uint32_t(src - row0);
+          uint4 nb0, nb1;
+          if (local < uint32_t(kTileM)) {
+            const uint32_t a = hbase + sw_off(int(local), sub);
+            nb0 = lds128(a);
+            nb1 = lds128(a + kKbBytes);
+          } else {
+            nb0 = hv[int64_t(src) * 16];
+            nb1 = hv[int64_t(src) * 16 + 8];
+          }
+          const uint32_t t = tvs + (e >> kSrcBits) * 256u;
+          add_message(acc, nb0, lds128(t));
+          add_message(acc + 8, nb1, lds128(t + 128u));
+        }
+        if (cur.deg[k] > kWin) {                                     // rare: longer rows
+          const int beg = p.row_ptr[row0 + lr];
+          for (int eidx = beg + kWin; eidx < beg + cur.deg[k]; ++eidx) {
+            const int src = p.col_src[eidx];
+          const uint32_t t = tvs + uint32_t(p.col_type[eidx]) * 256u;
+            add_message(acc, hv[int64_t(src) * 16], lds128(t));
+            add_message(acc + 8, hv[int64_t(src) * 16 + 8], lds128(t + 128u));
+          }
+        }
+        uint4 o0 = make_uint4(0, 0, 0, 0), o1 = make_uint4(0, 0, 0, 0);
+        const uint32_t so = sw_off(lr, sub);
+        if (row0 + lr < n) {
+          const uint4 self0 = lds128(hbase + so), self1 = lds128(hbase + so + kKbBytes);
+          const __half2 *s0 = reinterpret_cast<const __half2 *>(&self0);
+          const __half2 *s1 = reinterpret_cast<const __half2 *>(&self1);
+          uint32_t *p0 = reinterpret_cast<uint32_t *>(&o0), *p1 = reinterpret_cast<uint32_t *>(&o1);
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            const float2 f0 = __half22float2(s0[ch]), f1 = __half22float2(s1[ch]);
+            p0[ch] = pack2(fmaf(p.eps1, f0.x, acc[2 * ch]), fmaf(p.eps1, f0.y, acc[2 * ch + 1]));
+            p1[ch] = pack2(fmaf(p.eps1, f1.x, acc[8 + 2 * ch]), fmaf(p.eps1, f1.y, acc[8 + 2 * ch + 1]));
+          }
+        }
+        sts128(zbase + so, o0);
+        sts128(zbase + so + kKbBytes, o1);
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(a1f[s]);
+    }
+  } else if (warp == kMmaWarp) {
+    // ================= weights (both CTAs) + MMA issue (rank 0) ======================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar + kBarWLocal, 8 * kWPiece);
+      const uint8_t *w1g = reinterpret_cast<const uint8_t *>(p.w1_img);
+      const uint8_t *w2g = reinterpret_cast<const uint8_t *>(p.w2_img);
+      for (int kb = 0; kb < 2; ++kb)
+        for (int half = 0; half < 2; ++half)      // rows [128 half + 64 rank, +64) of K block kb
+          bulk_g2s(w1s + (kb * 2 + half) * kWPiece,
+                   w1g + kb * (HID * 128) + (H * half + 64 * int(rank)) * 128, kWPiece,
+                   bar + kBarWLocal);
+      for (int kb = 0; kb < 4; ++kb)              // rows [64 rank, +64) of K block kb
+        bulk_g2s(w2s + kb * kWPiece, w2g + kb * (kHidden * 128) + 64 * int(rank) * 128, kWPiece,
+                 bar + kBarWLocal);
+      mbar_wait_parked(bar + kBarWLocal, 0);
+      mbar_arrive_cluster(leader(kBarWReady));
+      if (rank == 0) {
+        mbar_wait_c(bar + kBarWReady, 0);
+        constexpr uint32_t idesc = idesc_f16(2 * kTileM, H);     // M = 256 over the pair, N = 128
+        const uint32_t w1a = smem_u32(w1s), w2a = smem_u32(w2s);
+        uint32_t it = 0;
+        for (int pair = cluster_id; pair < pairs; pair += clusters, ++it) {
+          const uint32_t s = it & 1, g = it & 1, ph2 = (it >> 1) & 1, ph = it & 1;
+          const uint32_t za = smem_u32(zs) + s * kTileBytes;
+          mbar_wait_c(bar + kBarA1Full + s, ph2);
+          tc_fence_after();
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+              const int kb = kk >> 2, k = kk & 3;
+              const uint64_t da = smem_desc_sw128(za + kb * kKbBytes + k * 32);
+              const uint64_t db = smem_desc_sw128(w1a + (kb * 2 + half) * kWPiece + k * 32);
+              mma2_f16_ss(tmem + half * H, da, db, idesc, kk != 0);
+            }
+            mma2_commit(bar + (half ? kBarD1bFull : kBarD1aFull));
+          }
+          mma2_commit(bar + kBarA1Empty + s);          // z consumed in both CTAs
+          mbar_wait_c(bar + kBarA2aFull, ph);
+          mbar_wait_c(bar + kBarD2Empty + g, ph2 ^ 1);
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < HID / 16; ++kk) {
+            if (kk == H / 16) {
+              mbar_wait_c(bar + kBarA2bFull, ph);
+              tc_fence_after();
+            }
+            const uint64_t db = smem_desc_sw128(w2a + (kk >> 2) * kWPiece + (kk & 3) * 32);
+            mma2_f16_ts(tmem + kD2Col + g * kHidden, tmem + kk * 8, db, idesc, kk != 0);
+          }
+          mma2_commit(bar + kBarD2Full + g);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == kLoadWarp) {
+    // ================= h tiles (TMA) =================================================
+    if (lane == 0) {
+      prefetch_tmap(&maps.h);
+      uint32_t it = 0;
+      for (int pair = cluster_id; pair < pairs; pair += clusters, ++it) {
+        const uint32_t hb = it % kHBufs;
+        const int row0 = (2 * pair + int(rank)) * kTileM;
+        uint8_t *dst = hs + hb * kTileBytes;
+        mbar_wait_parked(bar + kBarHEmpty + hb, ((it / kHBufs) & 1) ^ 1);
+        mbar_arrive_expect_tx(bar + kBarHFull + hb, kTileBytes);
+        tma_load_2d(dst, &maps.h, 0, row0, bar + kBarHFull + hb);
+        tma_load_2d(dst + kKbBytes, &maps.h, 64, row0, bar + kBarHFull + hb);
+      }
+    }
+    __syncwarp();
+  } else if (warp == kStoreWarp) {
+    // ================= output store (TMA) ============================================
+    if (lane == 0) {
+      prefetch_tmap(&maps.out);
+      uint32_t it = 0;
+      for (int pair = cluster_id; pair < pairs; pair += clusters, ++it) {
+        const uint32_t hb = it % kHBufs;
+        const int row0 = (2 * pair + int(rank)) * kTileM;
+        const uint8_t *src = hs + hb * kTileBytes;
+        mbar_wait_parked(bar + kBarOReady + hb, (it / kHBufs) & 1);
+        if (row0 < n) {
+          tma_store_2d(&maps.out, 0, row0, src);
+          tma_store_2d(&maps.out, 64, row0, src + kKbBytes);
+        }
+        bulk_commit();
+        bulk_wait_read<0>();                      // shared memory has been read: the buffer is free
+        mbar_arrive(bar + kBarHEmpty + hb);
+      }
+      bulk_wait_all();
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                             // the peer may still be arriving on our barriers
+  if (warp == kMmaWarp) tmem_dealloc2(tmem, kTmemCols);
+}
+
+}  // namespace v6
+
+int fused6_layer(const gfx_model *m, int layer, const __half *h, const int32_t *row_ptr,
+                 const int32_t *col_src, const uint8_t *col_type, int64_t n, __half *h_out,
+                 cudaStream_t st) {
+  if ((reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(h_out)) & 15)
+    return fail(GFX_ERR_ARGUMENT, "fused layer: activation buffers must be 16-byte aligned");
+  if (h == h_out) return fail(GFX_ERR_ARGUMENT, "fused layer: h and h_out must not alias");
+  if (n > (int64_t(1) << v6::kSrcBits))
+    return fail(GFX_ERR_UNSUPPORTED, "fused layer (CTA pairs): at most 2^27 nodes per call");
+  if (m->edge_dim >= v6::kTabRows)
+    return fail(GFX_ERR_UNSUPPORTED, "fused layer (CTA pairs): at most 10 edge types");
+  v6::Maps maps;
+  int rc = tma::make_rows128_map(&maps.h, h, n, v6::kTileM);
+  if (!rc) rc = tma::make_rows128_map(&maps.out, h_out, n, v6::kTileM);
+  if (rc) return rc;
+  v6::Consts c;
+  const gfx_host_vectors &hv = m->host;
+  for (int i = 0; i < kMlpHidden; ++i) c.b1[i] = hv.b1[size_t(layer) * kMlpHidden + i];
+  const size_t wi = size_t(layer) * kMlpHidden * kHidden;
+  v6::Args a{};
+  a.h = h; a.row_ptr = row_ptr; a.col_src = col_src; a.col_type = col_type;
+  a.table16 = m->table16 + size_t(layer) * m->edge_dim * kHidden;
+  a.w1_img = m->w1_img + wi; a.w2_img = m->w2_img + wi;
+  a.b2 = m->b2 + size_t(layer) * kHidden;
+  a.g = m->ln_g + size_t(layer) * kHidden;
+  a.b = m->ln_b + size_t(layer) * kHidden;
+  a.n = n; a.edge_dim = m->edge_dim; a.eps1 = m->eps1[layer];
+  GFX_CUDA(cudaFuncSetAttribute(v6::fused_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                v6::Smem::total));
+  const int64_t tiles = (n + v6::kTileM - 1) / v6::kTileM;
+  const int64_t pairs = (tiles + 1) / 2;
+  const int clusters = int(pairs < kNumSMs / 2 ? pairs : kNumSMs / 2);
+  v6::fused_pair_kernel<<<2 * clusters, v6::kWarps * 32, v6::Smem::total, st>>>(maps, c, a);
+  GFX_LAUNCH_CHECK();
+  return GFX_OK;
+}
+
+}  // namespace gfx
+
+extern "C" int gfx_layer_fused_pair(const gfx_model *m, int layer, const void *h,
+                                    const int32_t *row_ptr, const int32_t *col_src,
+                                    const uint8_t *col_type, int64_t n, void *h_out,
+                                    void *stream) {
+  using namespace gfx;
+  if (!m || layer < 0 || layer >= m->layers)
+    return fail(GFX_ERR_ARGUMENT, "gfx_layer_fused_pair: bad model or layer");
+  if (n <= 0) return GFX_OK;
+  cudaStream_t st = as_stream(stream);
+  StageScope scope(GFX_STAGE_FUSED_LAYER, st, 1);
+  return fused6_layer(m, layer, static_cast<const __half *>(h), row_ptr, col_src, col_type, n,
+                      static_cast<__half *>(h_out), st);
+}

@@ -235,6 +235,14 @@ int gfx_layer_fused(const gfx_model *model, int layer, const void *h,
                     const uint8_t *col_type, int64_t num_nodes, void *h_out,
                     void *stream);
 
+/* K1+K2 in one kernel on CTA pairs (tcgen05 cta_group::2: the pair shares
+ * the weights, each CTA keeps its tile of h resident as neighbour source,
+ * residual and output staging); GFX_F16 only, <= 10 edge types, <= 2^27 nodes */
+int gfx_layer_fused_pair(const gfx_model *model, int layer, const void *h,
+                         const int32_t *row_ptr, const int32_t *col_src,
+                         const uint8_t *col_type, int64_t num_nodes, void *h_out,
+                         void *stream);
+
 /* K3: y = Wb relu(Wa h + ba) + bb; out[out_row[i]] = y_i / max(|y_i|, 1e-12)
  * cast to out_dtype.  out_row == NULL means identity.
  *                                (_model.py:61-63,72; api.py:250-259) */

@@ -332,22 +332,25 @@ def test_head_l2norm(nat, dev, problem, code, impl, out_code):
         1e-5 if out_code == 1 else 2e-3)
 
 
-def test_fused_layer_matches_oracle(nat, dev, problem):
+@pytest.mark.parametrize("entry", ["gfx_layer_fused", "gfx_layer_fused_pair"])
+def test_fused_layer_matches_oracle(nat, dev, problem, entry):
     """K1+K2 in one kernel (aggregation warps feed the tcgen05 pipeline through
-    shared memory) against the oracle's h1 given its h0."""
+    shared memory; one CTA per SM, or CTA pairs sharing the weights) against
+    the oracle's h1 given its h0."""
+    fused = getattr(nat.lib, entry)
     keep = problem["keep16"]
     rp, cs, ct = problem["csr"]
     n = keep["h0"].shape[0]
     h = _up(keep["h0"], dev).to(torch.float16)
     out = _buf(n, 0, dev)
-    nat.check(nat.lib.gfx_layer_fused(problem["handle"], 0, h.data_ptr(), rp.data_ptr(),
-                                      cs.data_ptr(), ct.data_ptr(), n, out.data_ptr(), _stream()))
+    nat.check(fused(problem["handle"], 0, h.data_ptr(), rp.data_ptr(),
+                    cs.data_ptr(), ct.data_ptr(), n, out.data_ptr(), _stream()))
     torch.cuda.synchronize()
     got, want = out.float().cpu().numpy(), keep["h1"]
     assert np.abs(got - want).max() <= 4e-3 * np.abs(want).max()
     out2 = _buf(n, 0, dev)
-    nat.check(nat.lib.gfx_layer_fused(problem["handle"], 0, h.data_ptr(), rp.data_ptr(),
-                                      cs.data_ptr(), ct.data_ptr(), n, out2.data_ptr(), _stream()))
+    nat.check(fused(problem["handle"], 0, h.data_ptr(), rp.data_ptr(),
+                    cs.data_ptr(), ct.data_ptr(), n, out2.data_ptr(), _stream()))
     torch.cuda.synchronize()
     assert torch.equal(out, out2)          # deterministic
 
@@ -369,7 +372,7 @@ def test_tile_edges(nat, dev, problem, n):
         assert (o.float() - outs[0].float()).abs().max().item() <= 4e-3 * float(np.abs(keep["h1"]).max())
 
 
-@pytest.mark.parametrize("code,impl,fused", [(1, 1, 0), (0, 1, 0), (0, 2, 0), (0, 3, 0), (0, 4, 0), (0, 5, 0), (0, 2, 1)])
+@pytest.mark.parametrize("code,impl,fused", [(1, 1, 0), (0, 1, 0), (0, 2, 0), (0, 3, 0), (0, 4, 0), (0, 5, 0), (0, 2, 1), (0, 5, 2)])
 def test_whole_forward(nat, dev, problem, code, impl, fused):
     """gfx_encode (all stages chained on device) against the oracle."""
     x = _up(problem["shard"].node_features, dev)

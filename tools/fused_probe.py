@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Developer probe: run gfx_layer_fused a few times on a tiled synthetic graph
-(for ncu captures of the fused layer kernel)."""
+"""Developer probe: run a fused layer entry point (argv[1]: gfx_layer_fused or
+gfx_layer_fused_pair, default the pair kernel) a few times on a synthetic
+graph, for ncu captures."""
 import sys
 from pathlib import Path
 
@@ -32,8 +33,9 @@ nat.check(lib.gfx_csr_build(ei[0].data_ptr(), ei[1].data_ptr(), et.data_ptr(), N
                             ws.data_ptr(), need, S()))
 h = torch.randn(N, 128, device=dev).half()
 out = torch.empty_like(h)
+entry = getattr(lib, sys.argv[1] if len(sys.argv) > 1 else "gfx_layer_fused_pair")
 def run():
-    nat.check(lib.gfx_layer_fused(handle, 0, h.data_ptr(), row_ptr.data_ptr(), col_src.data_ptr(),
+    nat.check(entry(handle, 0, h.data_ptr(), row_ptr.data_ptr(), col_src.data_ptr(),
                                   col_type.data_ptr(), N, out.data_ptr(), S()))
 for _ in range(4):
     run()

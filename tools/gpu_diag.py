@@ -6,6 +6,7 @@ block) and times every stage kernel with CUDA events.  Not a test, not the
 bench; output goes to stdout and gpurun_out/diag.json.
 """
 import json
+import os
 import sys
 import time
 from pathlib import Path
@@ -106,7 +107,7 @@ def main():
     t = timeit(csr)
     report["csr_s"] = t
     print(f"csr_build: {t * 1e3:.3f} ms  ({E / t / 1e9:.2f} Gedge/s)")
-    for code, name in ((0, "f16"), (1, "f32")):
+    for code, name in (((0, "f16"),) if os.environ.get("GFX_DIAG_FAST") else ((0, "f16"), (1, "f32"))):
         tdt = torch.float16 if code == 0 else torch.float32
         hh = torch.randn(N, 128, device=dev).to(tdt)
         zz = torch.empty_like(hh)
@@ -120,6 +121,8 @@ def main():
         report[f"aggregate_{name}_s"] = t
         report[f"aggregate_{name}_gbs"] = alg / t / 1e9
         impls = ((1, "simt"), (3, "umma_serial"), (2, "umma"), (4, "umma_tma"), (5, "umma_lean")) if code == 0 else ((1, "simt"),)
+        if os.environ.get("GFX_DIAG_FAST"):
+            impls = ((5, "umma_lean"),) if code == 0 else ()
         for impl, iname in impls:
             t = timeit(lambda: nat.check(lib.gfx_mlp_ln_residual(handle, 0, zz.data_ptr(), hh.data_ptr(), N, h2.data_ptr(), code, impl, S())), iters=5, warm=2)
             fl = N * 131072.0
@@ -143,6 +146,12 @@ def main():
             t = timeit(lambda: nat.check(lib.gfx_encode(handle, x_d.data_ptr(), row_ptr.data_ptr(), col_src.data_ptr(), col_type.data_ptr(), None, N, out.data_ptr(), 0, 0, 2, 1, wse.data_ptr(), need_e, S())), iters=3, warm=1)
             print(f"encode[f16,fused]: {t * 1e3:.3f} ms  {N / t / 1e6:.1f} M nt/s")
             report["encode_f16_fused_nts"] = N / t
+            t = timeit(lambda: nat.check(lib.gfx_layer_fused_pair(handle, 0, hh.data_ptr(), row_ptr.data_ptr(), col_src.data_ptr(), col_type.data_ptr(), N, h2.data_ptr(), S())), iters=5, warm=2)
+            print(f"fused_pair_layer[f16]: {t * 1e3:.3f} ms  {N * 131072.0 / t / 1e12:.1f} TFLOP/s  {N / t / 1e9:.2f} G node-layers/s")
+            report["fused_pair_layer_s"] = t
+            t = timeit(lambda: nat.check(lib.gfx_encode(handle, x_d.data_ptr(), row_ptr.data_ptr(), col_src.data_ptr(), col_type.data_ptr(), None, N, out.data_ptr(), 0, 0, 5, 2, wse.data_ptr(), need_e, S())), iters=3, warm=1)
+            print(f"encode[f16,fused_pair]: {t * 1e3:.3f} ms  {N / t / 1e6:.1f} M nt/s")
+            report["encode_f16_fused_pair_nts"] = N / t
     Path(ROOT / "gpurun_out").mkdir(exist_ok=True)
     (ROOT / "gpurun_out" / "diag.json").write_text(json.dumps(report, indent=1))
 
