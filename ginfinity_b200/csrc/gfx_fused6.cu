@@ -23,20 +23,21 @@
 // it only overwrites what it has already read), D2 double-buffered at
 // [256,384) and [384,512).
 //
-// Warps (32 x 64 registers), per CTA:
+// Warps (24; 80 registers per thread at launch, re-balanced with setmaxnreg: the producers get
+// 104, the utility warpgroup 40), per CTA:
 //    0-3   epilogue A   D1 -> + b1, ReLU, fp16 -> A2 (in place)
 //    4-11  epilogue B   two groups of 4, alternating tiles: D2 -> + b2,
 //                       LayerNorm (two passes over TMEM, full rows: no
 //                       exchange between warps), + residual, in place in the
 //                       h-tile buffer
-//   12-27  producers    quarter-warp per node (as K1: shuffled edge fetch,
+//   12-19  producers    quarter-warp per node (as K1: shuffled edge fetch,
 //                       branch-free missing edges), rows from the h-tile
 //                       buffer, z row into the z stage; the CSR entries of the
 //                       NEXT tile are fetched before the current one is summed
-//   28     MMA issuer   (rank 0 of the pair issues for both CTAs; both fetch
+//   20     MMA issuer   (rank 0 of the pair issues for both CTAs; both fetch
 //                       their halves of the weights)
-//   29     h-tile loader (TMA)
-//   30     output store  (TMA)
+//   21     h-tile loader (TMA)
+//   22     output store  (TMA)
 // Barriers that collect arrivals from both CTAs (z full, A2 full, D2 empty,
 // weights ready) live in rank 0 and are reached with mapa + a cluster-scope
 // arrive; completions of the MMAs are multicast to both CTAs by tcgen05.commit.
@@ -58,8 +59,11 @@ constexpr int kStages = 2, kHBufs = 3;
 constexpr int kWPiece = 64 * 128;             // 64 weight rows x 64 columns (one CTA's share)
 constexpr int kTabRows = 11;                  // edge types 0..9 + the "no edge" row
 constexpr uint32_t kTmemCols = 512, kD2Col = 256;
-constexpr int kEpiBWarp0 = 4, kProdWarp0 = 12, kProdWarps = 16, kMmaWarp = 28, kLoadWarp = 29,
-              kStoreWarp = 30, kWarps = 32;
+constexpr int kEpiBWarp0 = 4, kProdWarp0 = 12, kProdWarps = 8, kMmaWarp = 20, kLoadWarp = 21,
+              kStoreWarp = 22, kWarps = 24;
+constexpr int kQuarters = kProdWarps * 4;             // quarter-warps producing z rows
+constexpr int kRowsPerQuarter = kTileM / kQuarters;   // rows of a tile per quarter-warp
+static_assert(kRowsPerQuarter * kQuarters == kTileM, "tile rows must divide evenly");
 constexpr int kSrcBits = 27;
 constexpr uint32_t kSrcMask = (1u << kSrcBits) - 1u;
 constexpr int kWin = 5;
@@ -169,6 +173,16 @@ __device__ __forceinline__ void mma2_commit(uint64_t *bar) {
       "h"(uint16_t(3))
       : "memory");
 }
+// Register reallocation between warpgroups (4 consecutive warps): the launch gives every thread
+// 64 registers (1024 threads); the utility warpgroup needs far fewer and the producers a few more.
+template <int N>
+__device__ __forceinline__ void reg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void reg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
 __device__ __forceinline__ void fence_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t relu_pack2(float lo, float hi) {
@@ -183,11 +197,11 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
 }
 __device__ __forceinline__ uint32_t hfma2_relu_add(uint32_t x, uint32_t t) {
   uint32_t r;
-  asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(0x3c003c00u), "r"(t));
+  asm volatile("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(0x3c003c00u), "r"(t));
   return r;
 }
 __device__ __forceinline__ void add_pair(float &a0, float &a1, uint32_t m) {
-  asm("{\n.reg .b16 lo, hi;\nmov.b32 {lo, hi}, %2;\nadd.rn.f32.f16 %0, lo, %0;\n"
+  asm volatile("{\n.reg .b16 lo, hi;\nmov.b32 {lo, hi}, %2;\nadd.rn.f32.f16 %0, lo, %0;\n"
       "add.rn.f32.f16 %1, hi, %1;\n}"
       : "+f"(a0), "+f"(a1)
       : "r"(m));
@@ -209,6 +223,23 @@ __device__ __forceinline__ void sts128(uint32_t saddr, const uint4 &v) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z),
                "r"(v.w)
                : "memory");
+}
+// 16 bytes of a neighbour row: from the resident h tile when the source lies in this tile, else
+// from global memory (L2).  One predicated instruction of each kind writing the SAME registers:
+// written as an if/else, the compiler predicates both paths into separate registers and merges
+// them with eight moves per row.
+__device__ __forceinline__ uint4 ld_tile_or_global(uint32_t in_tile, uint32_t saddr, const uint4 *gptr) {
+  uint4 v;
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "setp.ne.b32 q, %4, 0;\n"
+      "@q ld.shared.v4.u32 {%0, %1, %2, %3}, [%5];\n"
+      "@!q ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%6];\n"
+      "}\n"
+      : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+      : "r"(in_tile), "r"(saddr), "l"(gptr));
+  return v;
 }
 // byte offset of 16-byte chunk `c8` (0..7) of row `r` inside one swizzled K block
 __device__ __forceinline__ uint32_t sw_off(int r, int c8) {
@@ -293,6 +324,7 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Con
 
   if (warp < kEpiBWarp0) {
     // ================= epilogue A =================================================
+    reg_dec<64>();
     const uint32_t trow = tmem + (uint32_t(warp * 32) << 16);
     const uint32_t a2a = leader(kBarA2aFull), a2b = leader(kBarA2bFull);
     uint32_t it = 0;
@@ -376,107 +408,136 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Con
     }
   } else if (warp < kMmaWarp) {
     // ================= producers: aggregation into the z stage ======================
+    reg_inc<104>();
     const int ptid = (warp - kProdWarp0) * 32 + lane;
     const int qid = ptid >> 3, sub = ptid & 7, qbase = lane & 24;
     const uint4 *hv = reinterpret_cast<const uint4 *>(p.h) + sub;     // row r -> hv[r*16], hv[r*16+8]
     const uint32_t tvs = smem_u32(tab) + uint32_t(sub) * 16u;          // type t -> tvs + t*256 (+128)
-    const uint32_t none = uint32_t(p.edge_dim) << kSrcBits;
     const uint32_t a1f[2] = {leader(kBarA1Full), leader(kBarA1Full + 1)};
 
-    struct Idx {                      // CSR entries of this quarter's two rows of a tile
-      int deg[2];
-      uint32_t pk[2];                 // this lane's edge: source | type << 27
+    // This quarter-warp owns rows qid + 32 k (k = 0..3) of every tile of its CTA: a sequence of
+    // "row steps" j (tile iteration j / 4, row group j % 4).  The CSR entries travel through a
+    // register pipeline so that no load is consumed near the step that issues it: row_ptr
+    // three steps ahead (A), this lane's edge (source, type) two steps ahead (B1 -> B0),
+    // packed and used now.
+    const int my_iters = cluster_id < pairs ? (pairs - cluster_id + clusters - 1) / clusters : 0;
+    const int steps = kRowsPerQuarter * my_iters;
+    auto row_of = [&](int j) {
+      return (2 * (cluster_id + (j / kRowsPerQuarter) * clusters) + int(rank)) * kTileM + qid +
+             kQuarters * (j % kRowsPerQuarter);
     };
-    auto fetch_idx = [&](int tile, Idx &x) {
-      int beg[2];
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const int row = tile * kTileM + qid + 64 * k;
-        beg[k] = 0;
-        x.deg[k] = 0;
+    int begA = 0, endA = 0, srcB0 = 0, typB0 = 0, srcB1 = 0, typB1 = 0;
+    auto load_a = [&](int j) {
+      begA = endA = 0;
+      if (j < steps) {
+        const int row = row_of(j);
         if (row < n) {
-          beg[k] = p.row_ptr[row];
-          x.deg[k] = p.row_ptr[row + 1] - beg[k];
+          begA = p.row_ptr[row];
+          endA = p.row_ptr[row + 1];
         }
       }
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const int row = tile * kTileM + qid + 64 * k;
-        uint32_t pk = (uint32_t(row < n ? row : 0) & kSrcMask) | none;
-        if (sub < x.deg[k])
-          pk = uint32_t(p.col_src[beg[k] + sub]) | (uint32_t(p.col_type[beg[k] + sub]) << kSrcBits);
-        x.pk[k] = pk;
+    };
+    auto load_b = [&](int j, int &src, int &typ) {       // consumes A
+      const int row = j < steps ? row_of(j) : 0;
+      src = row < n ? row : 0;                           // no edge: the node itself, "none" type
+      typ = p.edge_dim;
+      if (begA + sub < endA) {
+        src = p.col_src[begA + sub];
+        typ = p.col_type[begA + sub];
       }
     };
-    Idx nxt;
-    if (cluster_id < pairs) fetch_idx(2 * cluster_id + int(rank), nxt);
-    uint32_t it = 0;
-    for (int pair = cluster_id; pair < pairs; pair += clusters, ++it) {
-      const int tile = 2 * pair + int(rank);
-      const int row0 = tile * kTileM;
+    load_a(0);
+    load_b(0, srcB0, typB0);
+    load_a(1);
+    load_b(1, srcB1, typB1);
+    load_a(2);
+#pragma unroll 1
+    for (int j = 0; j < steps; ++j) {
+      const uint32_t it = uint32_t(j) / kRowsPerQuarter;
+      const int k = j % kRowsPerQuarter;
       const uint32_t s = it & 1, hb = it % kHBufs;
-      const Idx cur = nxt;
-      if (pair + clusters < pairs) fetch_idx(2 * (pair + clusters) + int(rank), nxt);
+      const int row0 = (2 * (cluster_id + int(it) * clusters) + int(rank)) * kTileM;
+      const uint32_t pk = (uint32_t(srcB0) & kSrcMask) | (uint32_t(typB0) << kSrcBits);
+      srcB0 = srcB1;
+      typB0 = typB1;
+      load_b(j + 2, srcB1, typB1);
+      load_a(j + 3);
       const uint32_t hbase = smem_u32(hs) + hb * kTileBytes;
       const uint32_t zbase = smem_u32(zs) + s * kTileBytes;
-      mbar_wait_c(bar + kBarHFull + hb, (it / kHBufs) & 1);
-      mbar_wait_c(bar + kBarA1Empty + s, ((it >> 1) & 1) ^ 1);
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const int lr = qid + 64 * k;
-        float acc[16];
-#pragma unroll
-        for (int ch = 0; ch < 16; ++ch) acc[ch] = 0.f;
-#pragma unroll
-        for (int u = 0; u < kWin; ++u) {
-          const uint32_t e = __shfl_sync(0xffffffffu, cur.pk[k], qbase + u);
-          const int src = int(e & kSrcMask);
-          const uint32_t local = uint32_t(src - row0);
-          uint4 nb0, nb1;
-          if (local < uint32_t(kTileM)) {
-            const uint32_t a = hbase + sw_off(int(local), sub);
-            nb0 = lds128(a);
-            nb1 = lds128(a + kKbBytes);
-          } else {
-            nb0 = hv[int64_t(src) * 16];
-            nb1 = hv[int64_t(src) * 16 + 8];
-          }
-          const uint32_t t = tvs + (e >> kSrcBits) * 256u;
-          add_message(acc, nb0, lds128(t));
-          add_message(acc + 8, nb1, lds128(t + 128u));
-        }
-        if (cur.deg[k] > kWin) {                                     // rare: longer rows
-          const int beg = p.row_ptr[row0 + lr];
-          for (int eidx = beg + kWin; eidx < beg + cur.deg[k]; ++eidx) {
-            const int src = p.col_src[eidx];
-          const uint32_t t = tvs + uint32_t(p.col_type[eidx]) * 256u;
-            add_message(acc, hv[int64_t(src) * 16], lds128(t));
-            add_message(acc + 8, hv[int64_t(src) * 16 + 8], lds128(t + 128u));
-          }
-        }
-        uint4 o0 = make_uint4(0, 0, 0, 0), o1 = make_uint4(0, 0, 0, 0);
-        const uint32_t so = sw_off(lr, sub);
-        if (row0 + lr < n) {
-          const uint4 self0 = lds128(hbase + so), self1 = lds128(hbase + so + kKbBytes);
-          const __half2 *s0 = reinterpret_cast<const __half2 *>(&self0);
-          const __half2 *s1 = reinterpret_cast<const __half2 *>(&self1);
-          uint32_t *p0 = reinterpret_cast<uint32_t *>(&o0), *p1 = reinterpret_cast<uint32_t *>(&o1);
-#pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
-            const float2 f0 = __half22float2(s0[ch]), f1 = __half22float2(s1[ch]);
-            p0[ch] = pack2(fmaf(p.eps1, f0.x, acc[2 * ch]), fmaf(p.eps1, f0.y, acc[2 * ch + 1]));
-            p1[ch] = pack2(fmaf(p.eps1, f1.x, acc[8 + 2 * ch]), fmaf(p.eps1, f1.y, acc[8 + 2 * ch + 1]));
-          }
-        }
-        sts128(zbase + so, o0);
-        sts128(zbase + so + kKbBytes, o1);
+      if (k == 0) {
+        mbar_wait_c(bar + kBarHFull + hb, (it / kHBufs) & 1);
+        mbar_wait_c(bar + kBarA1Empty + s, ((it >> 1) & 1) ^ 1);
       }
-      fence_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(a1f[s]);
+      const int lr = qid + kQuarters * k;
+      float acc[16];
+#pragma unroll
+      for (int ch = 0; ch < 16; ++ch) acc[ch] = 0.f;
+      // Half a row (16 bytes per lane) ahead: the next half row is requested before the current
+      // one is summed.  The asm statements are volatile, so this order is the order of the
+      // machine code; left to itself the compiler hoists all ten row loads and spills.
+      struct Edge {
+        uint32_t in_tile, a, t;        // smem address of the row chunk, table address
+        const uint4 *gp;
+      };
+      auto edge = [&](int u) {
+        const uint32_t e = __shfl_sync(0xffffffffu, pk, qbase + u);
+        const int src = int(e & kSrcMask);
+        const uint32_t local = uint32_t(src - row0);
+        Edge x;
+        x.in_tile = local < uint32_t(kTileM) ? 1u : 0u;
+        x.a = hbase + sw_off(int(local), sub);
+        x.gp = hv + int64_t(src) * 16;
+        x.t = tvs + (e >> kSrcBits) * 256u;
+        return x;
+      };
+      Edge cur = edge(0);
+      uint4 d0 = ld_tile_or_global(cur.in_tile, cur.a, cur.gp);
+#pragma unroll
+      for (int u = 0; u < kWin; ++u) {
+        const uint4 d1 = ld_tile_or_global(cur.in_tile, cur.a + kKbBytes, cur.gp + 8);
+        add_message(acc, d0, lds128(cur.t));
+        const uint32_t t1 = cur.t + 128u;
+        if (u + 1 < kWin) {
+          cur = edge(u + 1);
+          d0 = ld_tile_or_global(cur.in_tile, cur.a, cur.gp);
+        }
+        add_message(acc + 8, d1, lds128(t1));
+      }
+      // rare: rows longer than the window (lane kWin of the quarter holds edge kWin, if any)
+      if ((__shfl_sync(0xffffffffu, pk, qbase + kWin) >> kSrcBits) != uint32_t(p.edge_dim)) {
+        const int beg = p.row_ptr[row0 + lr], end = p.row_ptr[row0 + lr + 1];
+        for (int eidx = beg + kWin; eidx < end; ++eidx) {
+          const int src = p.col_src[eidx];
+          const uint32_t t = tvs + uint32_t(p.col_type[eidx]) * 256u;
+          add_message(acc, hv[int64_t(src) * 16], lds128(t));
+          add_message(acc + 8, hv[int64_t(src) * 16 + 8], lds128(t + 128u));
+        }
+      }
+      uint4 o0 = make_uint4(0, 0, 0, 0), o1 = make_uint4(0, 0, 0, 0);
+      const uint32_t so = sw_off(lr, sub);
+      if (row0 + lr < n) {
+        const uint4 self0 = lds128(hbase + so), self1 = lds128(hbase + so + kKbBytes);
+        const __half2 *s0 = reinterpret_cast<const __half2 *>(&self0);
+        const __half2 *s1 = reinterpret_cast<const __half2 *>(&self1);
+        uint32_t *p0 = reinterpret_cast<uint32_t *>(&o0), *p1 = reinterpret_cast<uint32_t *>(&o1);
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          const float2 f0 = __half22float2(s0[ch]), f1 = __half22float2(s1[ch]);
+          p0[ch] = pack2(fmaf(p.eps1, f0.x, acc[2 * ch]), fmaf(p.eps1, f0.y, acc[2 * ch + 1]));
+          p1[ch] = pack2(fmaf(p.eps1, f1.x, acc[8 + 2 * ch]), fmaf(p.eps1, f1.y, acc[8 + 2 * ch + 1]));
+        }
+      }
+      sts128(zbase + so, o0);
+      sts128(zbase + so + kKbBytes, o1);
+      if (k == kRowsPerQuarter - 1) {
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(a1f[s]);
+      }
     }
   } else if (warp == kMmaWarp) {
     // ================= weights (both CTAs) + MMA issue (rank 0) ======================
+    reg_dec<40>();
     if (lane == 0) {
       mbar_arrive_expect_tx(bar + kBarWLocal, 8 * kWPiece);
       const uint8_t *w1g = reinterpret_cast<const uint8_t *>(p.w1_img);
@@ -532,6 +593,7 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Con
     __syncwarp();
   } else if (warp == kLoadWarp) {
     // ================= h tiles (TMA) =================================================
+    reg_dec<40>();
     if (lane == 0) {
       prefetch_tmap(&maps.h);
       uint32_t it = 0;
@@ -548,6 +610,7 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Con
     __syncwarp();
   } else if (warp == kStoreWarp) {
     // ================= output store (TMA) ============================================
+    reg_dec<40>();
     if (lane == 0) {
       prefetch_tmap(&maps.out);
       uint32_t it = 0;
@@ -567,6 +630,8 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Con
       bulk_wait_all();
     }
     __syncwarp();
+  } else {
+    reg_dec<40>();                                // spare warp of the utility warpgroup
   }
   tc_fence_before();
   __syncthreads();
