@@ -42,6 +42,7 @@ UNIT = "nt/s"
 MAX_BATCH_NODES, MAX_BATCH_EDGES = 60_000, 300_000
 FLOP_PER_NODE_MLP = 2 * 128 * 256 * 2            # K2, per layer  
 BYTES_PER_NODE_AGG = 539.0                        # K1 fp16, per layer
+BYTES_PER_NODE_FUSED = 539.0                      # fused layer: h in 256, h' out 256, CSR 26.7
 
 
 def measured_peaks():
@@ -250,7 +251,7 @@ def main() -> None:
         step()
     barrier()
     nat.launch_counts(reset=True)
-    nat.profile_enable("mlp", "aggregate")
+    nat.profile_enable("mlp", "aggregate", "fused_layer")
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
@@ -264,6 +265,7 @@ def main() -> None:
     launches = {k: int(v) for k, v in launches.items()}
     mlp_ms, mlp_calls = nat.profile_read("mlp")
     agg_ms, agg_calls = nat.profile_read("aggregate")
+    fused_ms, fused_calls = nat.profile_read("fused_layer")
     # one more pass, untimed, with every stage bracketed: where the step goes
     nat.profile_enable(*nat.STAGES)
     step()
@@ -354,6 +356,24 @@ def main() -> None:
                         "peak_source": peaks["source"]}
         dominant, other = ((roofline_mlp, roofline_agg) if mlp_ms >= agg_ms
                            else (roofline_agg, roofline_mlp))
+        if fused_ms:
+            # K1 + K2 as one kernel on CTA pairs: the layer's dense FLOPs against the tensor peak
+            # (its HBM side -- h in, h' out, CSR entries: 539 B per node-layer -- is the "other")
+            fl = node_layers * FLOP_PER_NODE_MLP / (fused_ms * 1e-3) / 1e12
+            gb = node_layers * BYTES_PER_NODE_FUSED / (fused_ms * 1e-3) / 1e9
+            common = {"launches": fused_calls, "avg_launch_ms": fused_ms / max(fused_calls, 1),
+                      "share_of_step": fused_ms / args.steps / step_ms_rank,
+                      "peak_source": peaks["source"]}
+            name = ("fused_pair_kernel (K1 + K2 in one kernel: aggregation producing the tcgen05 "
+                    "cta_group::2 A operand, MLP + LayerNorm + residual)")
+            dominant = {"kernel": name, "bound": "tensor", "achieved": fl, "peak": peaks["tflops"],
+                        "unit": "TFLOP/s", "frac": fl / peaks["tflops"],
+                        "traffic": ncu_traffic("fused_layer", node_layers / max(fused_calls, 1)),
+                        **common}
+            other = {"kernel": name + " -- HBM side", "bound": "hbm", "achieved": gb,
+                     "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gb / peaks["hbm_gbs"],
+                     "traffic": ncu_traffic("fused_layer", node_layers / max(fused_calls, 1)),
+                     **common}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,

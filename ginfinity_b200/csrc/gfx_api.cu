@@ -251,6 +251,8 @@ extern "C" int gfx_encode(const gfx_model *model, const float *x, const int32_t 
     return fail(GFX_ERR_WORKSPACE, "gfx_encode: workspace too small");
   if (fused && dtype != GFX_F16)
     return fail(GFX_ERR_UNSUPPORTED, "gfx_encode: fused layers exist for GFX_F16 only");
+  // the CTA-pair kernel covers <= 10 edge types and <= 2^27 nodes; outside that: K1 + K2
+  if (fused == 2 && (model->edge_dim > 10 || n > (int64_t(1) << 27))) fused = 0;
   char *base = static_cast<char *>(ws);
   void *h = base, *z = base + act_bytes(n, dtype), *h2 = base + 2 * act_bytes(n, dtype);
   int rc = gfx_input_linear(model, x, n, h, dtype, stream);

@@ -29,6 +29,8 @@ Deviations from the reference, all deliberate:
 """
 from __future__ import annotations
 
+import os
+
 import json
 from pathlib import Path
 from typing import Optional, Sequence
@@ -160,7 +162,10 @@ class Ginfinity:
         self._scratch = _Scratch(self._torch_device)
         # dense-stage implementation: 0 auto (tcgen05 for fp16), 1 SIMT
         self.impl = nat.IMPL_AUTO
-        self.fused = False
+        # layer kernels: 2 = fused layer on CTA pairs (default for the fp16 model; gfx_encode
+        # falls back to K1 + K2 where that kernel does not apply), 0 = K1 + K2,
+        # 1 = fused layer with one CTA per SM; GFX_FUSED overrides for measurements
+        self.fused = 0 if full_precision else int(os.environ.get("GFX_FUSED", "2"))
         self.chunk_nodes = DEFAULT_CHUNK_NODES
         self.device_builder = True       # encode_many builds full-molecule graphs on the GPU
         self.last_microbatch_bounds: Optional[np.ndarray] = None
@@ -448,7 +453,7 @@ class Ginfinity:
                 self._handle, slot["x"].data_ptr(), row_ptr.data_ptr(),
                 col_src.data_ptr(), col_type.data_ptr(),
                 None if out_row is None else out_row[n0:].data_ptr(), n, out_base,
-                act, out_code, self.impl, 1 if self.fused else 0, enc_ws.data_ptr(),
+                act, out_code, self.impl, int(self.fused), enc_ws.data_ptr(),
                 enc_ws_bytes, main.cuda_stream))
             slot["in_free"].record(main)
             slot["out_ready"].record(main)
@@ -616,7 +621,7 @@ class Ginfinity:
             nat.check(lib.gfx_encode(
                 self._handle, ds.node_features[n0:].data_ptr(), row_ptr.data_ptr(),
                 col_src.data_ptr(), col_type.data_ptr(), None, n, out.data_ptr(), act, out_code,
-                self.impl, 1 if self.fused else 0, enc_ws.data_ptr(), enc_ws_bytes,
+                self.impl, int(self.fused), enc_ws.data_ptr(), enc_ws_bytes,
                 main.cuda_stream))
             ready = torch.cuda.Event()
             ready.record(main)
@@ -710,7 +715,7 @@ class Ginfinity:
         nat.check(lib.gfx_encode(
             self._handle, ds.node_features[n0:].data_ptr(), row_ptr.data_ptr(),
             col_src.data_ptr(), col_type.data_ptr(), map_ptr, n, out_base, act,
-            out_dtype, self.impl, 1 if self.fused else 0, enc_ws.data_ptr(),
+            out_dtype, self.impl, int(self.fused), enc_ws.data_ptr(),
             enc_ws_bytes, stream))
 
 
