@@ -272,6 +272,18 @@ def main() -> None:
     torch.cuda.synchronize()
     stage_ms = {name: round(nat.profile_read(name)[0], 4) for name in nat.STAGES}
     stage_ms = {k: v for k, v in stage_ms.items() if v > 0}
+    # the two-kernel form of a layer (K1 aggregation, K2 MLP) on the same shard, untimed: the
+    # north-star's per-kernel roofline targets are stated for these
+    split = None
+    if getattr(encoder, "fused", 0):
+        keep_fused, encoder.fused = encoder.fused, 0
+        step()                                     # warm
+        torch.cuda.synchronize()
+        nat.profile_enable("mlp", "aggregate")
+        step()
+        torch.cuda.synchronize()
+        split = (nat.profile_read("mlp"), nat.profile_read("aggregate"))
+        encoder.fused = keep_fused
     nat.profile_enable()
     nat.launch_counts(reset=True)
     if world > 1:
@@ -374,6 +386,20 @@ def main() -> None:
                      "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gb / peaks["hbm_gbs"],
                      "traffic": ncu_traffic("fused_layer", node_layers / max(fused_calls, 1)),
                      **common}
+        split_line = None
+        if split is not None:
+            (s_mlp_ms, s_mlp_calls), (s_agg_ms, s_agg_calls) = split
+            nl = nodes * 4
+            split_line = {
+                "what": "one untimed pass with the layer as two kernels (GFX_FUSED=0)",
+                "k1_aggregate": {"bound": "hbm", "unit": "GB/s", "peak": peaks["hbm_gbs"],
+                                 "achieved": nl * BYTES_PER_NODE_AGG / (s_agg_ms * 1e-3) / 1e9,
+                                 "frac": nl * BYTES_PER_NODE_AGG / (s_agg_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                 "launches": s_agg_calls, "ms_per_pass": s_agg_ms},
+                "k2_mlp": {"bound": "tensor", "unit": "TFLOP/s", "peak": peaks["tflops"],
+                           "achieved": nl * FLOP_PER_NODE_MLP / (s_mlp_ms * 1e-3) / 1e12,
+                           "frac": nl * FLOP_PER_NODE_MLP / (s_mlp_ms * 1e-3) / 1e12 / peaks["tflops"],
+                           "launches": s_mlp_calls, "ms_per_pass": s_mlp_ms}}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
@@ -390,7 +416,7 @@ def main() -> None:
             "gpu_launches_by_stage": launches,
             "stage_ms_per_step": stage_ms,
             "e2e_from_records": from_records,
-            "roofline": dominant, "roofline_other": other,
+            "roofline": dominant, "roofline_other": other, "roofline_two_kernel_layer": split_line,
             "setup": {"workload_generation_s": gen_s, "host_cpus": os.cpu_count(), "numa_binding": numa},
         }
         if world == 1 and not args.no_cpu_baseline:
