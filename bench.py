@@ -237,7 +237,7 @@ def main() -> None:
     shard, gen_s = build_workload(args.records, seed=rank)   # weak scaling: a shard per GPU
     encoder = Ginfinity.from_state(state, device=device)
     if args.chunk_nodes > 0:
-        encoder.chunk_nodes = args.chunk_nodes
+        encoder.chunk_nodes = encoder.resident_chunk_nodes = args.chunk_nodes
     nodes, edges = shard.node_count, shard.edge_count
 
     # ---------------- device-resident throughput (`value`) --------------------
@@ -408,7 +408,8 @@ def main() -> None:
             "config": {**workload_config(args, shard.record_count),
                        "nodes_per_gpu": nodes, "edges_per_gpu": edges,
                        "microbatches_per_step": microbatches,
-                       "chunk_nodes": encoder.chunk_nodes},
+                       "chunk_nodes": max(encoder.chunk_nodes, encoder.resident_chunk_nodes),
+                       "chunk_nodes_e2e": encoder.chunk_nodes},
             "clocks": clocks, "clocks_e2e": clocks_e2e,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s.item() / args.steps * 1e3},
