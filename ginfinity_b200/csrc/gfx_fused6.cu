@@ -103,6 +103,7 @@ struct Args {
   int64_t n;
   int edge_dim;
   float eps1;
+  long long *trace;          // developer timeline (tools/fused_trace.py); null in production
 };
 
 // ---- cluster / cta_group::2 wrappers ------------------------------------------------
@@ -271,6 +272,11 @@ __device__ __forceinline__ void epi_a(const Consts &c, uint32_t trow, uint64_t *
   if (lane == 0) mbar_arrive_cluster(leader_bar);
 }
 
+// developer timeline: event `ev` of tile iteration `it`, CTA 0 only
+__device__ __forceinline__ void trace_ev(const Args &p, uint32_t it, int ev) {
+  if (p.trace != nullptr && blockIdx.x == 0 && it < 64) p.trace[it * 16 + ev] = clock64();
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWarps * 32, 1)
 fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Consts c, const Args p) {
   using L = Smem;
@@ -329,8 +335,10 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Con
     const uint32_t a2a = leader(kBarA2aFull), a2b = leader(kBarA2bFull);
     uint32_t it = 0;
     for (int pair = cluster_id; pair < pairs; pair += clusters, ++it) {
+      if (tid == 0) trace_ev(p, it, 6);
       epi_a<0>(c, trow, bar, it & 1, lane, a2a);
       epi_a<1>(c, trow, bar, it & 1, lane, a2b);
+      if (tid == 0) trace_ev(p, it, 7);
     }
   } else if (warp < kProdWarp0) {
     // ================= epilogue B (group g takes iterations it % 2 == g) ===========
@@ -347,6 +355,7 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Con
       const uint32_t hb = it % kHBufs;
       mbar_wait_c(bar + kBarD2Full + g, (it >> 1) & 1);
       tc_fence_after();
+      if (lane == 0 && quad == 0) trace_ev(p, it, 8);
       // 16 columns at a time, loops NOT unrolled: an unrolled body lets the compiler hoist the
       // vector loads of several chunks and spill (64 registers per thread)
       float s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};
@@ -405,6 +414,7 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Con
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar + kBarOReady + hb);
+      if (lane == 0 && quad == 0) trace_ev(p, it, 9);
     }
   } else if (warp < kMmaWarp) {
     // ================= producers: aggregation into the z stage ======================
@@ -467,6 +477,7 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Con
       if (k == 0) {
         mbar_wait_c(bar + kBarHFull + hb, (it / kHBufs) & 1);
         mbar_wait_c(bar + kBarA1Empty + s, ((it >> 1) & 1) ^ 1);
+        if (ptid == 0) trace_ev(p, it, 0);
       }
       const int lr = qid + kQuarters * k;
       float acc[16];
@@ -533,6 +544,7 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Con
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(a1f[s]);
+        if (ptid == 0) trace_ev(p, it, 1);
       }
     }
   } else if (warp == kMmaWarp) {
@@ -562,6 +574,7 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Con
           const uint32_t za = smem_u32(zs) + s * kTileBytes;
           mbar_wait_c(bar + kBarA1Full + s, ph2);
           tc_fence_after();
+          trace_ev(p, it, 2);
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
 #pragma unroll
@@ -574,9 +587,11 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Con
             mma2_commit(bar + (half ? kBarD1bFull : kBarD1aFull));
           }
           mma2_commit(bar + kBarA1Empty + s);          // z consumed in both CTAs
+          trace_ev(p, it, 3);
           mbar_wait_c(bar + kBarA2aFull, ph);
           mbar_wait_c(bar + kBarD2Empty + g, ph2 ^ 1);
           tc_fence_after();
+          trace_ev(p, it, 4);
 #pragma unroll
           for (int kk = 0; kk < HID / 16; ++kk) {
             if (kk == H / 16) {
@@ -587,6 +602,7 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Con
             mma2_f16_ts(tmem + kD2Col + g * kHidden, tmem + kk * 8, db, idesc, kk != 0);
           }
           mma2_commit(bar + kBarD2Full + g);
+          trace_ev(p, it, 5);
         }
       }
     }
@@ -602,6 +618,7 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Con
         const int row0 = (2 * pair + int(rank)) * kTileM;
         uint8_t *dst = hs + hb * kTileBytes;
         mbar_wait_parked(bar + kBarHEmpty + hb, ((it / kHBufs) & 1) ^ 1);
+        trace_ev(p, it, 12);
         mbar_arrive_expect_tx(bar + kBarHFull + hb, kTileBytes);
         tma_load_2d(dst, &maps.h, 0, row0, bar + kBarHFull + hb);
         tma_load_2d(dst + kKbBytes, &maps.h, 64, row0, bar + kBarHFull + hb);
@@ -619,6 +636,7 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Con
         const int row0 = (2 * pair + int(rank)) * kTileM;
         const uint8_t *src = hs + hb * kTileBytes;
         mbar_wait_parked(bar + kBarOReady + hb, (it / kHBufs) & 1);
+        trace_ev(p, it, 10);
         if (row0 < n) {
           tma_store_2d(&maps.out, 0, row0, src);
           tma_store_2d(&maps.out, 64, row0, src + kKbBytes);
@@ -626,6 +644,7 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Con
         bulk_commit();
         bulk_wait_read<0>();                      // shared memory has been read: the buffer is free
         mbar_arrive(bar + kBarHEmpty + hb);
+        trace_ev(p, it, 11);
       }
       bulk_wait_all();
     }
@@ -640,6 +659,8 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Con
 }
 
 }  // namespace v6
+
+static long long *g_trace = nullptr;
 
 int fused6_layer(const gfx_model *m, int layer, const __half *h, const int32_t *row_ptr,
                  const int32_t *col_src, const uint8_t *col_type, int64_t n, __half *h_out,
@@ -667,6 +688,7 @@ int fused6_layer(const gfx_model *m, int layer, const __half *h, const int32_t *
   a.g = m->ln_g + size_t(layer) * kHidden;
   a.b = m->ln_b + size_t(layer) * kHidden;
   a.n = n; a.edge_dim = m->edge_dim; a.eps1 = m->eps1[layer];
+  a.trace = g_trace;
   GFX_CUDA(cudaFuncSetAttribute(v6::fused_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 v6::Smem::total));
   const int64_t tiles = (n + v6::kTileM - 1) / v6::kTileM;
@@ -678,6 +700,13 @@ int fused6_layer(const gfx_model *m, int layer, const __half *h, const int32_t *
 }
 
 }  // namespace gfx
+
+// developer hook (not part of include/gfx.h): device buffer of 64 x 16 int64 that CTA 0 of the
+// next gfx_layer_fused_pair launches fills with clock64() stamps; null switches it off
+extern "C" int gfx_debug_fused_trace(long long *device_buffer) {
+  gfx::g_trace = device_buffer;
+  return GFX_OK;
+}
 
 extern "C" int gfx_layer_fused_pair(const gfx_model *m, int layer, const void *h,
                                     const int32_t *row_ptr, const int32_t *col_src,
