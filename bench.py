@@ -277,9 +277,12 @@ def main() -> None:
     split = None
     if getattr(encoder, "fused", 0):
         keep_fused, encoder.fused = encoder.fused, 0
+        nat.profile_enable()
         step()                                     # warm
         torch.cuda.synchronize()
         nat.profile_enable("mlp", "aggregate")
+        nat.profile_read("mlp")                    # reset the accumulators
+        nat.profile_read("aggregate")
         step()
         torch.cuda.synchronize()
         split = (nat.profile_read("mlp"), nat.profile_read("aggregate"))
