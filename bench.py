@@ -275,7 +275,7 @@ def main() -> None:
     # the two-kernel form of a layer (K1 aggregation, K2 MLP) on the same shard, untimed: the
     # north-star's per-kernel roofline targets are stated for these
     split = None
-    if getattr(encoder, "fused", 0):
+    if getattr(encoder, "fused", 0) > 0:
         keep_fused, encoder.fused = encoder.fused, 0
         nat.profile_enable()
         step()                                     # warm
@@ -421,6 +421,12 @@ def main() -> None:
             "stage_ms_per_step": stage_ms,
             "e2e_from_records": from_records,
             "roofline": dominant, "roofline_other": other, "roofline_two_kernel_layer": split_line,
+            "layer_kernel": {"chosen": "fused_pair_kernel" if getattr(encoder, "fused", 0) == 2
+                             else "K1 + K2",
+                             "tuning_ms_2e19_nodes": {("fused_pair" if k == 2 else "k1_k2"): round(v, 4)
+                                                      for k, v in (encoder.layer_kernel_times or {}).items()},
+                             "how": "both forms of the layer timed once per device on a fixed "
+                                    "synthetic chunk; GFX_FUSED pins the choice"},
             "setup": {"workload_generation_s": gen_s, "host_cpus": os.cpu_count(), "numa_binding": numa},
         }
         if world == 1 and not args.no_cpu_baseline:

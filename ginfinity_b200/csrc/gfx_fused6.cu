@@ -41,6 +41,8 @@
 // Barriers that collect arrivals from both CTAs (z full, A2 full, D2 empty,
 // weights ready) live in rank 0 and are reached with mapa + a cluster-scope
 // arrive; completions of the MMAs are multicast to both CTAs by tcgen05.commit.
+#include <cstdlib>
+
 #include "gfx_common.cuh"
 #include "gfx_tma.cuh"
 #include "gfx_umma.cuh"
@@ -693,7 +695,36 @@ int fused6_layer(const gfx_model *m, int layer, const __half *h, const int32_t *
                                 v6::Smem::total));
   const int64_t tiles = (n + v6::kTileM - 1) / v6::kTileM;
   const int64_t pairs = (tiles + 1) / 2;
-  const int clusters = int(pairs < kNumSMs / 2 ? pairs : kNumSMs / 2);
+  // One CTA pair per TPC -- but only as many as this GPU can hold at once: which SMs are fused off
+  // differs from chip to chip, and a pair that does not fit waits for a whole wave to finish.
+  static int resident[64] = {};                   // per device; 0 = not asked yet
+  int device = 0;
+  GFX_CUDA(cudaGetDevice(&device));
+  if (device >= 0 && device < 64 && resident[device] == 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(kNumSMs, 1, 1);
+    cfg.blockDim = dim3(v6::kWarps * 32, 1, 1);
+    cfg.dynamicSmemBytes = v6::Smem::total;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    int max_clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, v6::fused_pair_kernel, &cfg) != cudaSuccess ||
+        max_clusters < 1) {
+      (void)cudaGetLastError();
+      max_clusters = kNumSMs / 2;
+    }
+    resident[device] = max_clusters < kNumSMs / 2 ? max_clusters : kNumSMs / 2;
+    if (getenv("GFX_VERBOSE"))
+      fprintf(stderr, "libgfx: fused pair kernel: %d resident CTA pairs on device %d\n",
+              resident[device], device);
+  }
+  const int cap = device >= 0 && device < 64 ? resident[device] : kNumSMs / 2;
+  const int clusters = int(pairs < cap ? pairs : cap);
   v6::fused_pair_kernel<<<2 * clusters, v6::kWarps * 32, v6::Smem::total, st>>>(maps, c, a);
   GFX_LAUNCH_CHECK();
   return GFX_OK;

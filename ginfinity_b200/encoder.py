@@ -49,6 +49,7 @@ DEFAULT_CHUNK_NODES = 1 << 20
 # device-resident shards have no copy pipeline to keep fine-grained: larger chunks amortise the
 # fill and drain of the persistent layer kernel (measured: 2^20 -> 675, 2^21 -> 699 M nt/s)
 RESIDENT_CHUNK_NODES = 1 << 21
+_LAYER_KERNEL_CHOICE = {}          # device index -> (gfx_encode `fused` mode, {mode: ms})
 
 
 def _embedding_dtype(value) -> np.dtype:
@@ -165,10 +166,14 @@ class Ginfinity:
         self._scratch = _Scratch(self._torch_device)
         # dense-stage implementation: 0 auto (tcgen05 for fp16), 1 SIMT
         self.impl = nat.IMPL_AUTO
-        # layer kernels: 2 = fused layer on CTA pairs (default for the fp16 model; gfx_encode
-        # falls back to K1 + K2 where that kernel does not apply), 0 = K1 + K2,
-        # 1 = fused layer with one CTA per SM; GFX_FUSED overrides for measurements
-        self.fused = 0 if full_precision else int(os.environ.get("GFX_FUSED", "2"))
+        # layer kernels: 2 = fused layer on CTA pairs (gfx_encode falls back to K1 + K2 where that
+        # kernel does not apply), 0 = K1 + K2, 1 = fused layer with one CTA per SM.  Which of 2
+        # and 0 is faster differs from one B200 to the next (measured on this pool: 690 vs 620
+        # M nt/s on some boards, 607 vs 702 on others), so by default (-1) both are timed once
+        # per device on a fixed synthetic chunk before the first encode and the faster one is
+        # kept (_choose_layer_kernel).  Both pass the same parity tests; GFX_FUSED pins the choice.
+        self.fused = 0 if full_precision else int(os.environ.get("GFX_FUSED", "-1"))
+        self.layer_kernel_times = None    # {2: ms, 0: ms} of the tuning chunk, once chosen
         self.chunk_nodes = DEFAULT_CHUNK_NODES
         self.resident_chunk_nodes = RESIDENT_CHUNK_NODES
         self.device_builder = True       # encode_many builds full-molecule graphs on the GPU
@@ -278,6 +283,69 @@ class Ginfinity:
     def encode_graph(self, graph: Graph, *, embedding_dtype=np.float16
                      ) -> np.ndarray:
         return self.encode_graphs([graph], embedding_dtype=embedding_dtype)[0]
+
+    def _gfx_encode(self, n: int, stream: int, *args_before, tail) -> None:
+        """gfx_encode on the current torch stream (`stream` is its raw handle) with the layer
+        kernel chosen as described in __init__."""
+        if self.fused < 0:
+            self._choose_layer_kernel()
+        nat.check(nat.lib.gfx_encode(*args_before, self.impl, int(self.fused), *tail, stream))
+
+    def _choose_layer_kernel(self) -> None:
+        """Once per device and process: encode a fixed synthetic chunk (2^19 nodes, banded RNA-like
+        graph) with the fused pair kernel and with K1 + K2, timed with CUDA events, and keep the
+        faster.  The choice never depends on user data, so every encoder of a process on a given
+        GPU computes with the same kernels."""
+        key = self._torch_device.index or 0
+        if key not in _LAYER_KERNEL_CHOICE:
+            _LAYER_KERNEL_CHOICE[key] = self._measure_layer_kernels()
+        self.fused, self.layer_kernel_times = _LAYER_KERNEL_CHOICE[key]
+
+    def _measure_layer_kernels(self, nodes: int = 1 << 19):
+        dev, lib = self._torch_device, nat.lib
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream().cuda_stream
+            i = torch.arange(nodes, device=dev, dtype=torch.int32)
+            src, dst, typ = [], [], []
+            for offset, code in ((-1, 0), (1, 1), (-2, 4), (2, 5)):      # backbone and skip-2 edges
+                s_ = i + offset
+                ok = (s_ >= 0) & (s_ < nodes)
+                src.append(s_[ok]); dst.append(i[ok])
+                typ.append(torch.full((int(ok.sum()),), code, dtype=torch.uint8, device=dev))
+            mate = i ^ 32                                                  # a pair 32 nt away
+            src.append(mate); dst.append(i)
+            typ.append(torch.where(mate < i, 2, 3).to(torch.uint8))
+            src, dst, typ = torch.cat(src), torch.cat(dst), torch.cat(typ)
+            e = int(src.shape[0])
+            x = torch.rand((nodes, 7), device=dev, dtype=torch.float32)
+            row_ptr = torch.empty(nodes + 1, dtype=torch.int32, device=dev)
+            col_src = torch.empty(e, dtype=torch.int32, device=dev)
+            col_type = torch.empty(e, dtype=torch.uint8, device=dev)
+            need = lib.gfx_csr_workspace_bytes(nodes, e)
+            ws = torch.empty(need, dtype=torch.uint8, device=dev)
+            nat.check(lib.gfx_csr_build(src.data_ptr(), dst.data_ptr(), typ.data_ptr(), nodes, e, 0,
+                                        row_ptr.data_ptr(), col_src.data_ptr(), col_type.data_ptr(),
+                                        ws.data_ptr(), need, stream))
+            need = lib.gfx_encode_workspace_bytes(nodes, nat.GFX_F16)
+            ews = torch.empty(need, dtype=torch.uint8, device=dev)
+            out = torch.empty((nodes, 128), dtype=torch.float16, device=dev)
+            times = {}
+            for mode in (2, 0):
+                def run():
+                    nat.check(lib.gfx_encode(self._handle, x.data_ptr(), row_ptr.data_ptr(),
+                                             col_src.data_ptr(), col_type.data_ptr(), None, nodes,
+                                             out.data_ptr(), nat.GFX_F16, nat.GFX_F16, self.impl,
+                                             mode, ews.data_ptr(), need, stream))
+                run()                      # first use: module load, attributes, occupancy query
+                start = torch.cuda.Event(enable_timing=True)
+                stop = torch.cuda.Event(enable_timing=True)
+                start.record()
+                run()
+                run()
+                stop.record()
+                stop.synchronize()
+                times[mode] = start.elapsed_time(stop) / 2
+        return min(times, key=times.get), times
 
     # -- shard-level API (api.py:180-230) ------------------------------------
     def _check_request(self, spec, max_nodes_per_record, max_edges_per_record,
@@ -453,12 +521,11 @@ class Ginfinity:
                 csr_ws.data_ptr(), csr_ws_bytes, main.cuda_stream))
             # ranks in out_row are shard-global: bias the base so rank c0 lands on row 0
             out_base = slot["out"].data_ptr() - (0 if out_row is None else c0 * 128 * esize)
-            nat.check(lib.gfx_encode(
-                self._handle, slot["x"].data_ptr(), row_ptr.data_ptr(),
+            self._gfx_encode(
+                n, main.cuda_stream, self._handle, slot["x"].data_ptr(), row_ptr.data_ptr(),
                 col_src.data_ptr(), col_type.data_ptr(),
                 None if out_row is None else out_row[n0:].data_ptr(), n, out_base,
-                act, out_code, self.impl, int(self.fused), enc_ws.data_ptr(),
-                enc_ws_bytes, main.cuda_stream))
+                act, out_code, tail=(enc_ws.data_ptr(), enc_ws_bytes))
             slot["in_free"].record(main)
             slot["out_ready"].record(main)
             with torch.cuda.stream(s_out):
@@ -622,11 +689,10 @@ class Ginfinity:
                 ds.edge_types[e0:].data_ptr() if e else None, n, e, n0, row_ptr.data_ptr(),
                 col_src.data_ptr(), col_type.data_ptr(), csr_ws.data_ptr(), csr_ws_bytes,
                 main.cuda_stream))
-            nat.check(lib.gfx_encode(
-                self._handle, ds.node_features[n0:].data_ptr(), row_ptr.data_ptr(),
-                col_src.data_ptr(), col_type.data_ptr(), None, n, out.data_ptr(), act, out_code,
-                self.impl, int(self.fused), enc_ws.data_ptr(), enc_ws_bytes,
-                main.cuda_stream))
+            self._gfx_encode(
+                n, main.cuda_stream, self._handle, ds.node_features[n0:].data_ptr(),
+                row_ptr.data_ptr(), col_src.data_ptr(), col_type.data_ptr(), None, n,
+                out.data_ptr(), act, out_code, tail=(enc_ws.data_ptr(), enc_ws_bytes))
             ready = torch.cuda.Event()
             ready.record(main)
             with torch.cuda.stream(s_out):
@@ -717,11 +783,10 @@ class Ginfinity:
         else:
             out_base = out.data_ptr()           # ranks in out_row are global
             map_ptr = out_row[n0:].data_ptr()
-        nat.check(lib.gfx_encode(
-            self._handle, ds.node_features[n0:].data_ptr(), row_ptr.data_ptr(),
+        self._gfx_encode(
+            n, stream, self._handle, ds.node_features[n0:].data_ptr(), row_ptr.data_ptr(),
             col_src.data_ptr(), col_type.data_ptr(), map_ptr, n, out_base, act,
-            out_dtype, self.impl, int(self.fused), enc_ws.data_ptr(),
-            enc_ws_bytes, stream))
+            out_dtype, tail=(enc_ws.data_ptr(), enc_ws_bytes))
 
 
 def _check_unique_ids(records) -> None:
