@@ -355,6 +355,34 @@ def test_fused_layer_matches_oracle(nat, dev, problem, entry):
     assert torch.equal(out, out2)          # deterministic
 
 
+@pytest.mark.parametrize("seed,count", [(41, 1), (42, 2), (43, 3), (44, 7), (45, 40), (46, 333)])
+def test_fused_pair_layer_ragged_sizes(nat, dev, problem, seed, count):
+    """The CTA-pair kernel on node counts that leave the last tile partly empty, an odd number of
+    tiles (the second CTA of the last pair has no rows) or fewer tiles than CTAs: every layer
+    against K1 + K2 on the same input."""
+    import ginfinity_b200 as g
+    shard = g.GraphBuilder().build_shard(random_records(seed, count))
+    n = shard.node_count
+    rp, cs, ct = device_csr(nat, dev, shard.edge_index, shard.edge_types, n)
+    rng = np.random.default_rng(seed)
+    h = _up((rng.standard_normal((n, 128)) * 2).astype(np.float16), dev)
+    for layer in range(4):
+        z = _buf(n, 0, dev)
+        want = _buf(n, 0, dev)
+        got = torch.full((n + 64, 128), 7.0, dtype=torch.float16, device=dev)   # guard rows
+        nat.check(nat.lib.gfx_aggregate(problem["handle"], layer, h.data_ptr(), rp.data_ptr(),
+                                        cs.data_ptr(), ct.data_ptr(), n, z.data_ptr(), 0, _stream()))
+        nat.check(nat.lib.gfx_mlp_ln_residual(problem["handle"], layer, z.data_ptr(), h.data_ptr(),
+                                              n, want.data_ptr(), 0, 5, _stream()))
+        nat.check(nat.lib.gfx_layer_fused_pair(problem["handle"], layer, h.data_ptr(), rp.data_ptr(),
+                                               cs.data_ptr(), ct.data_ptr(), n, got.data_ptr(),
+                                               _stream()))
+        torch.cuda.synchronize()
+        assert torch.all(got[n:] == 7.0)                       # nothing written past the last row
+        diff = (got[:n].float() - want.float()).abs().max().item()
+        assert diff <= 4e-3 * max(1.0, want.float().abs().max().item()), (layer, n, diff)
+
+
 @pytest.mark.parametrize("n", [1, 127, 128, 129, 200, 64 * 3 + 1])
 def test_tile_edges(nat, dev, problem, n):
     """Ragged sizes around the 128-row tile / 64-row block boundaries: all
