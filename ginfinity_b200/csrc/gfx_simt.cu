@@ -322,12 +322,14 @@ aggregate_f16_kernel(const __half *__restrict__ h, const int32_t *__restrict__ r
 //     node ahead, rows now).
 // Rows with more than 8 edges finish in a plain loop.  Sources must fit 27
 // bits (the caller falls back to the half-warp kernel above 2^27 nodes).
+// 4 resident blocks per SM (64 registers, no spills): 0.074 ms on a 603k-node
+// chunk against 0.081 ms at 2 blocks (115 registers).
 // ---------------------------------------------------------------------------
 constexpr int kWinQ = 5;              // edges per node covered by the straight-line code
 constexpr int kSrcBits = 27;
 constexpr uint32_t kSrcMask = (1u << kSrcBits) - 1u;
 
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 4)
 aggregate_f16_q_kernel(const __half *__restrict__ h, const int32_t *__restrict__ row_ptr,
                        const int32_t *__restrict__ col_src, const uint8_t *__restrict__ col_type,
                        const __half *__restrict__ table16, int edge_dim, float eps1, int64_t n,
@@ -682,7 +684,7 @@ extern "C" int gfx_aggregate(const gfx_model *m, int layer, const void *h, const
     }();
     if (!half_warp && n <= (int64_t(1) << kSrcBits)) {
       int64_t b = (n + 31) / 32;
-      const int grid = int(b > 2 * kNumSMs ? 2 * kNumSMs : b);
+      const int grid = int(b > 4 * kNumSMs ? 4 * kNumSMs : b);
       aggregate_f16_q_kernel<<<grid, 256, 0, st>>>(
           static_cast<const __half *>(h), row_ptr, col_src, col_type, m->table16 + toff,
           m->edge_dim, m->eps1[layer], n, static_cast<__half *>(z));
