@@ -293,7 +293,7 @@ def test_aggregate_irregular_rows(nat, dev, problem, n):
     assert (got != want).mean() < 0.02
 
 
-@pytest.mark.parametrize("code,impl", [(1, 1), (0, 1), (0, 2), (0, 3), (0, 4), (0, 5)])
+@pytest.mark.parametrize("code,impl", [(1, 1), (0, 1), (0, 2), (0, 3), (0, 4), (0, 5), (0, 6)])
 def test_mlp_layernorm_residual_layer0(nat, dev, problem, code, impl):
     """K2 (SIMT fp32, SIMT fp16-storage, pipelined tcgen05, serial tcgen05) against the oracle's h1."""
     keep = problem["keep32" if code == 1 else "keep16"]
@@ -390,7 +390,7 @@ def test_tile_edges(nat, dev, problem, n):
     keep = problem["keep16"]
     z, h = _up(keep["z0"][:n], dev).half(), _up(keep["h0"][:n], dev).half()
     outs = []
-    for impl in (1, 2, 3, 4, 5):
+    for impl in (1, 2, 3, 4, 5, 6):
         o = _buf(n, 0, dev)
         nat.check(nat.lib.gfx_mlp_ln_residual(problem["handle"], 0, z.data_ptr(), h.data_ptr(),
                                               n, o.data_ptr(), 0, impl, _stream()))
@@ -400,7 +400,7 @@ def test_tile_edges(nat, dev, problem, n):
         assert (o.float() - outs[0].float()).abs().max().item() <= 4e-3 * float(np.abs(keep["h1"]).max())
 
 
-@pytest.mark.parametrize("code,impl,fused", [(1, 1, 0), (0, 1, 0), (0, 2, 0), (0, 3, 0), (0, 4, 0), (0, 5, 0), (0, 2, 1), (0, 5, 2)])
+@pytest.mark.parametrize("code,impl,fused", [(1, 1, 0), (0, 1, 0), (0, 2, 0), (0, 3, 0), (0, 4, 0), (0, 5, 0), (0, 6, 0), (0, 2, 1), (0, 5, 2)])
 def test_whole_forward(nat, dev, problem, code, impl, fused):
     """gfx_encode (all stages chained on device) against the oracle."""
     x = _up(problem["shard"].node_features, dev)
