@@ -52,7 +52,7 @@ enum {
   GFX_IMPL_UMMA_SERIAL = 3, /* first, un-pipelined tcgen05 kernel (kept as a cross-check) */
   GFX_IMPL_UMMA_TMA = 4,    /* pipelined tcgen05 with all tile I/O on 2-D tiled TMA (K2) */
   GFX_IMPL_UMMA_LEAN = 5,   /* TMA I/O + 16 lean epilogue warps, constants as kernel parameters (K2) */
-  GFX_IMPL_UMMA_STREAM = 6  /* the same with W2 streamed through a ring and a double-buffered residual/output tile (K2) */
+  GFX_IMPL_UMMA_STREAM = 6  /* three stage buffers cycling z -> residual -> output instead of a separate residual tile (K2) */
 };
 
 int gfx_abi_version(void);
