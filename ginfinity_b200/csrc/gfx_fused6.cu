@@ -45,6 +45,7 @@
 
 #include "gfx_common.cuh"
 #include "gfx_tma.cuh"
+#include "gfx_pair.cuh"
 #include "gfx_umma.cuh"
 
 namespace gfx {
@@ -77,7 +78,7 @@ enum Bar {
 };
 
 struct Smem {
-  static constexpr int off_w1 = 0;                                   // [kb 2][half 2] x 8 KB
+  static constexpr int off_w1 = 0;                                   // [kb 2] x 16 KB (128 rows)
   static constexpr int off_w2 = off_w1 + 4 * kWPiece;                // [kb 4] x 8 KB
   static constexpr int off_z = off_w2 + 4 * kWPiece;                 // 2 stages x 32 KB
   static constexpr int off_h = off_z + kStages * kTileBytes;         // 3 tiles x 32 KB
@@ -108,83 +109,9 @@ struct Args {
   long long *trace;          // developer timeline (tools/fused_trace.py); null in production
 };
 
-// ---- cluster / cta_group::2 wrappers ------------------------------------------------
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n"
-               "barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// shared::cta address -> shared::cluster address of the same location in CTA `rank`
-__device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
-  return r;
-}
-// Arrive on a barrier of another CTA of the cluster.  Default semantics (release at CTA scope),
-// as CUTLASS's ClusterBarrier::arrive does: what the arrival publishes is consumed by the tensor
-// core (shared memory through the async proxy after fence.proxy.async, or TMEM after
-// tcgen05.fence), never through the waiting thread's L1.  The cluster-scope forms cost a
-// MEMBAR + ERRBAR per arrive and a CCTL.IVALL (L1 invalidate) per wait: 30 % of all stall
-// samples in the first version of this kernel.
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
 // parked wait (suspend-time hint) on a local barrier
 __device__ __forceinline__ void mbar_wait_c(uint64_t *bar, uint32_t parity) {
   mbar_wait_parked(bar, parity);
-}
-__device__ __forceinline__ void tmem_alloc2(uint32_t *dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
-               "r"(cols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void mma2_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
-                                            uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void mma2_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
-                                            uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem),
-      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// arrive on `bar` (same offset in both CTAs of the pair) when all MMAs issued so far are done
-__device__ __forceinline__ void mma2_commit(uint64_t *bar) {
-  asm volatile(
-      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::
-          "r"(smem_u32(bar)),
-      "h"(uint16_t(3))
-      : "memory");
-}
-// Register reallocation between warpgroups (4 consecutive warps): the launch gives every thread
-// 64 registers (1024 threads); the utility warpgroup needs far fewer and the producers a few more.
-template <int N>
-__device__ __forceinline__ void reg_dec() {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
-}
-template <int N>
-__device__ __forceinline__ void reg_inc() {
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
 }
 __device__ __forceinline__ void fence_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
@@ -279,6 +206,7 @@ __device__ __forceinline__ void trace_ev(const Args &p, uint32_t it, int ev) {
   if (p.trace != nullptr && blockIdx.x == 0 && it < 64) p.trace[it * 16 + ev] = clock64();
 }
 
+template <bool WIDE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWarps * 32, 1)
 fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Consts c, const Args p) {
   using L = Smem;
@@ -291,6 +219,11 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Con
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
+  if (p.trace != nullptr && tid == 0) {          // every CTA: wall-clock start (end below)
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    p.trace[1024 + 2 * blockIdx.x] = (long long)ns;
+  }
   if (warp == kMmaWarp) {
     tmem_alloc2(tmem_slot, kTmemCols);
   } else if (tid == 0) {
@@ -556,11 +489,15 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Con
       mbar_arrive_expect_tx(bar + kBarWLocal, 8 * kWPiece);
       const uint8_t *w1g = reinterpret_cast<const uint8_t *>(p.w1_img);
       const uint8_t *w2g = reinterpret_cast<const uint8_t *>(p.w2_img);
+      // Each CTA supplies W1' rows [128 rank, +128) of every K block (two 8 KB pieces, contiguous:
+      // one B operand of an N = 256 MMA).  In pair mode an MMA costs ~128 cycles whether N is 128
+      // or 256 (measured with gfx_umma7.cu), so GEMM 1 runs as 8 MMAs of N = 256, not 16 of N = 128.
       for (int kb = 0; kb < 2; ++kb)
-        for (int half = 0; half < 2; ++half)      // rows [128 half + 64 rank, +64) of K block kb
+        for (int half = 0; half < 2; ++half)
           bulk_g2s(w1s + (kb * 2 + half) * kWPiece,
-                   w1g + kb * (HID * 128) + (H * half + 64 * int(rank)) * 128, kWPiece,
-                   bar + kBarWLocal);
+                   w1g + kb * (HID * 128) +
+                       (WIDE ? H * int(rank) + 64 * half : H * half + 64 * int(rank)) * 128,
+                   kWPiece, bar + kBarWLocal);
       for (int kb = 0; kb < 4; ++kb)              // rows [64 rank, +64) of K block kb
         bulk_g2s(w2s + kb * kWPiece, w2g + kb * (kHidden * 128) + 64 * int(rank) * 128, kWPiece,
                  bar + kBarWLocal);
@@ -577,16 +514,29 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Con
           mbar_wait_c(bar + kBarA1Full + s, ph2);
           tc_fence_after();
           trace_ev(p, it, 2);
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
+          if (WIDE) {
+            constexpr uint32_t idesc_w = idesc_f16(2 * kTileM, HID);   // GEMM 1: N = 256
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk) {
               const int kb = kk >> 2, k = kk & 3;
               const uint64_t da = smem_desc_sw128(za + kb * kKbBytes + k * 32);
-              const uint64_t db = smem_desc_sw128(w1a + (kb * 2 + half) * kWPiece + k * 32);
-              mma2_f16_ss(tmem + half * H, da, db, idesc, kk != 0);
+              const uint64_t db = smem_desc_sw128(w1a + kb * 2 * kWPiece + k * 32);
+              mma2_f16_ss(tmem, da, db, idesc_w, kk != 0);
             }
-            mma2_commit(bar + (half ? kBarD1bFull : kBarD1aFull));
+            mma2_commit(bar + kBarD1aFull);
+            mma2_commit(bar + kBarD1bFull);
+          } else {                      // two column halves of N = 128 (rows [128 half + 64 rank, +64))
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+#pragma unroll
+              for (int kk = 0; kk < 8; ++kk) {
+                const int kb = kk >> 2, k = kk & 3;
+                const uint64_t da = smem_desc_sw128(za + kb * kKbBytes + k * 32);
+                const uint64_t db = smem_desc_sw128(w1a + (kb * 2 + half) * kWPiece + k * 32);
+                mma2_f16_ss(tmem + half * H, da, db, idesc, kk != 0);
+              }
+              mma2_commit(bar + (half ? kBarD1bFull : kBarD1aFull));
+            }
           }
           mma2_commit(bar + kBarA1Empty + s);          // z consumed in both CTAs
           trace_ev(p, it, 3);
@@ -658,6 +608,11 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Con
   __syncthreads();
   cluster_sync_all();                             // the peer may still be arriving on our barriers
   if (warp == kMmaWarp) tmem_dealloc2(tmem, kTmemCols);
+  if (p.trace != nullptr && tid == 0) {
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    p.trace[1024 + 2 * blockIdx.x + 1] = (long long)ns;
+  }
 }
 
 }  // namespace v6
@@ -691,8 +646,12 @@ int fused6_layer(const gfx_model *m, int layer, const __half *h, const int32_t *
   a.b = m->ln_b + size_t(layer) * kHidden;
   a.n = n; a.edge_dim = m->edge_dim; a.eps1 = m->eps1[layer];
   a.trace = g_trace;
-  GFX_CUDA(cudaFuncSetAttribute(v6::fused_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                v6::Smem::total));
+  static const bool wide = [] {
+    const char *v = getenv("GFX_FUSED_WIDE");      // developer switch: "0" = GEMM 1 as two N = 128 halves
+    return !(v && *v == '0');
+  }();
+  auto kernel = wide ? v6::fused_pair_kernel<true> : v6::fused_pair_kernel<false>;
+  GFX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v6::Smem::total));
   const int64_t tiles = (n + v6::kTileM - 1) / v6::kTileM;
   const int64_t pairs = (tiles + 1) / 2;
   // One CTA pair per TPC -- but only as many as this GPU can hold at once: which SMs are fused off
@@ -713,7 +672,7 @@ int fused6_layer(const gfx_model *m, int layer, const __half *h, const int32_t *
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
     int max_clusters = 0;
-    if (cudaOccupancyMaxActiveClusters(&max_clusters, v6::fused_pair_kernel, &cfg) != cudaSuccess ||
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, kernel, &cfg) != cudaSuccess ||
         max_clusters < 1) {
       (void)cudaGetLastError();
       max_clusters = kNumSMs / 2;
@@ -725,15 +684,16 @@ int fused6_layer(const gfx_model *m, int layer, const __half *h, const int32_t *
   }
   const int cap = device >= 0 && device < 64 ? resident[device] : kNumSMs / 2;
   const int clusters = int(pairs < cap ? pairs : cap);
-  v6::fused_pair_kernel<<<2 * clusters, v6::kWarps * 32, v6::Smem::total, st>>>(maps, c, a);
+  kernel<<<2 * clusters, v6::kWarps * 32, v6::Smem::total, st>>>(maps, c, a);
   GFX_LAUNCH_CHECK();
   return GFX_OK;
 }
 
 }  // namespace gfx
 
-// developer hook (not part of include/gfx.h): device buffer of 64 x 16 int64 that CTA 0 of the
-// next gfx_layer_fused_pair launches fills with clock64() stamps; null switches it off
+// developer hook (not part of include/gfx.h): device buffer of 64 x 16 + 2 x 160 int64; CTA 0 of the
+// next gfx_layer_fused_pair launches fills the first part with clock64() stamps, every CTA writes its
+// wall-clock start and end (globaltimer) into the second; null switches it off
 extern "C" int gfx_debug_fused_trace(long long *device_buffer) {
   gfx::g_trace = device_buffer;
   return GFX_OK;

@@ -634,6 +634,8 @@ int umma6_mlp_ln_residual(const gfx_model *m, int layer, const __half *z, const 
                           int64_t n, __half *h_out, cudaStream_t st);
 int umma4_mlp_ln_residual(const gfx_model *m, int layer, const __half *z, const __half *h,
                           int64_t n, __half *h_out, cudaStream_t st);
+int umma7_mlp_ln_residual(const gfx_model *m, int layer, const __half *z, const __half *h,
+                          int64_t n, __half *h_out, cudaStream_t st);
 
 }  // namespace gfx
 
@@ -715,10 +717,11 @@ extern "C" int gfx_mlp_ln_residual(const gfx_model *m, int layer, const void *z,
   StageScope scope(GFX_STAGE_MLP, st, 1);
   if (impl == GFX_IMPL_AUTO) impl = dtype == GFX_F16 ? GFX_IMPL_UMMA_LEAN : GFX_IMPL_SIMT;
   if (impl == GFX_IMPL_UMMA || impl == GFX_IMPL_UMMA_SERIAL || impl == GFX_IMPL_UMMA_TMA ||
-      impl == GFX_IMPL_UMMA_LEAN || impl == GFX_IMPL_UMMA_STREAM) {
+      impl == GFX_IMPL_UMMA_LEAN || impl == GFX_IMPL_UMMA_STREAM || impl == GFX_IMPL_UMMA_PAIR) {
     if (dtype != GFX_F16)
       return fail(GFX_ERR_UNSUPPORTED, "tcgen05 MLP exists for GFX_F16 only");
-    auto fn = impl == GFX_IMPL_UMMA_STREAM ? umma6_mlp_ln_residual
+    auto fn = impl == GFX_IMPL_UMMA_PAIR ? umma7_mlp_ln_residual
+              : impl == GFX_IMPL_UMMA_STREAM ? umma6_mlp_ln_residual
               : impl == GFX_IMPL_UMMA_LEAN ? umma4_mlp_ln_residual
               : impl == GFX_IMPL_UMMA_TMA ? umma3_mlp_ln_residual
               : impl == GFX_IMPL_UMMA   ? umma_mlp_ln_residual
@@ -751,7 +754,8 @@ extern "C" int gfx_head_l2norm(const gfx_model *m, const void *h, const int32_t 
   cudaStream_t st = as_stream(stream);
   StageScope scope(GFX_STAGE_HEAD, st, 1);
   if (impl == GFX_IMPL_AUTO) impl = dtype == GFX_F16 ? GFX_IMPL_UMMA : GFX_IMPL_SIMT;
-  if (impl == GFX_IMPL_UMMA_TMA || impl == GFX_IMPL_UMMA_LEAN || impl == GFX_IMPL_UMMA_STREAM)
+  if (impl == GFX_IMPL_UMMA_TMA || impl == GFX_IMPL_UMMA_LEAN || impl == GFX_IMPL_UMMA_STREAM ||
+      impl == GFX_IMPL_UMMA_PAIR)
     impl = GFX_IMPL_UMMA;  // head: v2 kernel
   if (impl == GFX_IMPL_UMMA || impl == GFX_IMPL_UMMA_SERIAL) {
     if (dtype != GFX_F16)

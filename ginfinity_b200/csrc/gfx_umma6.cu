@@ -350,7 +350,7 @@ umma6_mlp_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Cons
 
 }  // namespace v6k
 
-static long long *g_k2_trace = nullptr;
+long long *g_k2_trace = nullptr;   // shared with gfx_umma7.cu
 
 int umma6_mlp_ln_residual(const gfx_model *m, int layer, const __half *z, const __half *h,
                           int64_t n, __half *h_out, cudaStream_t st) {

@@ -52,7 +52,8 @@ enum {
   GFX_IMPL_UMMA_SERIAL = 3, /* first, un-pipelined tcgen05 kernel (kept as a cross-check) */
   GFX_IMPL_UMMA_TMA = 4,    /* pipelined tcgen05 with all tile I/O on 2-D tiled TMA (K2) */
   GFX_IMPL_UMMA_LEAN = 5,   /* TMA I/O + 16 lean epilogue warps, constants as kernel parameters (K2) */
-  GFX_IMPL_UMMA_STREAM = 6  /* three stage buffers cycling z -> residual -> output instead of a separate residual tile (K2) */
+  GFX_IMPL_UMMA_STREAM = 6, /* three stage buffers cycling z -> residual -> output instead of a separate residual tile (K2) */
+  GFX_IMPL_UMMA_PAIR = 7    /* CTA pairs (tcgen05 cta_group::2): weights split across the pair, five cycling stage buffers (K2) */
 };
 
 int gfx_abi_version(void);

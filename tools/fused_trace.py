@@ -39,14 +39,16 @@ run = lambda: nat.check(lib.gfx_layer_fused_pair(handle, 0, h.data_ptr(), row_pt
 for _ in range(3):
     run()
 torch.cuda.synchronize()
-trace = torch.zeros(64 * 16, dtype=torch.int64, device=dev)
+trace = torch.zeros(64 * 16 + 2 * 160, dtype=torch.int64, device=dev)
 raw = ctypes.CDLL(str(ROOT / "ginfinity_b200" / "libgfx.so"))
 raw.gfx_debug_fused_trace.argtypes = [ctypes.c_void_p]
 raw.gfx_debug_fused_trace(trace.data_ptr())
 run()
 torch.cuda.synchronize()
 raw.gfx_debug_fused_trace(None)
-t = trace.cpu().numpy().reshape(64, 16)
+full = trace.cpu().numpy()
+t = full[:1024].reshape(64, 16)
+spans = full[1024:].reshape(-1, 2)
 t0 = t[t > 0].min()
 names = ["prodS", "prodE", "A1full", "mma1", "A2+D2e", "mma2", "epiA_S", "epiA_E", "epiB_S", "epiB_E",
          "stO", "stE", "load"]
@@ -56,3 +58,10 @@ for it in range(40):
     if not t[it].any():
         break
     print(f"{it:3d}  " + " ".join(f"{(t[it, k] - t0) if t[it, k] else -1:7d}" for k in range(13)))
+live = spans[spans[:, 0] > 0]
+if len(live):
+    s0 = live[:, 0].min()
+    start, end = live[:, 0] - s0, live[:, 1] - s0
+    print(f"{len(live)} CTAs: start {start.min()}..{start.max()} ns, end {end.min()}..{end.max()} ns, "
+          f"duration median {np.median(end - start):.0f} ns (min {np.min(end - start)}, max {np.max(end - start)})")
+    print("duration (us) by CTA:", " ".join(str(int(x)) for x in (end - start) // 1000))

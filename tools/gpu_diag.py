@@ -120,9 +120,9 @@ def main():
         print(f"aggregate[{name}]: {t * 1e3:.3f} ms  {alg / t / 1e9:.0f} GB/s algorithmic ({alg / N:.0f} B/node)")
         report[f"aggregate_{name}_s"] = t
         report[f"aggregate_{name}_gbs"] = alg / t / 1e9
-        impls = ((1, "simt"), (3, "umma_serial"), (2, "umma"), (4, "umma_tma"), (5, "umma_lean"), (6, "umma_stream")) if code == 0 else ((1, "simt"),)
+        impls = ((1, "simt"), (3, "umma_serial"), (2, "umma"), (4, "umma_tma"), (5, "umma_lean"), (6, "umma_stream"), (7, "umma_pair")) if code == 0 else ((1, "simt"),)
         if os.environ.get("GFX_DIAG_FAST"):
-            impls = ((5, "umma_lean"), (6, "umma_stream")) if code == 0 else ()
+            impls = ((5, "umma_lean"), (6, "umma_stream"), (7, "umma_pair")) if code == 0 else ()
         for impl, iname in impls:
             t = timeit(lambda: nat.check(lib.gfx_mlp_ln_residual(handle, 0, zz.data_ptr(), hh.data_ptr(), N, h2.data_ptr(), code, impl, S())), iters=5, warm=2)
             fl = N * 131072.0

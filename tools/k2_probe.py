@@ -30,11 +30,12 @@ def timeit(fn, iters=20, warm=5):
     return a.elapsed_time(b) / iters * 1e-3
 
 
-for n in (1 << 15, 1 << 16, 1 << 17, 1 << 18, 1 << 19, 1 << 20, 1 << 21):
+impls = [int(a) for a in sys.argv[1:]] or [5]
+for impl, n in ((i, n) for i in impls for n in (1 << 15, 1 << 16, 1 << 17, 1 << 18, 1 << 19, 1 << 20, 1 << 21)):
     z = torch.randn(n, 128, device=dev).half()
     h = torch.randn(n, 128, device=dev).half()
     o = torch.empty_like(h)
     t = timeit(lambda: nat.check(lib.gfx_mlp_ln_residual(handle, 0, z.data_ptr(), h.data_ptr(), n,
-                                                         o.data_ptr(), 0, 5, S())))
-    print(f"K2 n={n:8d}  {t * 1e6:8.1f} us  {t / n * 1e9:.4f} ns/node  {n * 131072 / t / 1e12:7.1f} TFLOP/s"
+                                                         o.data_ptr(), 0, impl, S())))
+    print(f"K2[{impl}] n={n:8d}  {t * 1e6:8.1f} us  {t / n * 1e9:.4f} ns/node  {n * 131072 / t / 1e12:7.1f} TFLOP/s"
           f"  {n * 768 / t / 1e12:.2f} TB/s   working set {3 * n * 256 / 1e6:.0f} MB")
