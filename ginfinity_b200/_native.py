@@ -67,6 +67,8 @@ _SIGNATURES = {
     "gfx_mlp_ln_residual": (C.c_int, [_p, C.c_int, _p, _p, _i64, _p, C.c_int, C.c_int, _p]),
     "gfx_layer_fused": (C.c_int, [_p, C.c_int, _p, _p, _p, _p, _i64, _p, _p]),
     "gfx_layer_fused_pair": (C.c_int, [_p, C.c_int, _p, _p, _p, _p, _i64, _p, _p]),
+    "gfx_row_describe": (C.c_int, [_p, _p, _p, _i64, _p, _p]),
+    "gfx_layer_fused_banded": (C.c_int, [_p, C.c_int, _p, _p, _p, _p, _p, _i64, _p, _p]),
     "gfx_head_l2norm": (C.c_int, [_p, _p, _p, _i64, _p, C.c_int, C.c_int, C.c_int, _p]),
     "gfx_encode_workspace_bytes": (_sz, [_i64, C.c_int]),
     "gfx_encode": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _p, C.c_int, C.c_int,

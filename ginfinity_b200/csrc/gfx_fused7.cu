@@ -1,46 +1,24 @@
-// One GINE layer in one kernel on CTA PAIRS (tcgen05 cta_group::2): K1 (the
-// aggregation) produces K2's GEMM-1 A operand in shared memory, so z never
-// exists in HBM and h is read once and written once per layer.
+// One GINE layer in one kernel on CTA pairs, BANDED producers (seventh fused version).
 //
 //   h_out = h + LayerNorm(W2 relu(W1' z + b1') + b2),
 //   z_i   = (1+eps) h_i + sum_{e: dst=i} relu(h[src_e] + table[type_e])
 //
-// Why pairs: gfx_fused5.cu (one CTA per SM) keeps 128 KB of weights resident
-// and has 99 KB left, i.e. two 32 KB buffers that each have to be z tile,
-// residual tile and output tile in turn; their life cycle, not the tensor
-// pipe, set its pace.  A CTA pair splits the B operands
-// (each CTA holds the half of W1 / W2 that produces half of the N columns:
-// 64 KB), runs M = 256 MMAs over both CTAs' 128-row tiles, and has 160 KB per
-// CTA for data:
-//   * 3 h-tile buffers (32 KB, TMA, 128-byte swizzle): the tile's own rows of
-//     h serve (i) the producers' self rows and in-tile neighbour rows (~97 % of
-//     the edges of RNA graphs stay inside a 128-row tile; the rest are read
-//     from global memory / L2), (ii) epilogue B's residual, (iii) the output
-//     staging for the TMA store -- loaded once, stored once;
-//   * 2 z stages (32 KB, the UMMA K-major swizzled A operand of GEMM 1).
-// TMEM (512 columns per CTA): D1 [0,256) fp32, overwritten IN PLACE by the
-// fp16 hidden activation A2 [0,128) (epilogue A walks the columns upwards, so
-// it only overwrites what it has already read), D2 double-buffered at
-// [256,384) and [384,512).
-//
-// Warps (24; 80 registers per thread at launch, re-balanced with setmaxnreg: the producers get
-// 104, the utility warpgroup 40), per CTA:
-//    0-3   epilogue A   D1 -> + b1, ReLU, fp16 -> A2 (in place)
-//    4-11  epilogue B   two groups of 4, alternating tiles: D2 -> + b2,
-//                       LayerNorm (two passes over TMEM, full rows: no
-//                       exchange between warps), + residual, in place in the
-//                       h-tile buffer
-//   12-19  producers    quarter-warp per node (as K1: shuffled edge fetch,
-//                       branch-free missing edges), rows from the h-tile
-//                       buffer, z row into the z stage; the CSR entries of the
-//                       NEXT tile are fetched before the current one is summed
-//   20     MMA issuer   (rank 0 of the pair issues for both CTAs; both fetch
-//                       their halves of the weights)
-//   21     h-tile loader (TMA)
-//   22     output store  (TMA)
-// Barriers that collect arrivals from both CTAs (z full, A2 full, D2 empty,
-// weights ready) live in rank 0 and are reached with mapa + a cluster-scope
-// arrive; completions of the MMAs are multicast to both CTAs by tcgen05.commit.
+// Same skeleton as gfx_fused6.cu (CTA pairs, tcgen05 cta_group::2, three resident h-tile buffers
+// that serve as neighbour source, residual and output staging, two z stages, epilogues in TMEM);
+// what changes is how z is produced.  gfx_fused6.cu is bound by shared-memory bandwidth: per node
+// its quarter-warp producers read 6.5 neighbour/self rows and 5.5 table rows of 256 B.  RNA graphs
+// are BANDED: the incoming edges of nucleotide i are, in the reference's edge order,
+//     (i-1, backbone fwd) (i+1, backbone rev) [(partner, pair fwd|rev)] (i-2, skip fwd) (i+2, skip rev)
+// with some of them missing at molecule ends.  gfx_row_describe() classifies every CSR row once
+// per chunk into a 32-bit descriptor (presence bits, pair type, partner index; or GENERIC when the
+// row is anything else).  A producer WARP then owns a run of consecutive rows, each lane 4
+// channels (8 bytes of a row): the run's rows i-2 .. i+2 are loaded ONCE into a register window
+// (statically indexed, fully unrolled), the six table rows live in registers, only the pairing
+// partner's row is fetched per node.  Shared-memory traffic of the producers drops from ~3.3 KB to
+// ~0.9 KB per node, the CSR arrays are not read at all on the fast path (4 B instead of 29 B per
+// node and layer), and the sum is taken in CSR order with the same arithmetic as gfx_fused6.cu, so
+// the two kernels agree BIT FOR BIT.  GENERIC rows (sliced windows with context nodes, arbitrary
+// graphs) are recomputed from the CSR arrays by a slow warp-per-row loop after the run.
 #include <cstdlib>
 
 #include "gfx_common.cuh"
@@ -52,7 +30,7 @@ namespace gfx {
 
 using namespace ptx;
 
-namespace v6 {
+namespace v7 {
 
 constexpr int HID = kMlpHidden, H = HID / 2;
 constexpr int kTileM = 128;
@@ -60,16 +38,17 @@ constexpr int kKbBytes = kTileM * 128;        // one K block of a tile: [128 x 6
 constexpr int kTileBytes = 2 * kKbBytes;      // a whole [128 x 128] fp16 tile
 constexpr int kStages = 2, kHBufs = 3;
 constexpr int kWPiece = 64 * 128;             // 64 weight rows x 64 columns (one CTA's share)
-constexpr int kTabRows = 11;                  // edge types 0..9 + the "no edge" row
 constexpr uint32_t kTmemCols = 512, kD2Col = 256;
 constexpr int kEpiBWarp0 = 4, kProdWarp0 = 12, kProdWarps = 8, kMmaWarp = 20, kLoadWarp = 21,
               kStoreWarp = 22, kWarps = 24;
-constexpr int kQuarters = kProdWarps * 4;             // quarter-warps producing z rows
-constexpr int kRowsPerQuarter = kTileM / kQuarters;   // rows of a tile per quarter-warp
-static_assert(kRowsPerQuarter * kQuarters == kTileM, "tile rows must divide evenly");
-constexpr int kSrcBits = 27;
-constexpr uint32_t kSrcMask = (1u << kSrcBits) - 1u;
-constexpr int kWin = 5;
+constexpr int kRowsPerWarp = kTileM / kProdWarps;     // 16 consecutive rows of a tile per producer warp
+constexpr int kRun = 8;                               // rows per register window
+static_assert(kRowsPerWarp % kRun == 0 && kRun % 4 == 0, "runs of whole partner groups");
+// row descriptor (gfx_row_describe)
+constexpr uint32_t kDescPrev = 1u, kDescNext = 2u, kDescPair = 4u, kDescPairRev = 8u, kDescPrev2 = 16u,
+                   kDescNext2 = 32u, kDescGeneric = 0x80000000u;
+constexpr int kDescPartnerShift = 6, kDescPartnerBits = 25;
+constexpr uint32_t kDescPartnerMask = (1u << kDescPartnerBits) - 1u;
 
 enum Bar {
   kBarWLocal = 0, kBarWReady = 1, kBarHFull = 2, kBarHEmpty = 5, kBarOReady = 8, kBarA1Full = 11,
@@ -82,8 +61,7 @@ struct Smem {
   static constexpr int off_w2 = off_w1 + 4 * kWPiece;                // [kb 4] x 8 KB
   static constexpr int off_z = off_w2 + 4 * kWPiece;                 // 2 stages x 32 KB
   static constexpr int off_h = off_z + kStages * kTileBytes;         // 3 tiles x 32 KB
-  static constexpr int off_tab = off_h + kHBufs * kTileBytes;        // fp16 [11][128]
-  static constexpr int off_bar = off_tab + kTabRows * kHidden * 2;
+  static constexpr int off_bar = off_h + kHBufs * kTileBytes;
   static constexpr int off_tmem = off_bar + kNumBars * 8;
   static constexpr int total = off_tmem + 8;
 };
@@ -101,6 +79,7 @@ struct Args {
   const __half *h;
   const int32_t *row_ptr, *col_src;
   const uint8_t *col_type;
+  const uint32_t *desc;      // [n] row descriptors
   const __half *table16, *w1_img, *w2_img;
   const float *b2, *g, *b;   // device vectors of this layer
   int64_t n;
@@ -136,11 +115,10 @@ __device__ __forceinline__ void add_pair(float &a0, float &a1, uint32_t m) {
       : "+f"(a0), "+f"(a1)
       : "r"(m));
 }
-__device__ __forceinline__ void add_message(float *acc, const uint4 &nb, const uint4 &tb) {
+// one message on this lane's 4 channels: fp16 relu(x + t), summed in fp32
+__device__ __forceinline__ void add_message4(float *acc, const uint2 &nb, const uint2 &tb) {
   add_pair(acc[0], acc[1], hfma2_relu_add(nb.x, tb.x));
   add_pair(acc[2], acc[3], hfma2_relu_add(nb.y, tb.y));
-  add_pair(acc[4], acc[5], hfma2_relu_add(nb.z, tb.z));
-  add_pair(acc[6], acc[7], hfma2_relu_add(nb.w, tb.w));
 }
 __device__ __forceinline__ uint4 lds128(uint32_t saddr) {
   uint4 v;
@@ -154,20 +132,26 @@ __device__ __forceinline__ void sts128(uint32_t saddr, const uint4 &v) {
                "r"(v.w)
                : "memory");
 }
-// 16 bytes of a neighbour row: from the resident h tile when the source lies in this tile, else
-// from global memory (L2).  One predicated instruction of each kind writing the SAME registers:
-// written as an if/else, the compiler predicates both paths into separate registers and merges
-// them with eight moves per row.
-__device__ __forceinline__ uint4 ld_tile_or_global(uint32_t in_tile, uint32_t saddr, const uint4 *gptr) {
-  uint4 v;
+__device__ __forceinline__ uint2 lds64(uint32_t saddr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts64(uint32_t saddr, const uint2 &v) {
+  asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(saddr), "r"(v.x), "r"(v.y) : "memory");
+}
+// 8 bytes of a row: from the resident h tile when the row lies in this tile, else from global
+// memory (L2); one predicated instruction of each kind writing the same registers
+__device__ __forceinline__ uint2 ld_tile_or_global8(uint32_t in_tile, uint32_t saddr, const uint2 *gptr) {
+  uint2 v;
   asm volatile(
       "{\n"
       ".reg .pred q;\n"
-      "setp.ne.b32 q, %4, 0;\n"
-      "@q ld.shared.v4.u32 {%0, %1, %2, %3}, [%5];\n"
-      "@!q ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%6];\n"
+      "setp.ne.b32 q, %2, 0;\n"
+      "@q ld.shared.v2.u32 {%0, %1}, [%3];\n"
+      "@!q ld.global.nc.v2.u32 {%0, %1}, [%4];\n"
       "}\n"
-      : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+      : "=r"(v.x), "=r"(v.y)
       : "r"(in_tile), "r"(saddr), "l"(gptr));
   return v;
 }
@@ -208,12 +192,11 @@ __device__ __forceinline__ void trace_ev(const Args &p, uint32_t it, int ev) {
 
 template <bool WIDE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWarps * 32, 1)
-fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Consts c, const Args p) {
+fused_banded_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Consts c, const Args p) {
   using L = Smem;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t *w1s = smem + L::off_w1, *w2s = smem + L::off_w2, *zs = smem + L::off_z;
   uint8_t *hs = smem + L::off_h;
-  uint4 *tab = reinterpret_cast<uint4 *>(smem + L::off_tab);
   uint64_t *bar = reinterpret_cast<uint64_t *>(smem + L::off_bar);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::off_tmem);
 
@@ -246,10 +229,6 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Con
     mbar_init(bar + kBarA2bFull, 8);
     fence_mbar_init();
   }
-  for (int i = tid; i < p.edge_dim * kHidden / 8; i += blockDim.x)
-    tab[i] = reinterpret_cast<const uint4 *>(p.table16)[i];
-  for (int i = tid; i < kHidden / 8; i += blockDim.x)               // the "no edge" row: -65504
-    tab[p.edge_dim * kHidden / 8 + i] = make_uint4(0xFBFFFBFFu, 0xFBFFFBFFu, 0xFBFFFBFFu, 0xFBFFFBFFu);
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();                          // both CTAs' barriers exist before any remote arrive
@@ -352,135 +331,137 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Con
       if (lane == 0 && quad == 0) trace_ev(p, it, 9);
     }
   } else if (warp < kMmaWarp) {
-    // ================= producers: aggregation into the z stage ======================
+    // ================= producers: banded aggregation into the z stage ================
     reg_inc<104>();
-    const int ptid = (warp - kProdWarp0) * 32 + lane;
-    const int qid = ptid >> 3, sub = ptid & 7, qbase = lane & 24;
-    const uint4 *hv = reinterpret_cast<const uint4 *>(p.h) + sub;     // row r -> hv[r*16], hv[r*16+8]
-    const uint32_t tvs = smem_u32(tab) + uint32_t(sub) * 16u;          // type t -> tvs + t*256 (+128)
+    const int pw = warp - kProdWarp0;                 // rows [16 pw, 16 pw + 16) of every tile
+    // this lane's 4 channels = 8 bytes of a row: 16-byte chunk lane / 2 of the 256-byte row
+    const uint32_t kboff = uint32_t(lane >> 4) * kKbBytes;
+    const uint32_t c8 = uint32_t(lane >> 1) & 7u, odd8 = uint32_t(lane & 1) * 8u;
+    auto cell = [&](int r) -> uint32_t {              // byte offset of this lane's piece of tile row r
+      return kboff + uint32_t(r) * 128u + (((c8 ^ uint32_t(r)) & 7u) << 4) + odd8;
+    };
+    const uint2 *hg = reinterpret_cast<const uint2 *>(p.h) + lane;     // row r -> hg[r * 32]
     const uint32_t a1f[2] = {leader(kBarA1Full), leader(kBarA1Full + 1)};
+    const uint2 kNone = make_uint2(0xFBFFFBFFu, 0xFBFFFBFFu);          // -65504: relu(x + it) = +0
+    uint2 tb[6];                                                       // table rows of types 0..5
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+      tb[k] = reinterpret_cast<const uint2 *>(p.table16 + k * kHidden)[lane];
 
-    // This quarter-warp owns rows qid + 32 k (k = 0..3) of every tile of its CTA: a sequence of
-    // "row steps" j (tile iteration j / 4, row group j % 4).  The CSR entries travel through a
-    // register pipeline so that no load is consumed near the step that issues it: row_ptr
-    // three steps ahead (A), this lane's edge (source, type) two steps ahead (B1 -> B0),
-    // packed and used now.
-    const int my_iters = cluster_id < pairs ? (pairs - cluster_id + clusters - 1) / clusters : 0;
-    const int steps = kRowsPerQuarter * my_iters;
-    auto row_of = [&](int j) {
-      return (2 * (cluster_id + (j / kRowsPerQuarter) * clusters) + int(rank)) * kTileM + qid +
-             kQuarters * (j % kRowsPerQuarter);
+    // lane l < 16 holds the descriptor of the warp's row l, fetched one tile ahead
+    auto fetch_desc = [&](int pr) -> uint32_t {
+      if (pr >= pairs || lane >= kRowsPerWarp) return 0u;
+      const int row = (2 * pr + int(rank)) * kTileM + kRowsPerWarp * pw + lane;
+      return row < n ? p.desc[row] : 0u;
     };
-    int begA = 0, endA = 0, srcB0 = 0, typB0 = 0, srcB1 = 0, typB1 = 0;
-    auto load_a = [&](int j) {
-      begA = endA = 0;
-      if (j < steps) {
-        const int row = row_of(j);
-        if (row < n) {
-          begA = p.row_ptr[row];
-          endA = p.row_ptr[row + 1];
-        }
-      }
+    // the two rows just outside the tile that the first / last warp's windows reach (global memory)
+    auto fetch_halo = [&](int pr, uint2 &x0, uint2 &x1) {
+      x0 = x1 = make_uint2(0u, 0u);
+      if (pr >= pairs || (pw != 0 && pw != kProdWarps - 1)) return;
+      const int r0 = (2 * pr + int(rank)) * kTileM;
+      const int g0 = pw == 0 ? r0 - 2 : r0 + kTileM, g1 = g0 + 1;
+      if (g0 >= 0 && g0 < n) x0 = __ldg(hg + int64_t(g0) * 32);
+      if (g1 >= 0 && g1 < n) x1 = __ldg(hg + int64_t(g1) * 32);
     };
-    auto load_b = [&](int j, int &src, int &typ) {       // consumes A
-      const int row = j < steps ? row_of(j) : 0;
-      src = row < n ? row : 0;                           // no edge: the node itself, "none" type
-      typ = p.edge_dim;
-      if (begA + sub < endA) {
-        src = p.col_src[begA + sub];
-        typ = p.col_type[begA + sub];
-      }
-    };
-    load_a(0);
-    load_b(0, srcB0, typB0);
-    load_a(1);
-    load_b(1, srcB1, typB1);
-    load_a(2);
-#pragma unroll 1
-    for (int j = 0; j < steps; ++j) {
-      const uint32_t it = uint32_t(j) / kRowsPerQuarter;
-      const int k = j % kRowsPerQuarter;
+    uint32_t dnext = fetch_desc(cluster_id);
+    uint2 hx0, hx1;
+    fetch_halo(cluster_id, hx0, hx1);
+    uint32_t it = 0;
+    for (int pair = cluster_id; pair < pairs; pair += clusters, ++it) {
       const uint32_t s = it & 1, hb = it % kHBufs;
-      const int row0 = (2 * (cluster_id + int(it) * clusters) + int(rank)) * kTileM;
-      const uint32_t pk = (uint32_t(srcB0) & kSrcMask) | (uint32_t(typB0) << kSrcBits);
-      srcB0 = srcB1;
-      typB0 = typB1;
-      load_b(j + 2, srcB1, typB1);
-      load_a(j + 3);
+      const int row0 = (2 * pair + int(rank)) * kTileM;
+      const uint32_t d = dnext;
+      const uint2 halo0 = hx0, halo1 = hx1;
+      dnext = fetch_desc(pair + clusters);
+      fetch_halo(pair + clusters, hx0, hx1);
       const uint32_t hbase = smem_u32(hs) + hb * kTileBytes;
       const uint32_t zbase = smem_u32(zs) + s * kTileBytes;
-      if (k == 0) {
-        mbar_wait_c(bar + kBarHFull + hb, (it / kHBufs) & 1);
-        mbar_wait_c(bar + kBarA1Empty + s, ((it >> 1) & 1) ^ 1);
-        if (ptid == 0) trace_ev(p, it, 0);
-      }
-      const int lr = qid + kQuarters * k;
-      float acc[16];
-#pragma unroll
-      for (int ch = 0; ch < 16; ++ch) acc[ch] = 0.f;
-      // Half a row (16 bytes per lane) ahead: the next half row is requested before the current
-      // one is summed.  The asm statements are volatile, so this order is the order of the
-      // machine code; left to itself the compiler hoists all ten row loads and spills.
-      struct Edge {
-        uint32_t in_tile, a, t;        // smem address of the row chunk, table address
-        const uint4 *gp;
-      };
-      auto edge = [&](int u) {
-        const uint32_t e = __shfl_sync(0xffffffffu, pk, qbase + u);
-        const int src = int(e & kSrcMask);
+      mbar_wait_c(bar + kBarHFull + hb, (it / kHBufs) & 1);
+      mbar_wait_c(bar + kBarA1Empty + s, ((it >> 1) & 1) ^ 1);
+      if (warp == kProdWarp0 && lane == 0) trace_ev(p, it, 0);
+      // partner row of the warp's row `idx` (a row without a pair reads itself; its message is +0)
+      auto partner = [&](int idx) -> uint2 {
+        const uint32_t dj = __shfl_sync(0xffffffffu, d, idx);
+        const int self = kRowsPerWarp * pw + idx;
+        const int src = (dj & kDescPair) ? int((dj >> kDescPartnerShift) & kDescPartnerMask) : row0 + self;
         const uint32_t local = uint32_t(src - row0);
-        Edge x;
-        x.in_tile = local < uint32_t(kTileM) ? 1u : 0u;
-        x.a = hbase + sw_off(int(local), sub);
-        x.gp = hv + int64_t(src) * 16;
-        x.t = tvs + (e >> kSrcBits) * 256u;
-        return x;
+        const uint32_t in_tile = local < uint32_t(kTileM) ? 1u : 0u;
+        return ld_tile_or_global8(in_tile, hbase + cell(int(local & (kTileM - 1))), hg + int64_t(src) * 32);
       };
-      Edge cur = edge(0);
-      uint4 d0 = ld_tile_or_global(cur.in_tile, cur.a, cur.gp);
+#pragma unroll 1
+      for (int run = 0; run < kRowsPerWarp / kRun; ++run) {
+        const int base = kRowsPerWarp * pw + kRun * run;   // first tile row of the run
+        uint2 pr[2][4];
 #pragma unroll
-      for (int u = 0; u < kWin; ++u) {
-        const uint4 d1 = ld_tile_or_global(cur.in_tile, cur.a + kKbBytes, cur.gp + 8);
-        add_message(acc, d0, lds128(cur.t));
-        const uint32_t t1 = cur.t + 128u;
-        if (u + 1 < kWin) {
-          cur = edge(u + 1);
-          d0 = ld_tile_or_global(cur.in_tile, cur.a, cur.gp);
-        }
-        add_message(acc + 8, d1, lds128(t1));
-      }
-      // rare: rows longer than the window (lane kWin of the quarter holds edge kWin, if any)
-      if ((__shfl_sync(0xffffffffu, pk, qbase + kWin) >> kSrcBits) != uint32_t(p.edge_dim)) {
-        const int beg = p.row_ptr[row0 + lr], end = p.row_ptr[row0 + lr + 1];
-        for (int eidx = beg + kWin; eidx < end; ++eidx) {
-          const int src = p.col_src[eidx];
-          const uint32_t t = tvs + uint32_t(p.col_type[eidx]) * 256u;
-          add_message(acc, hv[int64_t(src) * 16], lds128(t));
-          add_message(acc + 8, hv[int64_t(src) * 16 + 8], lds128(t + 128u));
-        }
-      }
-      uint4 o0 = make_uint4(0, 0, 0, 0), o1 = make_uint4(0, 0, 0, 0);
-      const uint32_t so = sw_off(lr, sub);
-      if (row0 + lr < n) {
-        const uint4 self0 = lds128(hbase + so), self1 = lds128(hbase + so + kKbBytes);
-        const __half2 *s0 = reinterpret_cast<const __half2 *>(&self0);
-        const __half2 *s1 = reinterpret_cast<const __half2 *>(&self1);
-        uint32_t *p0 = reinterpret_cast<uint32_t *>(&o0), *p1 = reinterpret_cast<uint32_t *>(&o1);
+        for (int q = 0; q < 4; ++q) pr[0][q] = partner(kRun * run + q);
+        // window: tile rows base - 2 .. base + kRun + 1
+        uint2 w[kRun + 4];
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          const float2 f0 = __half22float2(s0[ch]), f1 = __half22float2(s1[ch]);
-          p0[ch] = pack2(fmaf(p.eps1, f0.x, acc[2 * ch]), fmaf(p.eps1, f0.y, acc[2 * ch + 1]));
-          p1[ch] = pack2(fmaf(p.eps1, f1.x, acc[8 + 2 * ch]), fmaf(p.eps1, f1.y, acc[8 + 2 * ch + 1]));
+        for (int k = 0; k < kRun + 4; ++k) {
+          const int lr = base - 2 + k;
+          if (lr < 0)
+            w[k] = k == 0 ? halo0 : halo1;
+          else if (lr >= kTileM)
+            w[k] = lr == kTileM ? halo0 : halo1;
+          else
+            w[k] = lds64(hbase + cell(lr));
+        }
+#pragma unroll
+        for (int j = 0; j < kRun; ++j) {
+          if ((j & 3) == 0 && j + 4 < kRun) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) pr[((j >> 2) + 1) & 1][q] = partner(kRun * run + j + 4 + q);
+          }
+          const uint32_t dj = __shfl_sync(0xffffffffu, d, kRun * run + j);
+          float acc[4] = {0.f, 0.f, 0.f, 0.f};
+          uint2 tt;
+          tt = (dj & kDescPrev) ? tb[0] : kNone;
+          add_message4(acc, w[j + 1], tt);
+          tt = (dj & kDescNext) ? tb[1] : kNone;
+          add_message4(acc, w[j + 3], tt);
+          tt = (dj & kDescPairRev) ? tb[3] : tb[2];
+          tt = (dj & kDescPair) ? tt : kNone;
+          add_message4(acc, pr[(j >> 2) & 1][j & 3], tt);
+          tt = (dj & kDescPrev2) ? tb[4] : kNone;
+          add_message4(acc, w[j], tt);
+          tt = (dj & kDescNext2) ? tb[5] : kNone;
+          add_message4(acc, w[j + 4], tt);
+          const __half2 *sv = reinterpret_cast<const __half2 *>(&w[j + 2]);
+          const float2 f0 = __half22float2(sv[0]), f1 = __half22float2(sv[1]);
+          uint2 o;
+          o.x = pack2(fmaf(p.eps1, f0.x, acc[0]), fmaf(p.eps1, f0.y, acc[1]));
+          o.y = pack2(fmaf(p.eps1, f1.x, acc[2]), fmaf(p.eps1, f1.y, acc[3]));
+          sts64(zbase + cell(base + j), o);
         }
       }
-      sts128(zbase + so, o0);
-      sts128(zbase + so + kKbBytes, o1);
-      if (k == kRowsPerQuarter - 1) {
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(a1f[s]);
-        if (ptid == 0) trace_ev(p, it, 1);
+      // rows that are not banded: recomputed from the CSR arrays, one row at a time (warp-uniform)
+      if (__ballot_sync(0xffffffffu, (d & kDescGeneric) != 0u) != 0u) {
+#pragma unroll 1
+        for (int idx = 0; idx < kRowsPerWarp; ++idx) {
+          if (!(__shfl_sync(0xffffffffu, d, idx) & kDescGeneric)) continue;
+          const int lr = kRowsPerWarp * pw + idx, row = row0 + lr;
+          float acc[4] = {0.f, 0.f, 0.f, 0.f};
+          const int beg = p.row_ptr[row], end = p.row_ptr[row + 1];
+          for (int e = beg; e < end; ++e) {
+            const int src = p.col_src[e];
+            const uint2 tt = reinterpret_cast<const uint2 *>(p.table16 + int(p.col_type[e]) * kHidden)[lane];
+            const uint32_t local = uint32_t(src - row0);
+            const uint2 v = local < uint32_t(kTileM) ? lds64(hbase + cell(int(local))) : __ldg(hg + int64_t(src) * 32);
+            add_message4(acc, v, tt);
+          }
+          const uint2 self = lds64(hbase + cell(lr));
+          const __half2 *sv = reinterpret_cast<const __half2 *>(&self);
+          const float2 f0 = __half22float2(sv[0]), f1 = __half22float2(sv[1]);
+          uint2 o;
+          o.x = pack2(fmaf(p.eps1, f0.x, acc[0]), fmaf(p.eps1, f0.y, acc[1]));
+          o.y = pack2(fmaf(p.eps1, f1.x, acc[2]), fmaf(p.eps1, f1.y, acc[3]));
+          sts64(zbase + cell(lr), o);
+        }
       }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(a1f[s]);
+      if (warp == kProdWarp0 && lane == 0) trace_ev(p, it, 1);
     }
   } else if (warp == kMmaWarp) {
     // ================= weights (both CTAs) + MMA issue (rank 0) ======================
@@ -615,30 +596,55 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Con
   }
 }
 
-}  // namespace v6
+}  // namespace v7
 
-long long *g_trace = nullptr;       // shared with gfx_fused7.cu
+// ---- row descriptors ---------------------------------------------------------------------------
+// One thread per CSR row: does the row read, in order, (i-1, type 0) (i+1, type 1)
+// [(any, type 2|3)] (i-2, type 4) (i+2, type 5), each optional, and nothing else?
+__global__ void __launch_bounds__(256)
+row_describe_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col_src,
+                    const uint8_t *__restrict__ col_type, int64_t n, uint32_t *__restrict__ desc) {
+  using namespace v7;
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int end = row_ptr[i + 1];
+  int k = row_ptr[i];
+  uint32_t d = 0;
+  auto is = [&](int64_t src, int type) { return k < end && col_src[k] == src && col_type[k] == type; };
+  if (is(i - 1, 0)) { d |= kDescPrev; ++k; }
+  if (is(i + 1, 1)) { d |= kDescNext; ++k; }
+  if (k < end && (col_type[k] == 2 || col_type[k] == 3) && col_src[k] >= 0 &&
+      uint32_t(col_src[k]) <= kDescPartnerMask) {
+    d |= kDescPair | (col_type[k] == 3 ? kDescPairRev : 0u) | (uint32_t(col_src[k]) << kDescPartnerShift);
+    ++k;
+  }
+  if (is(i - 2, 4)) { d |= kDescPrev2; ++k; }
+  if (is(i + 2, 5)) { d |= kDescNext2; ++k; }
+  desc[i] = k == end ? d : kDescGeneric;
+}
 
-int fused6_layer(const gfx_model *m, int layer, const __half *h, const int32_t *row_ptr,
-                 const int32_t *col_src, const uint8_t *col_type, int64_t n, __half *h_out,
-                 cudaStream_t st) {
+extern long long *g_trace;              // gfx_fused6.cu (gfx_debug_fused_trace)
+
+int fused7_layer(const gfx_model *m, int layer, const __half *h, const int32_t *row_ptr,
+                 const int32_t *col_src, const uint8_t *col_type, const uint32_t *desc, int64_t n,
+                 __half *h_out, cudaStream_t st) {
   if ((reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(h_out)) & 15)
     return fail(GFX_ERR_ARGUMENT, "fused layer: activation buffers must be 16-byte aligned");
   if (h == h_out) return fail(GFX_ERR_ARGUMENT, "fused layer: h and h_out must not alias");
-  if (n > (int64_t(1) << v6::kSrcBits))
-    return fail(GFX_ERR_UNSUPPORTED, "fused layer (CTA pairs): at most 2^27 nodes per call");
-  if (m->edge_dim >= v6::kTabRows)
-    return fail(GFX_ERR_UNSUPPORTED, "fused layer (CTA pairs): at most 10 edge types");
-  v6::Maps maps;
-  int rc = tma::make_rows128_map(&maps.h, h, n, v6::kTileM);
-  if (!rc) rc = tma::make_rows128_map(&maps.out, h_out, n, v6::kTileM);
+  if (n > (int64_t(1) << v7::kDescPartnerBits))
+    return fail(GFX_ERR_UNSUPPORTED, "fused layer (banded): at most 2^25 nodes per call");
+  if (m->edge_dim < 6)
+    return fail(GFX_ERR_UNSUPPORTED, "fused layer (banded): needs the six backbone / pair / skip edge types");
+  v7::Maps maps;
+  int rc = tma::make_rows128_map(&maps.h, h, n, v7::kTileM);
+  if (!rc) rc = tma::make_rows128_map(&maps.out, h_out, n, v7::kTileM);
   if (rc) return rc;
-  v6::Consts c;
+  v7::Consts c;
   const gfx_host_vectors &hv = m->host;
   for (int i = 0; i < kMlpHidden; ++i) c.b1[i] = hv.b1[size_t(layer) * kMlpHidden + i];
   const size_t wi = size_t(layer) * kMlpHidden * kHidden;
-  v6::Args a{};
-  a.h = h; a.row_ptr = row_ptr; a.col_src = col_src; a.col_type = col_type;
+  v7::Args a{};
+  a.h = h; a.row_ptr = row_ptr; a.col_src = col_src; a.col_type = col_type; a.desc = desc;
   a.table16 = m->table16 + size_t(layer) * m->edge_dim * kHidden;
   a.w1_img = m->w1_img + wi; a.w2_img = m->w2_img + wi;
   a.b2 = m->b2 + size_t(layer) * kHidden;
@@ -646,24 +652,19 @@ int fused6_layer(const gfx_model *m, int layer, const __half *h, const int32_t *
   a.b = m->ln_b + size_t(layer) * kHidden;
   a.n = n; a.edge_dim = m->edge_dim; a.eps1 = m->eps1[layer];
   a.trace = g_trace;
-  static const bool wide = [] {
-    const char *v = getenv("GFX_FUSED_WIDE");      // developer switch: "0" = GEMM 1 as two N = 128 halves
-    return !(v && *v == '0');
-  }();
-  auto kernel = wide ? v6::fused_pair_kernel<true> : v6::fused_pair_kernel<false>;
-  GFX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v6::Smem::total));
-  const int64_t tiles = (n + v6::kTileM - 1) / v6::kTileM;
+  auto kernel = v7::fused_banded_kernel<true>;
+  GFX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v7::Smem::total));
+  const int64_t tiles = (n + v7::kTileM - 1) / v7::kTileM;
   const int64_t pairs = (tiles + 1) / 2;
-  // One CTA pair per TPC -- but only as many as this GPU can hold at once: which SMs are fused off
-  // differs from chip to chip, and a pair that does not fit waits for a whole wave to finish.
+  // as many CTA pairs as this GPU can hold at once (see gfx_fused6.cu)
   static int resident[64] = {};                   // per device; 0 = not asked yet
   int device = 0;
   GFX_CUDA(cudaGetDevice(&device));
   if (device >= 0 && device < 64 && resident[device] == 0) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(kNumSMs, 1, 1);
-    cfg.blockDim = dim3(v6::kWarps * 32, 1, 1);
-    cfg.dynamicSmemBytes = v6::Smem::total;
+    cfg.blockDim = dim3(v7::kWarps * 32, 1, 1);
+    cfg.dynamicSmemBytes = v7::Smem::total;
     cudaLaunchAttribute attr;
     attr.id = cudaLaunchAttributeClusterDimension;
     attr.val.clusterDim.x = 2;
@@ -678,37 +679,39 @@ int fused6_layer(const gfx_model *m, int layer, const __half *h, const int32_t *
       max_clusters = kNumSMs / 2;
     }
     resident[device] = max_clusters < kNumSMs / 2 ? max_clusters : kNumSMs / 2;
-    if (getenv("GFX_VERBOSE"))
-      fprintf(stderr, "libgfx: fused pair kernel: %d resident CTA pairs on device %d\n",
-              resident[device], device);
   }
   const int cap = device >= 0 && device < 64 ? resident[device] : kNumSMs / 2;
   const int clusters = int(pairs < cap ? pairs : cap);
-  kernel<<<2 * clusters, v6::kWarps * 32, v6::Smem::total, st>>>(maps, c, a);
+  kernel<<<2 * clusters, v7::kWarps * 32, v7::Smem::total, st>>>(maps, c, a);
   GFX_LAUNCH_CHECK();
   return GFX_OK;
 }
 
 }  // namespace gfx
 
-// developer hook (not part of include/gfx.h): device buffer of 64 x 16 + 2 x 160 int64; CTA 0 of the
-// next gfx_layer_fused_pair launches fills the first part with clock64() stamps, every CTA writes its
-// wall-clock start and end (globaltimer) into the second; null switches it off
-extern "C" int gfx_debug_fused_trace(long long *device_buffer) {
-  gfx::g_trace = device_buffer;
+extern "C" int gfx_row_describe(const int32_t *row_ptr, const int32_t *col_src,
+                                const uint8_t *col_type, int64_t n, uint32_t *desc, void *stream) {
+  using namespace gfx;
+  if (n <= 0) return GFX_OK;
+  if (!row_ptr || !desc) return fail(GFX_ERR_ARGUMENT, "gfx_row_describe: null array");
+  cudaStream_t st = as_stream(stream);
+  StageScope scope(GFX_STAGE_CSR, st, 1);
+  row_describe_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(row_ptr, col_src, col_type, n, desc);
+  GFX_LAUNCH_CHECK();
   return GFX_OK;
 }
 
-extern "C" int gfx_layer_fused_pair(const gfx_model *m, int layer, const void *h,
-                                    const int32_t *row_ptr, const int32_t *col_src,
-                                    const uint8_t *col_type, int64_t n, void *h_out,
-                                    void *stream) {
+extern "C" int gfx_layer_fused_banded(const gfx_model *m, int layer, const void *h,
+                                      const int32_t *row_ptr, const int32_t *col_src,
+                                      const uint8_t *col_type, const uint32_t *desc, int64_t n,
+                                      void *h_out, void *stream) {
   using namespace gfx;
   if (!m || layer < 0 || layer >= m->layers)
-    return fail(GFX_ERR_ARGUMENT, "gfx_layer_fused_pair: bad model or layer");
+    return fail(GFX_ERR_ARGUMENT, "gfx_layer_fused_banded: bad model or layer");
   if (n <= 0) return GFX_OK;
+  if (!desc) return fail(GFX_ERR_ARGUMENT, "gfx_layer_fused_banded: null row descriptors");
   cudaStream_t st = as_stream(stream);
   StageScope scope(GFX_STAGE_FUSED_LAYER, st, 1);
-  return fused6_layer(m, layer, static_cast<const __half *>(h), row_ptr, col_src, col_type, n,
+  return fused7_layer(m, layer, static_cast<const __half *>(h), row_ptr, col_src, col_type, desc, n,
                       static_cast<__half *>(h_out), st);
 }

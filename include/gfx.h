@@ -245,6 +245,21 @@ int gfx_layer_fused_pair(const gfx_model *model, int layer, const void *h,
                          const uint8_t *col_type, int64_t num_nodes, void *h_out,
                          void *stream);
 
+/* Banded form of the fused layer.  gfx_row_describe classifies every CSR row once per chunk:
+ * desc[i] says which of (i-1, type 0) (i+1, type 1) [(partner, type 2|3)] (i-2, type 4)
+ * (i+2, type 5) -- the reference builder's edge order for nucleotide i (graph.py:494-561) --
+ * the row holds, plus the partner index, or marks the row GENERIC.  gfx_layer_fused_banded
+ * computes the same layer as gfx_layer_fused_pair, bit for bit, reading banded rows from a
+ * register window over the resident h tile and GENERIC rows from the CSR arrays.
+ * GFX_F16 only, >= 6 edge types, <= 2^25 nodes. */
+int gfx_row_describe(const int32_t *row_ptr, const int32_t *col_src,
+                     const uint8_t *col_type, int64_t num_nodes, uint32_t *desc,
+                     void *stream);
+int gfx_layer_fused_banded(const gfx_model *model, int layer, const void *h,
+                           const int32_t *row_ptr, const int32_t *col_src,
+                           const uint8_t *col_type, const uint32_t *desc,
+                           int64_t num_nodes, void *h_out, void *stream);
+
 /* K3: y = Wb relu(Wa h + ba) + bb; out[out_row[i]] = y_i / max(|y_i|, 1e-12)
  * cast to out_dtype.  out_row == NULL means identity.
  *                                (_model.py:61-63,72; api.py:250-259) */

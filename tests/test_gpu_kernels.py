@@ -383,6 +383,106 @@ def test_fused_pair_layer_ragged_sizes(nat, dev, problem, seed, count):
         assert diff <= 4e-3 * max(1.0, want.float().abs().max().item()), (layer, n, diff)
 
 
+def _describe_rows(rp, cs, ct):
+    """NumPy restatement of gfx_row_describe (include/gfx.h): per row, the reference builder's
+    edge order (graph.py:494-561) with every edge optional, else GENERIC."""
+    n = len(rp) - 1
+    out = np.zeros(n, dtype=np.uint32)
+    for i in range(n):
+        k, end, d = int(rp[i]), int(rp[i + 1]), 0
+        def at(src, typ):
+            return k < end and cs[k] == src and ct[k] == typ
+        if at(i - 1, 0): d |= 1; k += 1
+        if at(i + 1, 1): d |= 2; k += 1
+        if k < end and ct[k] in (2, 3) and 0 <= cs[k] < (1 << 25):
+            d |= 4 | (8 if ct[k] == 3 else 0) | (int(cs[k]) << 6); k += 1
+        if at(i - 2, 4): d |= 16; k += 1
+        if at(i + 2, 5): d |= 32; k += 1
+        out[i] = d if k == end else 0x80000000
+    return out
+
+
+def _device_describe(nat, dev, rp, cs, ct, n):
+    desc = torch.empty(n, dtype=torch.int32, device=dev)
+    nat.check(nat.lib.gfx_row_describe(rp.data_ptr(), cs.data_ptr(), ct.data_ptr(), n,
+                                       desc.data_ptr(), _stream()))
+    return desc
+
+
+def _banded_vs_pair(nat, dev, problem, rp, cs, ct, n, seed, layers=(0, 1, 2, 3)):
+    rng = np.random.default_rng(seed)
+    h = _up((rng.standard_normal((n, 128)) * 2).astype(np.float16), dev)
+    desc = _device_describe(nat, dev, rp, cs, ct, n)
+    for layer in layers:
+        want = _buf(n, 0, dev)
+        got = torch.full((n + 64, 128), 7.0, dtype=torch.float16, device=dev)   # guard rows
+        nat.check(nat.lib.gfx_layer_fused_pair(problem["handle"], layer, h.data_ptr(), rp.data_ptr(),
+                                               cs.data_ptr(), ct.data_ptr(), n, want.data_ptr(),
+                                               _stream()))
+        nat.check(nat.lib.gfx_layer_fused_banded(problem["handle"], layer, h.data_ptr(), rp.data_ptr(),
+                                                 cs.data_ptr(), ct.data_ptr(), desc.data_ptr(), n,
+                                                 got.data_ptr(), _stream()))
+        torch.cuda.synchronize()
+        assert torch.all(got[n:] == 7.0)                       # nothing written past the last row
+        assert torch.equal(got[:n], want), (layer, n, (got[:n].float() - want.float()).abs().max().item())
+    return desc
+
+
+@pytest.mark.parametrize("seed,count", [(51, 1), (52, 3), (53, 40), (54, 333)])
+def test_row_descriptors_and_banded_layer_full_molecules(nat, dev, problem, seed, count):
+    """Full-molecule graphs: every row is banded (no GENERIC rows), descriptors equal the NumPy
+    restatement bit for bit, and the banded fused layer equals the pair kernel BIT FOR BIT (same
+    messages, same summation order) -- including odd tile counts and partly empty last tiles."""
+    import ginfinity_b200 as g
+    shard = g.GraphBuilder().build_shard(random_records(seed, count))
+    n = shard.node_count
+    rp, cs, ct = device_csr(nat, dev, shard.edge_index, shard.edge_types, n)
+    desc = _banded_vs_pair(nat, dev, problem, rp, cs, ct, n, seed)
+    want = _describe_rows(rp.cpu().numpy(), cs.cpu().numpy(), ct.cpu().numpy())
+    got = desc.cpu().numpy().view(np.uint32)
+    assert np.array_equal(got, want)
+    assert not (got & 0x80000000).any()
+
+
+def test_banded_layer_generic_rows_sliced_windows(nat, dev, problem):
+    """Windowed records with context nodes: remapped indices, partners without backbone -- many
+    rows are GENERIC and go through the CSR fallback; results still equal the pair kernel's."""
+    import ginfinity_b200 as g
+    recs = [g.RNA(r.identifier, r.sequence, r.structure, start=r.length // 4, end=r.length // 4 + r.length // 3)
+            for r in random_records(61, 60) if r.length >= 40]
+    shard = g.GraphBuilder(keep_paired_neighbours=True, context_hops=2).build_shard(recs)
+    n = shard.node_count
+    rp, cs, ct = device_csr(nat, dev, shard.edge_index, shard.edge_types, n)
+    desc = _banded_vs_pair(nat, dev, problem, rp, cs, ct, n, 61, layers=(0, 3))
+    got = desc.cpu().numpy().view(np.uint32)
+    assert np.array_equal(got, _describe_rows(rp.cpu().numpy(), cs.cpu().numpy(), ct.cpu().numpy()))
+
+
+def test_banded_layer_arbitrary_graph(nat, dev, problem):
+    """A graph that is nothing like an RNA (random sources, duplicate edges, self loops, hubs, all
+    ten edge types, isolated nodes): mostly GENERIC rows, a few that happen to look banded."""
+    rng = np.random.default_rng(62)
+    n, e = 1000, 4000
+    dst = rng.integers(0, n, e).astype(np.int32)
+    dst[:200] = 7                                               # a hub
+    src = rng.integers(0, n, e).astype(np.int32)
+    src[200:260] = dst[200:260]                                 # self loops
+    typ = rng.integers(0, 10, e).astype(np.uint8)
+    # some rows that ARE banded, appended in the canonical order
+    extra = []
+    for i in (300, 301, 500):
+        extra += [(i - 1, i, 0), (i + 1, i, 1), (i + 40, i, 2), (i - 2, i, 4), (i + 2, i, 5)]
+    keep = ~np.isin(dst, [300, 301, 500])
+    src = np.concatenate([src[keep], np.array([a for a, _, _ in extra], np.int32)])
+    dst = np.concatenate([dst[keep], np.array([b for _, b, _ in extra], np.int32)])
+    typ = np.concatenate([typ[keep], np.array([c for _, _, c in extra], np.uint8)])
+    rp, cs, ct = device_csr(nat, dev, np.stack([src, dst]), typ, n)
+    desc = _banded_vs_pair(nat, dev, problem, rp, cs, ct, n, 62, layers=(1,))
+    got = desc.cpu().numpy().view(np.uint32)
+    assert np.array_equal(got, _describe_rows(rp.cpu().numpy(), cs.cpu().numpy(), ct.cpu().numpy()))
+    assert (got[[300, 301, 500]] & 0x3f == 0x37).all() and (got & 0x80000000).sum() > 500
+
+
 @pytest.mark.parametrize("n", [1, 127, 128, 129, 200, 64 * 3 + 1])
 def test_tile_edges(nat, dev, problem, n):
     """Ragged sizes around the 128-row tile / 64-row block boundaries: all

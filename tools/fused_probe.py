@@ -33,10 +33,18 @@ nat.check(lib.gfx_csr_build(ei[0].data_ptr(), ei[1].data_ptr(), et.data_ptr(), N
                             ws.data_ptr(), need, S()))
 h = torch.randn(N, 128, device=dev).half()
 out = torch.empty_like(h)
-entry = getattr(lib, sys.argv[1] if len(sys.argv) > 1 else "gfx_layer_fused_pair")
+name = sys.argv[1] if len(sys.argv) > 1 else "gfx_layer_fused_pair"
+entry = getattr(lib, name)
+desc = torch.empty(N, dtype=torch.int32, device=dev)
+nat.check(lib.gfx_row_describe(row_ptr.data_ptr(), col_src.data_ptr(), col_type.data_ptr(), N,
+                               desc.data_ptr(), S()))
 def run():
-    nat.check(entry(handle, 0, h.data_ptr(), row_ptr.data_ptr(), col_src.data_ptr(),
-                                  col_type.data_ptr(), N, out.data_ptr(), S()))
+    if name == "gfx_layer_fused_banded":
+        nat.check(entry(handle, 0, h.data_ptr(), row_ptr.data_ptr(), col_src.data_ptr(),
+                        col_type.data_ptr(), desc.data_ptr(), N, out.data_ptr(), S()))
+    else:
+        nat.check(entry(handle, 0, h.data_ptr(), row_ptr.data_ptr(), col_src.data_ptr(),
+                        col_type.data_ptr(), N, out.data_ptr(), S()))
 for _ in range(4):
     run()
 torch.cuda.synchronize()
@@ -46,4 +54,4 @@ for _ in range(10):
     run()
 b.record()
 torch.cuda.synchronize()
-print("ok", N, E, "fused layer %.3f ms" % (a.elapsed_time(b) / 10))
+print("ok", name, N, E, "fused layer %.3f ms" % (a.elapsed_time(b) / 10))
