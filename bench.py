@@ -379,7 +379,8 @@ def main() -> None:
             common = {"launches": fused_calls, "avg_launch_ms": fused_ms / max(fused_calls, 1),
                       "share_of_step": fused_ms / args.steps / step_ms_rank,
                       "peak_source": peaks["source"]}
-            name = ("fused_pair_kernel (K1 + K2 in one kernel: aggregation producing the tcgen05 "
+            name = (("fused_banded_kernel" if getattr(encoder, "fused", 0) == 3 else "fused_pair_kernel") +
+                    " (K1 + K2 in one kernel: aggregation producing the tcgen05 "
                     "cta_group::2 A operand, MLP + LayerNorm + residual)")
             dominant = {"kernel": name, "bound": "tensor", "achieved": fl, "peak": peaks["tflops"],
                         "unit": "TFLOP/s", "frac": fl / peaks["tflops"],
@@ -421,11 +422,11 @@ def main() -> None:
             "stage_ms_per_step": stage_ms,
             "e2e_from_records": from_records,
             "roofline": dominant, "roofline_other": other, "roofline_two_kernel_layer": split_line,
-            "layer_kernel": {"chosen": "fused_pair_kernel" if getattr(encoder, "fused", 0) == 2
-                             else "K1 + K2",
-                             "tuning_ms_2e19_nodes": {("fused_pair" if k == 2 else "k1_k2"): round(v, 4)
+            "layer_kernel": {"chosen": {3: "fused_banded_kernel", 2: "fused_pair_kernel"}.get(
+                                 getattr(encoder, "fused", 0), "K1 + K2"),
+                             "tuning_ms_2e19_nodes": {{3: "fused_banded", 2: "fused_pair"}.get(k, "k1_k2"): round(v, 4)
                                                       for k, v in (encoder.layer_kernel_times or {}).items()},
-                             "how": "both forms of the layer timed once per device on a fixed "
+                             "how": "the forms of the layer timed once per device on a fixed "
                                     "synthetic chunk; GFX_FUSED pins the choice"},
             "setup": {"workload_generation_s": gen_s, "host_cpus": os.cpu_count(), "numa_binding": numa},
         }

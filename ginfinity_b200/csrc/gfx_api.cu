@@ -251,14 +251,24 @@ extern "C" int gfx_encode(const gfx_model *model, const float *x, const int32_t 
     return fail(GFX_ERR_WORKSPACE, "gfx_encode: workspace too small");
   if (fused && dtype != GFX_F16)
     return fail(GFX_ERR_UNSUPPORTED, "gfx_encode: fused layers exist for GFX_F16 only");
-  // the CTA-pair kernel covers <= 10 edge types and <= 2^27 nodes; outside that: K1 + K2
+  // the banded kernel covers >= 6 edge types and <= 2^25 nodes, the CTA-pair kernel <= 10 edge
+  // types and <= 2^27 nodes; outside that: K1 + K2
+  if (fused == 3 && (model->edge_dim < 6 || n > (int64_t(1) << 25))) fused = 2;
   if (fused == 2 && (model->edge_dim > 10 || n > (int64_t(1) << 27))) fused = 0;
   char *base = static_cast<char *>(ws);
   void *h = base, *z = base + act_bytes(n, dtype), *h2 = base + 2 * act_bytes(n, dtype);
   int rc = gfx_input_linear(model, x, n, h, dtype, stream);
   if (rc) return rc;
+  uint32_t *desc = static_cast<uint32_t *>(z);      // fused layers leave the z buffer free
+  if (fused == 3) {
+    rc = gfx_row_describe(row_ptr, col_src, col_type, n, desc, stream);
+    if (rc) return rc;
+  }
   for (int l = 0; l < model->layers; ++l) {
-    if (fused) {   // 1: one CTA per SM (gfx_fused5.cu); 2: CTA pairs (gfx_fused6.cu)
+    if (fused == 3) {   // CTA pairs, banded producers (gfx_fused7.cu)
+      rc = gfx_layer_fused_banded(model, l, h, row_ptr, col_src, col_type, desc, n, h2, stream);
+      if (rc) return rc;
+    } else if (fused) {   // 1: one CTA per SM (gfx_fused5.cu); 2: CTA pairs (gfx_fused6.cu)
       rc = (fused == 2 ? gfx_layer_fused_pair : gfx_layer_fused)(model, l, h, row_ptr, col_src,
                                                                  col_type, n, h2, stream);
       if (rc) return rc;

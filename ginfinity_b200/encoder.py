@@ -166,8 +166,9 @@ class Ginfinity:
         self._scratch = _Scratch(self._torch_device)
         # dense-stage implementation: 0 auto (tcgen05 for fp16), 1 SIMT
         self.impl = nat.IMPL_AUTO
-        # layer kernels: 2 = fused layer on CTA pairs (gfx_encode falls back to K1 + K2 where that
-        # kernel does not apply), 0 = K1 + K2, 1 = fused layer with one CTA per SM.  Which of 2
+        # layer kernels: 3 = fused layer on CTA pairs with banded producers, 2 = fused layer on CTA
+        # pairs with CSR-walking producers (gfx_encode falls back where a kernel does not apply),
+        # 0 = K1 + K2, 1 = fused layer with one CTA per SM.  Which of 3, 2
         # and 0 is faster differs from one B200 to the next (measured on this pool: 690 vs 620
         # M nt/s on some boards, 607 vs 702 on others), so by default (-1) both are timed once
         # per device on a fixed synthetic chunk before the first encode and the faster one is
@@ -284,17 +285,23 @@ class Ginfinity:
                      ) -> np.ndarray:
         return self.encode_graphs([graph], embedding_dtype=embedding_dtype)[0]
 
-    def _gfx_encode(self, n: int, stream: int, *args_before, tail) -> None:
+    def _gfx_encode(self, n: int, stream: int, *args_before, tail, banded: bool = True) -> None:
         """gfx_encode on the current torch stream (`stream` is its raw handle) with the layer
-        kernel chosen as described in __init__."""
+        kernel chosen as described in __init__.  `banded=False`: the shard holds context nodes
+        (windowed records), whose rows the banded kernel would take through its slow CSR
+        fallback; the pair kernel, which computes the same bits, is used instead (so a record
+        encodes to the same values alone, in a batch, and next to windowed records)."""
         if self.fused < 0:
             self._choose_layer_kernel()
-        nat.check(nat.lib.gfx_encode(*args_before, self.impl, int(self.fused), *tail, stream))
+        mode = int(self.fused)
+        if mode == 3 and not banded:
+            mode = 2
+        nat.check(nat.lib.gfx_encode(*args_before, self.impl, mode, *tail, stream))
 
     def _choose_layer_kernel(self) -> None:
         """Once per device and process: encode a fixed synthetic chunk (2^19 nodes, banded RNA-like
-        graph) with the fused pair kernel and with K1 + K2, timed with CUDA events, and keep the
-        faster.  The choice never depends on user data, so every encoder of a process on a given
+        graph) with the banded fused kernel, the fused pair kernel and K1 + K2, timed with CUDA
+        events, and keep the fastest.  The choice never depends on user data, so every encoder of a process on a given
         GPU computes with the same kernels."""
         key = self._torch_device.index or 0
         if key not in _LAYER_KERNEL_CHOICE:
@@ -307,14 +314,21 @@ class Ginfinity:
             stream = torch.cuda.current_stream().cuda_stream
             i = torch.arange(nodes, device=dev, dtype=torch.int32)
             src, dst, typ = [], [], []
-            for offset, code in ((-1, 0), (1, 1), (-2, 4), (2, 5)):      # backbone and skip-2 edges
+
+            def band(offset, code):
                 s_ = i + offset
                 ok = (s_ >= 0) & (s_ < nodes)
                 src.append(s_[ok]); dst.append(i[ok])
                 typ.append(torch.full((int(ok.sum()),), code, dtype=torch.uint8, device=dev))
+
+            # the reference builder's edge order (graph.py:494-561): backbone, pairs, skip-2
+            band(-1, 0)
+            band(1, 1)
             mate = i ^ 32                                                  # a pair 32 nt away
             src.append(mate); dst.append(i)
             typ.append(torch.where(mate < i, 2, 3).to(torch.uint8))
+            band(-2, 4)
+            band(2, 5)
             src, dst, typ = torch.cat(src), torch.cat(dst), torch.cat(typ)
             e = int(src.shape[0])
             x = torch.rand((nodes, 7), device=dev, dtype=torch.float32)
@@ -330,7 +344,7 @@ class Ginfinity:
             ews = torch.empty(need, dtype=torch.uint8, device=dev)
             out = torch.empty((nodes, 128), dtype=torch.float16, device=dev)
             times = {}
-            for mode in (2, 0):
+            for mode in (3, 2, 0):
                 def run():
                     nat.check(lib.gfx_encode(self._handle, x.data_ptr(), row_ptr.data_ptr(),
                                              col_src.data_ptr(), col_type.data_ptr(), None, nodes,
@@ -525,7 +539,7 @@ class Ginfinity:
                 n, main.cuda_stream, self._handle, slot["x"].data_ptr(), row_ptr.data_ptr(),
                 col_src.data_ptr(), col_type.data_ptr(),
                 None if out_row is None else out_row[n0:].data_ptr(), n, out_base,
-                act, out_code, tail=(enc_ws.data_ptr(), enc_ws_bytes))
+                act, out_code, tail=(enc_ws.data_ptr(), enc_ws_bytes), banded=out_row is None)
             slot["in_free"].record(main)
             slot["out_ready"].record(main)
             with torch.cuda.stream(s_out):
@@ -786,7 +800,7 @@ class Ginfinity:
         self._gfx_encode(
             n, stream, self._handle, ds.node_features[n0:].data_ptr(), row_ptr.data_ptr(),
             col_src.data_ptr(), col_type.data_ptr(), map_ptr, n, out_base, act,
-            out_dtype, tail=(enc_ws.data_ptr(), enc_ws_bytes))
+            out_dtype, tail=(enc_ws.data_ptr(), enc_ws_bytes), banded=map_ptr is None)
 
 
 def _check_unique_ids(records) -> None:

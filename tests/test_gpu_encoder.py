@@ -198,33 +198,45 @@ def test_synthetic_shard_matches_oracle_and_is_layout_invariant(gb, syn16, synth
     assert _cos(a, want).min() >= 0.9999
 
 
-def test_layer_kernel_is_chosen_once_per_device_and_both_forms_agree(gb, syn16, synthetic_state):
-    """The fp16 model's layer runs either as one kernel on CTA pairs or as K1 + K2; which is
-    faster differs between boards, so the encoder times both once per device on a fixed
-    synthetic chunk.  The choice is made before the first encode, is shared by every encoder
-    of the process on that device, and both forms stay within the fp16-path tolerance of the
-    oracle and of each other."""
+def test_layer_kernel_is_chosen_once_per_device_and_all_forms_agree(gb, syn16, synthetic_state):
+    """The fp16 model's layer runs as one kernel on CTA pairs (banded producers, or producers that
+    walk the CSR arrays) or as K1 + K2; which is fastest differs between boards, so the encoder
+    times the forms once per device on a fixed synthetic chunk.  The choice is made before the
+    first encode, is shared by every encoder of the process on that device, the two fused forms
+    agree bit for bit, and all stay within the fp16-path tolerance of the oracle and of each other.
+    Windowed shards (context nodes) never take the banded form."""
     from ginfinity_b200 import encoder as E
     shard = gb.GraphBuilder().build_shard(random_records(35, 120))
     fresh = gb.Ginfinity.from_state(synthetic_state, device="cuda:0")
     auto = np.concatenate(fresh.encode_graphs(shard, embedding_dtype=np.float32))
-    assert fresh.fused in (0, 2) and set(fresh.layer_kernel_times) == {0, 2}
+    assert fresh.fused in (0, 2, 3) and set(fresh.layer_kernel_times) == {0, 2, 3}
     assert E._LAYER_KERNEL_CHOICE[0][0] == fresh.fused
     other = gb.Ginfinity.from_state(synthetic_state, device="cuda:0")
     other.encode_graphs(shard)
     assert other.fused == fresh.fused                      # same choice, not re-measured
     outs = {}
-    for mode in (0, 2):
+    for mode in (0, 2, 3):
         pinned = gb.Ginfinity.from_state(synthetic_state, device="cuda:0")
         pinned.fused = mode
         outs[mode] = np.concatenate(pinned.encode_graphs(shard, embedding_dtype=np.float32))
     assert np.array_equal(auto, outs[fresh.fused])
+    assert np.array_equal(outs[2], outs[3])                # same messages, same summation order
     assert np.abs(outs[0] - outs[2]).max() <= 2e-3
     fw = O.fold_state(synthetic_state)
     want = np.concatenate(O.encode_shard(fw, shard, embedding_dtype=np.float32, half_storage=True))
-    for mode in (0, 2):
+    for mode in (0, 2, 3):
         assert np.abs(outs[mode] - want).max() <= 3e-3
         assert _cos(outs[mode], want).min() >= 0.9999
+    # windowed records with context nodes: pinned to the banded form or not, same bits as mode 2
+    recs = [gb.RNA(r.identifier, r.sequence, r.structure, start=r.length // 4, end=r.length // 2)
+            for r in random_records(36, 40)]
+    kw = dict(keep_paired_neighbours=True, context_hops=2, embedding_dtype=np.float32)
+    win = {}
+    for mode in (2, 3):
+        pinned = gb.Ginfinity.from_state(synthetic_state, device="cuda:0")
+        pinned.fused = mode
+        win[mode] = np.concatenate(pinned.encode_many(recs, **kw))
+    assert np.array_equal(win[2], win[3])
     full = gb.Ginfinity.from_state(synthetic_state, device="cuda:0", full_precision=True)
     assert full.fused == 0                                 # fp32 model: K1 + K2 (SIMT) only
 

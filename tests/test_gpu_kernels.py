@@ -523,7 +523,7 @@ def test_mlp_pair_kernel_many_tiles(nat, dev, problem, n):
     assert diff <= 4e-3 * max(1.0, outs[0][:n].float().abs().max().item()), (n, diff)
 
 
-@pytest.mark.parametrize("code,impl,fused", [(1, 1, 0), (0, 1, 0), (0, 2, 0), (0, 3, 0), (0, 4, 0), (0, 5, 0), (0, 6, 0), (0, 7, 0), (0, 2, 1), (0, 5, 2)])
+@pytest.mark.parametrize("code,impl,fused", [(1, 1, 0), (0, 1, 0), (0, 2, 0), (0, 3, 0), (0, 4, 0), (0, 5, 0), (0, 6, 0), (0, 7, 0), (0, 2, 1), (0, 5, 2), (0, 5, 3)])
 def test_whole_forward(nat, dev, problem, code, impl, fused):
     """gfx_encode (all stages chained on device) against the oracle."""
     x = _up(problem["shard"].node_features, dev)

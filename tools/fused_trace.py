@@ -33,9 +33,22 @@ nat.check(lib.gfx_csr_build(ei[0].data_ptr(), ei[1].data_ptr(), et.data_ptr(), N
                             ws.data_ptr(), need, S()))
 h = torch.randn(N, 128, device=dev).half()
 out = torch.empty_like(h)
-run = lambda: nat.check(lib.gfx_layer_fused_pair(handle, 0, h.data_ptr(), row_ptr.data_ptr(),  # noqa: E731
-                                                 col_src.data_ptr(), col_type.data_ptr(), N,
-                                                 out.data_ptr(), S()))
+banded = len(sys.argv) > 1 and sys.argv[1] == "banded"
+desc = torch.empty(N, dtype=torch.int32, device=dev)
+nat.check(lib.gfx_row_describe(row_ptr.data_ptr(), col_src.data_ptr(), col_type.data_ptr(), N,
+                               desc.data_ptr(), S()))
+
+
+def run():
+    if banded:
+        nat.check(lib.gfx_layer_fused_banded(handle, 0, h.data_ptr(), row_ptr.data_ptr(), col_src.data_ptr(),
+                                             col_type.data_ptr(), desc.data_ptr(), N, out.data_ptr(), S()))
+    else:
+        nat.check(lib.gfx_layer_fused_pair(handle, 0, h.data_ptr(), row_ptr.data_ptr(), col_src.data_ptr(),
+                                           col_type.data_ptr(), N, out.data_ptr(), S()))
+
+
+
 for _ in range(3):
     run()
 torch.cuda.synchronize()

@@ -16,13 +16,13 @@ timeout 600 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-records-
 cp gpurun_out/bench_short.json gpurun_out/bench_for_pin.json
 fi
 [ -f gpurun_out/bench_for_pin.json ] || cp gpurun_out/bench.json gpurun_out/bench_for_pin.json
-export GFX_FUSED=$(python -c "import json; print(2 if 'fused' in json.load(open('gpurun_out/bench_for_pin.json'))['layer_kernel']['chosen'].lower() else 0)")
+export GFX_FUSED=$(python -c "import json; c = json.load(open('gpurun_out/bench_for_pin.json'))['layer_kernel']['chosen'].lower(); print(3 if 'banded' in c else 2 if 'fused' in c else 0)")
 echo "ncu passes pinned to GFX_FUSED=$GFX_FUSED" > gpurun_out/ncu_pin.log
 NCU_CMD="python bench.py --steps 1 --warmup 1 --records 20000 --no-cpu-baseline"
 timeout 300 $NCU_CMD > gpurun_out/ncu_plain.log 2>&1 && \
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches.csv $NCU_CMD > gpurun_out/ncu_launches.log 2>&1
 timeout 300 $NCU_CMD > gpurun_out/ncu_plain2.log 2>&1 && \
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"fused_pair|umma4_mlp|aggregate_f16|umma2_kernel|input_linear4" -s 7 -c 7 -o gpurun_out/prof_top $NCU_CMD > gpurun_out/ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"fused_banded|fused_pair|umma4_mlp|aggregate_f16|umma2_kernel|input_linear4" -s 7 -c 7 -o gpurun_out/prof_top $NCU_CMD > gpurun_out/ncu_full.log 2>&1
 if [ "$1" != "ncu" ]; then
 unset GFX_FUSED
 SEARCH_CMD="python tools/search_bench.py 3"
