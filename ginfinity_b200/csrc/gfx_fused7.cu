@@ -80,6 +80,7 @@ struct Args {
   const int32_t *row_ptr, *col_src;
   const uint8_t *col_type;
   const uint32_t *desc;      // [n] row descriptors
+  uint32_t sleep_ns;         // sleep between barrier polls of the warp-wide waits
   const __half *table16, *w1_img, *w2_img;
   const float *b2, *g, *b;   // device vectors of this layer
   int64_t n;
@@ -91,6 +92,16 @@ struct Args {
 // parked wait (suspend-time hint) on a local barrier
 __device__ __forceinline__ void mbar_wait_c(uint64_t *bar, uint32_t parity) {
   mbar_wait_parked(bar, parity);
+}
+// Wait of a whole warp (or of a utility thread off the critical path) with a plain sleep between
+// polls.  The parked form (try_wait with a suspend-time hint) compiles to TRYWAIT + NANOSLEEP.SYNCS,
+// and that sleep ends on ANY barrier activity of the CTA: in this kernel a waiting warp re-polled
+// every ~50 cycles, and those loops were 30 % of all issued instructions of an issue-bound kernel
+// (ncu source page of the first banded version).
+__device__ __forceinline__ void mbar_wait_s(uint64_t *bar, uint32_t parity, uint32_t sleep_ns) {
+  while (!mbar_try_wait(bar, parity)) {
+    if (sleep_ns) __nanosleep(sleep_ns);
+  }
 }
 __device__ __forceinline__ void fence_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
@@ -163,9 +174,9 @@ __device__ __forceinline__ uint32_t sw_off(int r, int c8) {
 // D1[:, HALF*128 .. +128) -> bias + ReLU -> fp16 -> A2[:, HALF*64 .. +64), 32 columns at a time
 template <int HALF>
 __device__ __forceinline__ void epi_a(const Consts &c, uint32_t trow, uint64_t *bar, uint32_t ph,
-                                      int lane, uint32_t leader_bar) {
+                                      int lane, uint32_t leader_bar, uint32_t sleep_ns) {
   constexpr int col0 = HALF * H;
-  mbar_wait_c(bar + (HALF ? kBarD1bFull : kBarD1aFull), ph);
+  mbar_wait_s(bar + (HALF ? kBarD1bFull : kBarD1aFull), ph, sleep_ns);
   tc_fence_after();
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
@@ -250,8 +261,8 @@ fused_banded_kernel(const __grid_constant__ Maps maps, const __grid_constant__ C
     uint32_t it = 0;
     for (int pair = cluster_id; pair < pairs; pair += clusters, ++it) {
       if (tid == 0) trace_ev(p, it, 6);
-      epi_a<0>(c, trow, bar, it & 1, lane, a2a);
-      epi_a<1>(c, trow, bar, it & 1, lane, a2b);
+      epi_a<0>(c, trow, bar, it & 1, lane, a2a, p.sleep_ns);
+      epi_a<1>(c, trow, bar, it & 1, lane, a2b, p.sleep_ns);
       if (tid == 0) trace_ev(p, it, 7);
     }
   } else if (warp < kProdWarp0) {
@@ -267,7 +278,7 @@ fused_banded_kernel(const __grid_constant__ Maps maps, const __grid_constant__ C
     for (int pair = cluster_id; pair < pairs; pair += clusters, ++it) {
       if (int(it & 1) != g) continue;
       const uint32_t hb = it % kHBufs;
-      mbar_wait_c(bar + kBarD2Full + g, (it >> 1) & 1);
+      mbar_wait_s(bar + kBarD2Full + g, (it >> 1) & 1, p.sleep_ns);
       tc_fence_after();
       if (lane == 0 && quad == 0) trace_ev(p, it, 8);
       // 16 columns at a time, loops NOT unrolled: an unrolled body lets the compiler hoist the
@@ -292,7 +303,7 @@ fused_banded_kernel(const __grid_constant__ Maps maps, const __grid_constant__ C
       const float var = fmaxf((s2[0] + s2[1]) * (1.f / kHidden) - mean * mean, 0.f);
       const float rstd = rsqrtf(var + 1e-5f);
       const float nm = -mean * rstd;
-      mbar_wait_c(bar + kBarHFull + hb, (it / kHBufs) & 1);      // long complete: visibility only
+      mbar_wait_s(bar + kBarHFull + hb, (it / kHBufs) & 1, 0);   // long complete: visibility only
       const uint32_t hrow = smem_u32(hs) + hb * kTileBytes;
 #pragma unroll 1
       for (int q = 0; q < 8; ++q) {
@@ -376,8 +387,8 @@ fused_banded_kernel(const __grid_constant__ Maps maps, const __grid_constant__ C
       fetch_halo(pair + clusters, hx0, hx1);
       const uint32_t hbase = smem_u32(hs) + hb * kTileBytes;
       const uint32_t zbase = smem_u32(zs) + s * kTileBytes;
-      mbar_wait_c(bar + kBarHFull + hb, (it / kHBufs) & 1);
-      mbar_wait_c(bar + kBarA1Empty + s, ((it >> 1) & 1) ^ 1);
+      mbar_wait_s(bar + kBarHFull + hb, (it / kHBufs) & 1, p.sleep_ns);
+      mbar_wait_s(bar + kBarA1Empty + s, ((it >> 1) & 1) ^ 1, p.sleep_ns);
       if (warp == kProdWarp0 && lane == 0) trace_ev(p, it, 0);
       // partner row of the warp's row `idx` (a row without a pair reads itself; its message is +0)
       auto partner = [&](int idx) -> uint2 {
@@ -394,17 +405,31 @@ fused_banded_kernel(const __grid_constant__ Maps maps, const __grid_constant__ C
         uint2 pr[2][4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) pr[0][q] = partner(kRun * run + q);
-        // window: tile rows base - 2 .. base + kRun + 1
+        // window: tile rows base - 2 .. base + kRun + 1.  base is a multiple of 8, so the swizzle
+        // term of row base - 2 + k depends on k only: one XOR with an immediate per row.  Only
+        // the first two / last two rows of the window can lie outside the tile (first / last run
+        // of the tile: warp-uniform), where the prefetched halo rows stand in.
+        static_assert(kRun == 8, "the swizzle pattern repeats every 8 rows");
+        const uint32_t wbase = hbase + kboff + odd8 + uint32_t(base) * 128u;   // row `base`, chunk 0
+        const uint32_t c8s = c8 << 4;
+        auto wrow = [&](int k) -> uint2 {                   // k = 0 .. kRun + 3 <-> row base - 2 + k
+          return lds64(wbase + uint32_t((k - 2) * 128) + (c8s ^ (uint32_t((k - 2) & 7) << 4)));
+        };
+        const bool first = base == 0, last = base + kRun == kTileM;
         uint2 w[kRun + 4];
+        w[0] = halo0;
+        w[1] = halo1;
+        if (!first) {
+          w[0] = wrow(0);
+          w[1] = wrow(1);
+        }
 #pragma unroll
-        for (int k = 0; k < kRun + 4; ++k) {
-          const int lr = base - 2 + k;
-          if (lr < 0)
-            w[k] = k == 0 ? halo0 : halo1;
-          else if (lr >= kTileM)
-            w[k] = lr == kTileM ? halo0 : halo1;
-          else
-            w[k] = lds64(hbase + cell(lr));
+        for (int k = 2; k < kRun + 2; ++k) w[k] = wrow(k);
+        w[kRun + 2] = halo0;
+        w[kRun + 3] = halo1;
+        if (!last) {
+          w[kRun + 2] = wrow(kRun + 2);
+          w[kRun + 3] = wrow(kRun + 3);
         }
 #pragma unroll
         for (int j = 0; j < kRun; ++j) {
@@ -431,7 +456,7 @@ fused_banded_kernel(const __grid_constant__ Maps maps, const __grid_constant__ C
           uint2 o;
           o.x = pack2(fmaf(p.eps1, f0.x, acc[0]), fmaf(p.eps1, f0.y, acc[1]));
           o.y = pack2(fmaf(p.eps1, f1.x, acc[2]), fmaf(p.eps1, f1.y, acc[3]));
-          sts64(zbase + cell(base + j), o);
+          sts64(zbase + kboff + odd8 + uint32_t(base + j) * 128u + (c8s ^ (uint32_t(j & 7) << 4)), o);
         }
       }
       // rows that are not banded: recomputed from the CSR arrays, one row at a time (warp-uniform)
@@ -550,7 +575,7 @@ fused_banded_kernel(const __grid_constant__ Maps maps, const __grid_constant__ C
         const uint32_t hb = it % kHBufs;
         const int row0 = (2 * pair + int(rank)) * kTileM;
         uint8_t *dst = hs + hb * kTileBytes;
-        mbar_wait_parked(bar + kBarHEmpty + hb, ((it / kHBufs) & 1) ^ 1);
+        mbar_wait_s(bar + kBarHEmpty + hb, ((it / kHBufs) & 1) ^ 1, p.sleep_ns);
         trace_ev(p, it, 12);
         mbar_arrive_expect_tx(bar + kBarHFull + hb, kTileBytes);
         tma_load_2d(dst, &maps.h, 0, row0, bar + kBarHFull + hb);
@@ -568,7 +593,7 @@ fused_banded_kernel(const __grid_constant__ Maps maps, const __grid_constant__ C
         const uint32_t hb = it % kHBufs;
         const int row0 = (2 * pair + int(rank)) * kTileM;
         const uint8_t *src = hs + hb * kTileBytes;
-        mbar_wait_parked(bar + kBarOReady + hb, (it / kHBufs) & 1);
+        mbar_wait_s(bar + kBarOReady + hb, (it / kHBufs) & 1, p.sleep_ns);
         trace_ev(p, it, 10);
         if (row0 < n) {
           tma_store_2d(&maps.out, 0, row0, src);
@@ -652,6 +677,11 @@ int fused7_layer(const gfx_model *m, int layer, const __half *h, const int32_t *
   a.b = m->ln_b + size_t(layer) * kHidden;
   a.n = n; a.edge_dim = m->edge_dim; a.eps1 = m->eps1[layer];
   a.trace = g_trace;
+  static const uint32_t sleep_ns = [] {
+    const char *v = getenv("GFX_FUSED_SLEEP_NS");   // developer switch
+    return uint32_t(v ? atoi(v) : 64);
+  }();
+  a.sleep_ns = sleep_ns;
   auto kernel = v7::fused_banded_kernel<true>;
   GFX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v7::Smem::total));
   const int64_t tiles = (n + v7::kTileM - 1) / v7::kTileM;
