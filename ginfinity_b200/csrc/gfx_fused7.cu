@@ -20,6 +20,7 @@
 // the two kernels agree BIT FOR BIT.  GENERIC rows (sliced windows with context nodes, arbitrary
 // graphs) are recomputed from the CSR arrays by a slow warp-per-row loop after the run.
 #include <cstdlib>
+#include <type_traits>
 
 #include "gfx_common.cuh"
 #include "gfx_tma.cuh"
@@ -390,9 +391,8 @@ fused_banded_kernel(const __grid_constant__ Maps maps, const __grid_constant__ C
       mbar_wait_s(bar + kBarHFull + hb, (it / kHBufs) & 1, p.sleep_ns);
       mbar_wait_s(bar + kBarA1Empty + s, ((it >> 1) & 1) ^ 1, p.sleep_ns);
       if (warp == kProdWarp0 && lane == 0) trace_ev(p, it, 0);
-      // partner row of the warp's row `idx` (a row without a pair reads itself; its message is +0)
-      auto partner = [&](int idx) -> uint2 {
-        const uint32_t dj = __shfl_sync(0xffffffffu, d, idx);
+      // partner row of a row with descriptor dj (a row without a pair reads itself; its message is +0)
+      auto partner = [&](uint32_t dj, int idx) -> uint2 {
         const int self = kRowsPerWarp * pw + idx;
         const int src = (dj & kDescPair) ? int((dj >> kDescPartnerShift) & kDescPartnerMask) : row0 + self;
         const uint32_t local = uint32_t(src - row0);
@@ -402,9 +402,12 @@ fused_banded_kernel(const __grid_constant__ Maps maps, const __grid_constant__ C
 #pragma unroll 1
       for (int run = 0; run < kRowsPerWarp / kRun; ++run) {
         const int base = kRowsPerWarp * pw + kRun * run;   // first tile row of the run
+        uint32_t dj[kRun];                                 // the run's descriptors, warp-uniform
+#pragma unroll
+        for (int j = 0; j < kRun; ++j) dj[j] = __shfl_sync(0xffffffffu, d, kRun * run + j);
         uint2 pr[2][4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) pr[0][q] = partner(kRun * run + q);
+        for (int q = 0; q < 4; ++q) pr[0][q] = partner(dj[q], kRun * run + q);
         // window: tile rows base - 2 .. base + kRun + 1.  base is a multiple of 8, so the swizzle
         // term of row base - 2 + k depends on k only: one XOR with an immediate per row.  Only
         // the first two / last two rows of the window can lie outside the tile (first / last run
@@ -431,33 +434,47 @@ fused_banded_kernel(const __grid_constant__ Maps maps, const __grid_constant__ C
           w[kRun + 2] = wrow(kRun + 2);
           w[kRun + 3] = wrow(kRun + 3);
         }
+        // INTERIOR: every row of the run has its four backbone / skip neighbours (all but the runs
+        // at molecule ends): their table rows are used as they are, no selects
+        auto nodes = [&](auto interior_c) {
+          constexpr bool INTERIOR = decltype(interior_c)::value;
 #pragma unroll
-        for (int j = 0; j < kRun; ++j) {
-          if ((j & 3) == 0 && j + 4 < kRun) {
+          for (int j = 0; j < kRun; ++j) {
+            if ((j & 3) == 0 && j + 4 < kRun) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) pr[((j >> 2) + 1) & 1][q] = partner(kRun * run + j + 4 + q);
+              for (int q = 0; q < 4; ++q)
+                pr[((j >> 2) + 1) & 1][q] = partner(dj[j + 4 + q], kRun * run + j + 4 + q);
+            }
+            const uint32_t dd = dj[j];
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            uint2 tt;
+            tt = INTERIOR || (dd & kDescPrev) ? tb[0] : kNone;
+            add_message4(acc, w[j + 1], tt);
+            tt = INTERIOR || (dd & kDescNext) ? tb[1] : kNone;
+            add_message4(acc, w[j + 3], tt);
+            tt = (dd & kDescPairRev) ? tb[3] : tb[2];
+            tt = (dd & kDescPair) ? tt : kNone;
+            add_message4(acc, pr[(j >> 2) & 1][j & 3], tt);
+            tt = INTERIOR || (dd & kDescPrev2) ? tb[4] : kNone;
+            add_message4(acc, w[j], tt);
+            tt = INTERIOR || (dd & kDescNext2) ? tb[5] : kNone;
+            add_message4(acc, w[j + 4], tt);
+            const __half2 *sv = reinterpret_cast<const __half2 *>(&w[j + 2]);
+            const float2 f0 = __half22float2(sv[0]), f1 = __half22float2(sv[1]);
+            uint2 o;
+            o.x = pack2(fmaf(p.eps1, f0.x, acc[0]), fmaf(p.eps1, f0.y, acc[1]));
+            o.y = pack2(fmaf(p.eps1, f1.x, acc[2]), fmaf(p.eps1, f1.y, acc[3]));
+            sts64(zbase + kboff + odd8 + uint32_t(base + j) * 128u + (c8s ^ (uint32_t(j & 7) << 4)), o);
           }
-          const uint32_t dj = __shfl_sync(0xffffffffu, d, kRun * run + j);
-          float acc[4] = {0.f, 0.f, 0.f, 0.f};
-          uint2 tt;
-          tt = (dj & kDescPrev) ? tb[0] : kNone;
-          add_message4(acc, w[j + 1], tt);
-          tt = (dj & kDescNext) ? tb[1] : kNone;
-          add_message4(acc, w[j + 3], tt);
-          tt = (dj & kDescPairRev) ? tb[3] : tb[2];
-          tt = (dj & kDescPair) ? tt : kNone;
-          add_message4(acc, pr[(j >> 2) & 1][j & 3], tt);
-          tt = (dj & kDescPrev2) ? tb[4] : kNone;
-          add_message4(acc, w[j], tt);
-          tt = (dj & kDescNext2) ? tb[5] : kNone;
-          add_message4(acc, w[j + 4], tt);
-          const __half2 *sv = reinterpret_cast<const __half2 *>(&w[j + 2]);
-          const float2 f0 = __half22float2(sv[0]), f1 = __half22float2(sv[1]);
-          uint2 o;
-          o.x = pack2(fmaf(p.eps1, f0.x, acc[0]), fmaf(p.eps1, f0.y, acc[1]));
-          o.y = pack2(fmaf(p.eps1, f1.x, acc[2]), fmaf(p.eps1, f1.y, acc[3]));
-          sts64(zbase + kboff + odd8 + uint32_t(base + j) * 128u + (c8s ^ (uint32_t(j & 7) << 4)), o);
-        }
+        };
+        uint32_t all = dj[0];
+#pragma unroll
+        for (int j = 1; j < kRun; ++j) all &= dj[j];
+        constexpr uint32_t kBackbone = kDescPrev | kDescNext | kDescPrev2 | kDescNext2;
+        if ((all & kBackbone) == kBackbone)
+          nodes(std::true_type{});
+        else
+          nodes(std::false_type{});
       }
       // rows that are not banded: recomputed from the CSR arrays, one row at a time (warp-uniform)
       if (__ballot_sync(0xffffffffu, (d & kDescGeneric) != 0u) != 0u) {
