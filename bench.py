@@ -43,6 +43,7 @@ MAX_BATCH_NODES, MAX_BATCH_EDGES = 60_000, 300_000
 FLOP_PER_NODE_MLP = 2 * 128 * 256 * 2            # K2, per layer  
 BYTES_PER_NODE_AGG = 539.0                        # K1 fp16, per layer
 BYTES_PER_NODE_FUSED = 539.0                      # fused layer: h in 256, h' out 256, CSR 26.7
+BYTES_PER_NODE_BANDED = 516.0                     # banded fused layer: h in 256, h' out 256, row descriptor 4
 
 
 def measured_peaks():
@@ -375,7 +376,8 @@ def main() -> None:
             # K1 + K2 as one kernel on CTA pairs: the layer's dense FLOPs against the tensor peak
             # (its HBM side -- h in, h' out, CSR entries: 539 B per node-layer -- is the "other")
             fl = node_layers * FLOP_PER_NODE_MLP / (fused_ms * 1e-3) / 1e12
-            gb = node_layers * BYTES_PER_NODE_FUSED / (fused_ms * 1e-3) / 1e9
+            banded = getattr(encoder, "fused", 0) == 3
+            gb = node_layers * (BYTES_PER_NODE_BANDED if banded else BYTES_PER_NODE_FUSED) / (fused_ms * 1e-3) / 1e9
             common = {"launches": fused_calls, "avg_launch_ms": fused_ms / max(fused_calls, 1),
                       "share_of_step": fused_ms / args.steps / step_ms_rank,
                       "peak_source": peaks["source"]}
@@ -384,11 +386,13 @@ def main() -> None:
                     "cta_group::2 A operand, MLP + LayerNorm + residual)")
             dominant = {"kernel": name, "bound": "tensor", "achieved": fl, "peak": peaks["tflops"],
                         "unit": "TFLOP/s", "frac": fl / peaks["tflops"],
-                        "traffic": ncu_traffic("fused_layer", node_layers / max(fused_calls, 1)),
+                        "traffic": ncu_traffic("fused_banded" if banded else "fused_layer",
+                                               node_layers / max(fused_calls, 1)),
                         **common}
             other = {"kernel": name + " -- HBM side", "bound": "hbm", "achieved": gb,
                      "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gb / peaks["hbm_gbs"],
-                     "traffic": ncu_traffic("fused_layer", node_layers / max(fused_calls, 1)),
+                     "traffic": ncu_traffic("fused_banded" if banded else "fused_layer",
+                                            node_layers / max(fused_calls, 1)),
                      **common}
         split_line = None
         if split is not None:
