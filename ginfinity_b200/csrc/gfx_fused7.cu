@@ -202,7 +202,6 @@ __device__ __forceinline__ void trace_ev(const Args &p, uint32_t it, int ev) {
   if (p.trace != nullptr && blockIdx.x == 0 && it < 64) p.trace[it * 16 + ev] = clock64();
 }
 
-template <bool WIDE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWarps * 32, 1)
 fused_banded_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Consts c, const Args p) {
   using L = Smem;
@@ -519,7 +518,7 @@ fused_banded_kernel(const __grid_constant__ Maps maps, const __grid_constant__ C
         for (int half = 0; half < 2; ++half)
           bulk_g2s(w1s + (kb * 2 + half) * kWPiece,
                    w1g + kb * (HID * 128) +
-                       (WIDE ? H * int(rank) + 64 * half : H * half + 64 * int(rank)) * 128,
+                       (H * int(rank) + 64 * half) * 128,
                    kWPiece, bar + kBarWLocal);
       for (int kb = 0; kb < 4; ++kb)              // rows [64 rank, +64) of K block kb
         bulk_g2s(w2s + kb * kWPiece, w2g + kb * (kHidden * 128) + 64 * int(rank) * 128, kWPiece,
@@ -537,30 +536,16 @@ fused_banded_kernel(const __grid_constant__ Maps maps, const __grid_constant__ C
           mbar_wait_c(bar + kBarA1Full + s, ph2);
           tc_fence_after();
           trace_ev(p, it, 2);
-          if (WIDE) {
-            constexpr uint32_t idesc_w = idesc_f16(2 * kTileM, HID);   // GEMM 1: N = 256
+          constexpr uint32_t idesc_w = idesc_f16(2 * kTileM, HID);   // GEMM 1: N = 256
 #pragma unroll
-            for (int kk = 0; kk < 8; ++kk) {
-              const int kb = kk >> 2, k = kk & 3;
-              const uint64_t da = smem_desc_sw128(za + kb * kKbBytes + k * 32);
-              const uint64_t db = smem_desc_sw128(w1a + kb * 2 * kWPiece + k * 32);
-              mma2_f16_ss(tmem, da, db, idesc_w, kk != 0);
-            }
-            mma2_commit(bar + kBarD1aFull);
-            mma2_commit(bar + kBarD1bFull);
-          } else {                      // two column halves of N = 128 (rows [128 half + 64 rank, +64))
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-#pragma unroll
-              for (int kk = 0; kk < 8; ++kk) {
-                const int kb = kk >> 2, k = kk & 3;
-                const uint64_t da = smem_desc_sw128(za + kb * kKbBytes + k * 32);
-                const uint64_t db = smem_desc_sw128(w1a + (kb * 2 + half) * kWPiece + k * 32);
-                mma2_f16_ss(tmem + half * H, da, db, idesc, kk != 0);
-              }
-              mma2_commit(bar + (half ? kBarD1bFull : kBarD1aFull));
-            }
+          for (int kk = 0; kk < 8; ++kk) {
+            const int kb = kk >> 2, k = kk & 3;
+            const uint64_t da = smem_desc_sw128(za + kb * kKbBytes + k * 32);
+            const uint64_t db = smem_desc_sw128(w1a + kb * 2 * kWPiece + k * 32);
+            mma2_f16_ss(tmem, da, db, idesc_w, kk != 0);
           }
+          mma2_commit(bar + kBarD1aFull);
+          mma2_commit(bar + kBarD1bFull);
           mma2_commit(bar + kBarA1Empty + s);          // z consumed in both CTAs
           trace_ev(p, it, 3);
           mbar_wait_c(bar + kBarA2aFull, ph);
@@ -699,7 +684,7 @@ int fused7_layer(const gfx_model *m, int layer, const __half *h, const int32_t *
     return uint32_t(v ? atoi(v) : 64);
   }();
   a.sleep_ns = sleep_ns;
-  auto kernel = v7::fused_banded_kernel<true>;
+  auto kernel = v7::fused_banded_kernel;
   GFX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v7::Smem::total));
   const int64_t tiles = (n + v7::kTileM - 1) / v7::kTileM;
   const int64_t pairs = (tiles + 1) / 2;
