@@ -181,7 +181,7 @@ def run_reference(args, rank: int, world: int) -> None:
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "host_cpus": os.cpu_count(),
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, records):
@@ -190,6 +190,27 @@ def workload_config(args, records):
             "records_per_gpu": records, "max_batch_nodes": MAX_BATCH_NODES,
             "max_batch_edges": MAX_BATCH_EDGES, "parallelism": f"shard-per-gpu x{args.gpus}",
             "l2_policy": "inputs larger than L2 (1.4 GB of shard arrays per pass)"}
+
+
+_JSON_OUT = None
+
+
+def protect_stdout() -> None:
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version
+    banner on stdout at every NCCL_DEBUG level from VERSION up, WARN included), so file descriptor 1
+    is pointed at stderr for the whole run and the JSON line goes to a private copy of the
+    original stdout."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main() -> None:
@@ -207,6 +228,7 @@ def main() -> None:
     ap.add_argument("--chunk-nodes", type=int, default=0,
                     help="nodes per device chunk (0 = the encoder's default)")
     args = ap.parse_args()
+    protect_stdout()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -224,9 +246,9 @@ def main() -> None:
     from ginfinity_b200.multi_gpu import bind_to_gpu_numa_node
     numa = bind_to_gpu_numa_node(local_rank)       # before any pinned allocation
     if world > 1:
-        # NCCL prints its version banner on stdout when NCCL_DEBUG=VERSION/INFO; the
-        # contract is ONE JSON line there
+        # NCCL's log (version banner included) belongs on stderr; protect_stdout() is the backstop
         os.environ["NCCL_DEBUG"] = os.environ.get("GFX_NCCL_DEBUG", "WARN")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device(device))
 
     def barrier():
@@ -440,7 +462,7 @@ def main() -> None:
                 "value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                 "sample": f"first {sub.record_count} records ({sub.node_count} nt) of the same "
                           f"shard, fp16 model, {secs:.1f} s of CPU work"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -149,3 +149,30 @@ def test_shard_prefetcher_order_errors_and_overlap():
             got.append(path)
     assert got == paths[:2]
     assert list(ShardPrefetcher([], pin=False, load=load)) == []
+
+
+def test_bench_keeps_stdout_to_one_json_line():
+    """bench.py's contract is ONE JSON line on stdout; NCCL writes its version banner to file
+    descriptor 1 at every NCCL_DEBUG level from VERSION up.  protect_stdout() points fd 1 at stderr
+    and emit() writes the line to a private copy of the original stdout."""
+    import json
+    import subprocess
+    import sys
+    import textwrap
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    code = textwrap.dedent('''
+        import importlib.util, os, sys
+        spec = importlib.util.spec_from_file_location("bench", "bench.py")
+        bench = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(bench)
+        bench.protect_stdout()
+        os.write(1, b"NCCL version 2.28.9+cuda12.9\\n")     # what a C library does
+        print("a stray Python print")
+        bench.emit({"metric": "m", "value": 1.5})
+    ''')
+    run = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=root)
+    assert run.returncode == 0, run.stderr
+    assert json.loads(run.stdout) == {"metric": "m", "value": 1.5}
+    assert run.stdout.count("\n") == 1
+    assert "NCCL version" in run.stderr and "stray" in run.stderr
