@@ -271,6 +271,12 @@ int gfx_head_l2norm(const gfx_model *model, const void *h,
  * Whole forward over one packed chunk of graphs (all stages above in
  * order).  Replaces Ginfinity._run_graph_shard's device work
  * (api.py:236-252).  workspace holds the activation ping-pong buffers.
+ * `impl`: GFX_IMPL_* for the dense stages.  `fused` (GFX_F16 only) selects the
+ * layer kernel: 0 = K1 + K2 (gfx_aggregate, gfx_mlp_ln_residual), 1 =
+ * gfx_layer_fused, 2 = gfx_layer_fused_pair, 3 = gfx_row_describe once +
+ * gfx_layer_fused_banded per layer (descriptors live in the z buffer, which the
+ * fused forms do not use); a form that does not cover the call (edge types,
+ * node count) falls back to the next lower one that does.
  * ------------------------------------------------------------------------ */
 size_t gfx_encode_workspace_bytes(int64_t num_nodes, int dtype);
 int gfx_encode(const gfx_model *model, const float *x, const int32_t *row_ptr,
