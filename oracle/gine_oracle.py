@@ -153,6 +153,44 @@ def csr_by_destination(edge_index, edge_types, num_nodes):
 
 
 # --------------------------------------------------------------------------
+# Row descriptors of the banded fused layer (include/gfx.h: gfx_row_describe).
+# The PREMISE restated here is the reference's: GraphBuilder._build_full
+# (graph.py:494-561) lists backbone fwd, backbone rev, pairs fwd, pairs rev, then
+# skip-2 fwd/rev interleaved, so after the stable sort by destination the row of
+# nucleotide i reads (i-1, 0) (i+1, 1) [(partner, 2|3)] (i-2, 4) (i+2, 5).
+# --------------------------------------------------------------------------
+DESC_PREV, DESC_NEXT, DESC_PAIR, DESC_PAIR_REV, DESC_PREV2, DESC_NEXT2 = 1, 2, 4, 8, 16, 32
+DESC_GENERIC, DESC_PARTNER_SHIFT, DESC_PARTNER_BITS = 0x80000000, 6, 25
+
+
+def describe_rows(row_ptr, col_src, col_type):
+    """uint32 descriptor per CSR row: which of the five pattern edges the row holds (each
+    optional, in that order), pair type and partner index; GENERIC for any other row."""
+    n = len(row_ptr) - 1
+    out = np.zeros(n, dtype=np.uint32)
+    for i in range(n):
+        k, end, d = int(row_ptr[i]), int(row_ptr[i + 1]), 0
+
+        def at(src, typ):
+            return k < end and col_src[k] == src and col_type[k] == typ
+
+        if at(i - 1, 0):
+            d |= DESC_PREV; k += 1
+        if at(i + 1, 1):
+            d |= DESC_NEXT; k += 1
+        if k < end and col_type[k] in (2, 3) and 0 <= col_src[k] < (1 << DESC_PARTNER_BITS):
+            d |= DESC_PAIR | (DESC_PAIR_REV if col_type[k] == 3 else 0)
+            d |= int(col_src[k]) << DESC_PARTNER_SHIFT
+            k += 1
+        if at(i - 2, 4):
+            d |= DESC_PREV2; k += 1
+        if at(i + 2, 5):
+            d |= DESC_NEXT2; k += 1
+        out[i] = d if k == end else DESC_GENERIC
+    return out
+
+
+# --------------------------------------------------------------------------
 # encoder forward, literal form  (src/ginfinity/_model.py:39-46, 65-72)
 # --------------------------------------------------------------------------
 def forward_literal(state, x, edge_index, edge_types, *, layers=4, edge_dim=10,

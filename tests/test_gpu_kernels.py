@@ -384,22 +384,7 @@ def test_fused_pair_layer_ragged_sizes(nat, dev, problem, seed, count):
 
 
 def _describe_rows(rp, cs, ct):
-    """NumPy restatement of gfx_row_describe (include/gfx.h): per row, the reference builder's
-    edge order (graph.py:494-561) with every edge optional, else GENERIC."""
-    n = len(rp) - 1
-    out = np.zeros(n, dtype=np.uint32)
-    for i in range(n):
-        k, end, d = int(rp[i]), int(rp[i + 1]), 0
-        def at(src, typ):
-            return k < end and cs[k] == src and ct[k] == typ
-        if at(i - 1, 0): d |= 1; k += 1
-        if at(i + 1, 1): d |= 2; k += 1
-        if k < end and ct[k] in (2, 3) and 0 <= cs[k] < (1 << 25):
-            d |= 4 | (8 if ct[k] == 3 else 0) | (int(cs[k]) << 6); k += 1
-        if at(i - 2, 4): d |= 16; k += 1
-        if at(i + 2, 5): d |= 32; k += 1
-        out[i] = d if k == end else 0x80000000
-    return out
+    return O.describe_rows(rp, cs, ct)     # oracle/gine_oracle.py: the restatement gfx_row_describe is checked against
 
 
 def _device_describe(nat, dev, rp, cs, ct, n):

@@ -115,6 +115,45 @@ def test_oracle_windows_match_reference(real_state, golden_meta, golden_graphs, 
         assert np.abs(got - golden_embeddings[p + "/fp32_model_f32"]).max() <= 2e-6
 
 
+def test_reference_graphs_are_banded_in_the_order_the_fused_layer_expects(golden_meta, golden_graphs):
+    """The banded fused layer (gfx_row_describe / gfx_layer_fused_banded) relies on the edge order
+    of the reference's builder.  Checked on the arrays the REFERENCE itself produced
+    (tests/golden/golden_graphs.npz): in full-molecule graphs every row matches the pattern (no
+    GENERIC row), interior nucleotides carry all four backbone / skip-2 neighbours, partners are
+    mutual; a plain window (a contiguous stretch of the molecule) is banded as well, and every
+    descriptor of the context-node windows still accounts for the row's exact degree or is GENERIC."""
+    ei, et = golden_graphs["full/edge_index"], golden_graphs["full/edge_types"]
+    node_ptr = golden_graphs["full/node_ptr"]
+    n = int(node_ptr[-1])
+    rp, cs, ct = O.csr_by_destination(ei, et, n)
+    d = O.describe_rows(rp, cs, ct)
+    assert not (d & O.DESC_GENERIC).any()
+    backbone = O.DESC_PREV | O.DESC_NEXT | O.DESC_PREV2 | O.DESC_NEXT2
+    interior = np.zeros(n, dtype=bool)
+    for a, b in zip(node_ptr[:-1], node_ptr[1:]):
+        interior[int(a) + 2:int(b) - 2] = True
+    assert ((d[interior] & backbone) == backbone).all()
+    first = node_ptr[:-1][np.diff(node_ptr) >= 3].astype(int)
+    assert ((d[first] & backbone) == (O.DESC_NEXT | O.DESC_NEXT2)).all()      # 5' ends
+    paired = np.nonzero(d & O.DESC_PAIR)[0]
+    partner = (d[paired] >> O.DESC_PARTNER_SHIFT) & ((1 << O.DESC_PARTNER_BITS) - 1)
+    assert np.array_equal((d[partner] >> O.DESC_PARTNER_SHIFT) & ((1 << O.DESC_PARTNER_BITS) - 1), paired)
+    assert (((d[paired] & O.DESC_PAIR_REV) != 0) == (partner > paired)).all()   # close -> open edges reach the opening base
+    # degree implied by the descriptor == CSR degree
+    bits = sum(((d >> k) & 1).astype(np.int64) for k in (0, 1, 2, 4, 5))
+    assert np.array_equal(bits, np.diff(rp))
+    for k, w in enumerate(golden_meta["windows"]):
+        ei, et = golden_graphs[f"window{k}/edge_index"], golden_graphs[f"window{k}/edge_types"]
+        m = int(golden_graphs[f"window{k}/node_ptr"][-1])
+        wrp, wcs, wct = O.csr_by_destination(ei, et, m)
+        dw = O.describe_rows(wrp, wcs, wct)
+        generic = (dw & O.DESC_GENERIC) != 0
+        if not w["keep"]:
+            assert not generic.any()
+        bits = sum(((dw >> b) & 1).astype(np.int64) for b in (0, 1, 2, 4, 5))
+        assert np.array_equal(bits[~generic], np.diff(wrp)[~generic])
+
+
 def test_csr_is_a_stable_sort():
     rng = np.random.default_rng(0)
     ei = rng.integers(0, 50, (2, 400)).astype(np.int32)
