@@ -47,8 +47,9 @@ from .weights import (BUNDLED_CONFIG, EncoderConfig, FoldedWeights,
 
 DEFAULT_CHUNK_NODES = 1 << 20
 # device-resident shards have no copy pipeline to keep fine-grained: larger chunks amortise the
-# fill and drain of the persistent layer kernel (measured: 2^20 -> 675, 2^21 -> 699 M nt/s)
-RESIDENT_CHUNK_NODES = 1 << 21
+# fill and drain of the persistent layer kernel (measured: 2^20 -> 675, 2^21 -> 699 M nt/s with
+# the pair kernel; 2^21 -> 708, 2^22 -> 740, 2^23 -> 739 with the banded kernel)
+RESIDENT_CHUNK_NODES = 1 << 22
 _LAYER_KERNEL_CHOICE = {}          # device index -> (gfx_encode `fused` mode, {mode: ms})
 
 
