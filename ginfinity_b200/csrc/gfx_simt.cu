@@ -636,6 +636,8 @@ int umma4_mlp_ln_residual(const gfx_model *m, int layer, const __half *z, const 
                           int64_t n, __half *h_out, cudaStream_t st);
 int umma7_mlp_ln_residual(const gfx_model *m, int layer, const __half *z, const __half *h,
                           int64_t n, __half *h_out, cudaStream_t st);
+// implemented in gfx_head8.cu: fp16 in, fp16 out, identity row map
+int head8_l2norm(const gfx_model *m, const __half *h, int64_t n, __half *out, cudaStream_t st);
 
 }  // namespace gfx
 
@@ -753,6 +755,11 @@ extern "C" int gfx_head_l2norm(const gfx_model *m, const void *h, const int32_t 
     return fail(GFX_ERR_ARGUMENT, "gfx_head_l2norm: unknown out_dtype");
   cudaStream_t st = as_stream(stream);
   StageScope scope(GFX_STAGE_HEAD, st, 1);
+  // the common case -- fp16 model, fp16 embeddings, every node a core node -- has its own kernel
+  // with TMA tile I/O (gfx_head8.cu); GFX_IMPL_UMMA pins the general tcgen05 kernel (cross-check)
+  if (impl == GFX_IMPL_AUTO && dtype == GFX_F16 && out_dtype == GFX_F16 && out_row == nullptr &&
+      n <= (int64_t(1) << 30) && !((reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(out)) & 15))
+    return head8_l2norm(m, static_cast<const __half *>(h), n, static_cast<__half *>(out), st);
   if (impl == GFX_IMPL_AUTO) impl = dtype == GFX_F16 ? GFX_IMPL_UMMA : GFX_IMPL_SIMT;
   if (impl == GFX_IMPL_UMMA_TMA || impl == GFX_IMPL_UMMA_LEAN || impl == GFX_IMPL_UMMA_STREAM ||
       impl == GFX_IMPL_UMMA_PAIR)

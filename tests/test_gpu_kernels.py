@@ -313,7 +313,7 @@ def test_mlp_layernorm_residual_layer0(nat, dev, problem, code, impl):
     assert err <= (2e-5 if code == 1 else 4e-3) * scale, (err, scale)
 
 
-@pytest.mark.parametrize("code,impl,out_code", [(1, 1, 1), (0, 1, 0), (0, 2, 0), (0, 2, 1), (0, 3, 0)])
+@pytest.mark.parametrize("code,impl,out_code", [(1, 1, 1), (0, 1, 0), (0, 2, 0), (0, 2, 1), (0, 3, 0), (0, 0, 0), (0, 0, 1)])
 def test_head_l2norm(nat, dev, problem, code, impl, out_code):
     keep = problem["keep32" if code == 1 else "keep16"]
     y = problem["y32" if code == 1 else "y16"]
@@ -330,6 +330,23 @@ def test_head_l2norm(nat, dev, problem, code, impl, out_code):
     assert np.abs(got - want).max() <= tol
     assert np.abs(np.linalg.norm(got.astype(np.float64), axis=1) - 1).max() <= (
         1e-5 if out_code == 1 else 2e-3)
+
+
+@pytest.mark.parametrize("n", [1, 127, 129, 128 * 148 * 4 + 128 * 2 + 77, 128 * 148 * 9 + 5])
+def test_head_tma_kernel_against_the_general_one(nat, dev, problem, n):
+    """The TMA head (impl 0: fp16 in / fp16 out / no row map, gfx_head8.cu) against the general tcgen05
+    head (impl 2) beyond one wave: more than four tiles per CTA (every stage buffer reused, both
+    barrier parities), partly filled last tile, rows past n untouched, unit norms."""
+    g = torch.Generator(device="cpu").manual_seed(n)
+    h = (torch.randn(n, 128, generator=g) * 2).to(dev).half()
+    want = torch.empty((n, 128), dtype=torch.float16, device=dev)
+    got = torch.full((n + 256, 128), 7.0, dtype=torch.float16, device=dev)
+    nat.check(nat.lib.gfx_head_l2norm(problem["handle"], h.data_ptr(), None, n, want.data_ptr(), 0, 0, 2, _stream()))
+    nat.check(nat.lib.gfx_head_l2norm(problem["handle"], h.data_ptr(), None, n, got.data_ptr(), 0, 0, 0, _stream()))
+    torch.cuda.synchronize()
+    assert torch.all(got[n:] == 7.0)
+    assert (got[:n].float() - want.float()).abs().max().item() <= 1e-3
+    assert (got[:n].float().norm(dim=1) - 1).abs().max().item() <= 2e-3
 
 
 @pytest.mark.parametrize("entry", ["gfx_layer_fused", "gfx_layer_fused_pair"])
