@@ -166,3 +166,30 @@ def test_info(capsys):
     assert main(["info"]) == 0
     said = json.loads(capsys.readouterr().out)
     assert said["embedding_dimension"] == 128 and len(said["checkpoint_sha256"]) == 64
+
+
+@pytest.mark.gpu
+def test_embed_writes_one_array_per_window_and_no_slices_ignores_them(tmp_path):
+    """tests/test_sliced_graphs.py:205-243 of the reference: comma-separated windows become one
+    archive entry each (context nodes are computed but not returned); --no-slices encodes the
+    whole molecule under the plain identifier."""
+    _needs_gpu_and_model()
+    sequence, structure = "GGGAAACCCUUUUGGG", "......(((....)))"
+    source = tmp_path / "molecules.tsv"
+    source.write_text("transcript_id\tsequence\tsecondary_structure\tstart\tend\n"
+                      f"stem\t{sequence}\t{structure}\t9,6\t16,12\n")
+    output, manifest = tmp_path / "embeddings.npz", tmp_path / "manifest.json"
+    assert main(["embed", "--input", str(source), "--output", str(output), "--manifest", str(manifest),
+                 "--keep-paired-neighbours", "--context-hops", "2"]) == 0
+    with np.load(output) as archive:
+        assert set(archive.files) == {"stem:9-16", "stem:6-12"}
+        assert archive["stem:9-16"].shape == (7, 128) and archive["stem:6-12"].shape == (6, 128)
+    rows = {row["identifier"]: row for row in json.loads(manifest.read_text())["records"]}
+    assert (rows["stem:9-16"]["start"], rows["stem:9-16"]["end"], rows["stem:9-16"]["core_length"]) == (9, 16, 7)
+    single = tmp_path / "single.tsv"
+    single.write_text("transcript_id\tsequence\tsecondary_structure\tstart\tend\n"
+                      f"stem\t{sequence}\t{structure}\t9\t16\n")
+    whole = tmp_path / "whole.npz"
+    assert main(["embed", "--input", str(single), "--output", str(whole), "--no-slices"]) == 0
+    with np.load(whole) as archive:
+        assert archive.files == ["stem"] and archive["stem"].shape == (16, 128)
