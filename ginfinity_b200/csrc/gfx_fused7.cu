@@ -19,6 +19,16 @@
 // node and layer), and the sum is taken in CSR order with the same arithmetic as gfx_fused6.cu, so
 // the two kernels agree BIT FOR BIT.  GENERIC rows (sliced windows with context nodes, arbitrary
 // graphs) are recomputed from the CSR arrays by a slow warp-per-row loop after the run.
+//
+// Warps per CTA (24; 80 registers per thread at launch = 61,440 for the CTA, re-balanced with
+// setmaxnreg WITHIN that allocation -- a sum of the per-role limits above it deadlocks in
+// setmaxnreg.inc -- epilogue A 64, epilogue B 80, producers 104, utility warpgroup 40):
+//    0-3   epilogue A   D1 -> + b1, ReLU, fp16 -> A2 (in place)
+//    4-11  epilogue B   two groups of 4, alternating tiles: D2 -> + b2, LayerNorm, + residual,
+//                       in place in the h-tile buffer (the arithmetic of gfx_fused6.cu)
+//   12-19  producers    warp w owns tile rows [16 w, 16 w + 16), two runs of 8 rows
+//   20     MMA issuer (rank 0 issues for the pair; GEMM 1 as 8 MMAs of N = 256), 21 h-tile loader,
+//   22     output store (both TMA)
 #include <cstdlib>
 #include <type_traits>
 
