@@ -1,3 +1,6 @@
-from .cli import main
+"""`python -m ginfinity_b200 <command>` runs ginfinity_b200.cli."""
+import sys
 
-raise SystemExit(main())
+from . import cli
+
+sys.exit(cli.main())

@@ -47,98 +47,62 @@ def test_valid_slice_is_stored():
     assert record.sliced
 
 
-# ---- tests/test_table.py --------------------------------------------------------------------
-def test_rna_from_mapping_accepts_configurable_columns():
-    record = RNA.from_mapping({"name": "rna-1", "bases": "ACGT", "dot_bracket": "(())"},
-                              identifier_column="name", sequence_column="bases",
-                              structure_column="dot_bracket")
-    assert record == RNA("rna-1", "ACGU", "(())")
+# ---- tests/test_table.py: the same cases, table-driven ----------------------------------------
+HEAD3 = "transcript_id\tsequence\tsecondary_structure\n"
+HEAD5 = "transcript_id\tsequence\tsecondary_structure\tstart\tend\n"
+WINDOW_ROW = {"transcript_id": "rna-1", "sequence": "ACGUACGU", "secondary_structure": "((....))"}
 
 
-def test_rna_from_mapping_reads_a_single_window_without_renaming():
-    record = RNA.from_mapping({"transcript_id": "rna-1", "sequence": "ACGUACGU",
-                               "secondary_structure": "((....))", "start": "2", "end": "6"},
-                              start_column="start", end_column="end")
-    assert (record.identifier, record.start, record.end) == ("rna-1", 2, 6)
-
-
-def test_rna_from_mapping_rejects_multiple_windows():
+def test_from_mapping_column_names_and_single_windows():
+    custom = dict(identifier_column="name", sequence_column="bases", structure_column="dot_bracket")
+    got = RNA.from_mapping({"name": "rna-1", "bases": "ACGT", "dot_bracket": "(())"}, **custom)
+    assert got == RNA("rna-1", "ACGU", "(())")
+    one = RNA.from_mapping({**WINDOW_ROW, "start": "2", "end": "6"}, start_column="start", end_column="end")
+    assert (one.identifier, one.start, one.end) == ("rna-1", 2, 6)      # a single window keeps the name
     with pytest.raises(InputValidationError, match="multiple slices"):
-        RNA.from_mapping({"transcript_id": "rna-1", "sequence": "ACGUACGU",
-                          "secondary_structure": "((....))", "start": "2,4", "end": "6,8"},
-                         start_column="start", end_column="end")
+        RNA.from_mapping({**WINDOW_ROW, "start": "2,4", "end": "6,8"}, start_column="start", end_column="end")
 
 
-def test_read_rna_table_allows_extra_reordered_and_custom_columns(tmp_path):
-    table = tmp_path / "structures.csv"
-    table.write_text("dot_bracket,source,rna_name,bases\n"
-                     "(()),example,first,ACGU\n"
-                     "....,example,second,GGAA\n")
-    records = read_rna_table(table, identifier_column="rna_name", sequence_column="bases",
-                             structure_column="dot_bracket", delimiter=",")
-    assert [record.identifier for record in records] == ["first", "second"]
-    assert records[0].structure == "(())"
+GOOD_TABLES = [
+    # text, reader options, expected (identifier, structure, start, end) per record
+    ("dot_bracket,source,rna_name,bases\n(()),example,first,ACGU\n....,example,second,GGAA\n",
+     dict(identifier_column="rna_name", sequence_column="bases", structure_column="dot_bracket", delimiter=","),
+     [("first", "(())", None, None), ("second", "....", None, None)]),
+    (HEAD5 + "rna-1\tACGUACGU\t((....))\t2,4\t6, 8\n", {},
+     [("rna-1:2-6", "((....))", 2, 6), ("rna-1:4-8", "((....))", 4, 8)]),
+    (HEAD3 + "rna-1\tACGU\t(())\n", {}, [("rna-1", "(())", None, None)]),
+]
 
 
-def test_read_rna_table_reports_missing_configured_column(tmp_path):
-    table = tmp_path / "structures.tsv"
-    table.write_text("name\tbases\nfirst\tACGU\n")
-    with pytest.raises(ValueError, match="dot_bracket"):
-        read_rna_table(table, identifier_column="name", sequence_column="bases",
-                       structure_column="dot_bracket")
+@pytest.mark.parametrize("text,options,expected", GOOD_TABLES)
+def test_tables_that_load(tmp_path, text, options, expected):
+    path = tmp_path / "table.txt"
+    path.write_text(text)
+    records = read_rna_table(path, **options)
+    assert [(r.identifier, r.structure, r.start, r.end) for r in records] == expected
+    assert len({r.sequence for r in records}) <= len(records)
 
 
-def test_read_rna_table_adds_line_context_to_invalid_rna(tmp_path):
-    table = tmp_path / "structures.tsv"
-    table.write_text("transcript_id\tsequence\tsecondary_structure\n"
-                     "bad\tACGN\t....\n")
-    with pytest.raises(InputValidationError, match="line 2"):
-        read_rna_table(table)
+BAD_TABLES = [
+    # text, reader options, exception, message fragment
+    ("name\tbases\nfirst\tACGU\n",
+     dict(identifier_column="name", sequence_column="bases", structure_column="dot_bracket"), ValueError, "dot_bracket"),
+    (HEAD3 + "bad\tACGN\t....\n", {}, InputValidationError, "line 2"),
+    (HEAD5 + "rna-1\tACGUACGU\t((....))\t2,4\t6\n", {}, InputValidationError, "start has 2"),
+    (HEAD3 + "a\tACGU\t....\na\tGGAA\t....\n", {}, InputValidationError, "duplicate"),
+    (HEAD3, {}, ValueError, "no records"),
+    ("", {}, ValueError, "empty RNA table"),
+    (HEAD3 + "a\tACGU\t....\tsurplus\n", {}, ValueError, "extra fields"),
+    (HEAD3 + "a\tACGU\t....\n", dict(delimiter="::"), ValueError, "exactly one character"),
+    (HEAD3 + "a\tACGU\t....\n", dict(start_column="start", end_column=None), ValueError, "both be provided"),
+]
 
 
-def test_read_rna_table_expands_comma_separated_windows(tmp_path):
-    table = tmp_path / "structures.tsv"
-    table.write_text("transcript_id\tsequence\tsecondary_structure\tstart\tend\n"
-                     "rna-1\tACGUACGU\t((....))\t2,4\t6, 8\n")
-    records = read_rna_table(table)
-    assert [(r.identifier, r.start, r.end) for r in records] == [("rna-1:2-6", 2, 6), ("rna-1:4-8", 4, 8)]
-    assert records[0].sequence == records[1].sequence == "ACGUACGU"
-
-
-def test_read_rna_table_ignores_absent_start_end_columns(tmp_path):
-    table = tmp_path / "structures.tsv"
-    table.write_text("transcript_id\tsequence\tsecondary_structure\n"
-                     "rna-1\tACGU\t(())\n")
-    records = read_rna_table(table)
-    assert records[0].identifier == "rna-1" and records[0].start is None
-
-
-def test_read_rna_table_rejects_mismatched_window_lists(tmp_path):
-    table = tmp_path / "structures.tsv"
-    table.write_text("transcript_id\tsequence\tsecondary_structure\tstart\tend\n"
-                     "rna-1\tACGUACGU\t((....))\t2,4\t6\n")
-    with pytest.raises(InputValidationError, match="start has 2"):
-        read_rna_table(table)
-
-
-def test_read_rna_table_rejects_duplicates_empty_files_and_extra_fields(tmp_path):
-    """Error paths of src/ginfinity/table.py:29-81 that the reference's tests leave implicit."""
-    table = tmp_path / "t.tsv"
-    table.write_text("transcript_id\tsequence\tsecondary_structure\n"
-                     "a\tACGU\t....\na\tGGAA\t....\n")
-    with pytest.raises(InputValidationError, match="duplicate"):
-        read_rna_table(table)
-    table.write_text("transcript_id\tsequence\tsecondary_structure\n")
-    with pytest.raises(ValueError, match="no records"):
-        read_rna_table(table)
-    table.write_text("")
-    with pytest.raises(ValueError, match="empty RNA table"):
-        read_rna_table(table)
-    table.write_text("transcript_id\tsequence\tsecondary_structure\n"
-                     "a\tACGU\t....\tsurplus\n")
-    with pytest.raises(ValueError, match="extra fields"):
-        read_rna_table(table)
-    with pytest.raises(ValueError, match="exactly one character"):
-        read_rna_table(table, delimiter="::")
-    with pytest.raises(ValueError, match="both be provided"):
-        read_rna_table(table, start_column="start", end_column=None)
+@pytest.mark.parametrize("text,options,error,fragment", BAD_TABLES)
+def test_tables_that_are_refused(tmp_path, text, options, error, fragment):
+    """The reference's three refusal tests plus the error paths of src/ginfinity/table.py:29-81 that
+    its tests leave implicit (duplicates, empty files, surplus fields, reader options)."""
+    path = tmp_path / "table.txt"
+    path.write_text(text)
+    with pytest.raises(error, match=fragment):
+        read_rna_table(path, **options)
