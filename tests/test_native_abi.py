@@ -49,6 +49,10 @@ def test_library_is_sm_100a_and_uses_the_blackwell_units():
     assert "LDTM" in sass             # tcgen05.ld
     assert "UBLKCP" in sass           # bulk async copy (TMA engine)
     assert "HMMA." not in sass.replace("UTCHMMA", "")   # no legacy mma.sync path
+    assert "UTMALDG.2D" in sass and "UTMASTG.2D" in sass   # 2-D tiled TMA loads and stores
+    assert "UTCHMMA.2CTA" in sass      # tcgen05.mma.cta_group::2 (fused layer on CTA pairs)
+    assert "UTCBAR.2CTA.MULTICAST" in sass   # tcgen05.commit multicast to both CTAs of a pair
+    assert "STTM" in sass              # tcgen05.st: the hidden activation goes back into TMEM
 
 
 def test_argument_errors_surface_through_gfx_last_error(nat):
