@@ -51,6 +51,7 @@ _SIGNATURES = {
     "gfx_pack_microbatches": (C.c_int, [_p, _p, _i64, _i64, _i64, _p, _p, _p, _p]),
     "gfx_csr_workspace_bytes": (_sz, [_i64, _i64]),
     "gfx_csr_build": (C.c_int, [_p, _p, _p, _i64, _i64, _i32, _p, _p, _p, _p, _sz, _p]),
+    "gfx_csr_build_checked": (C.c_int, [_p, _p, _p, _i64, _i64, _i32, _p, _p, _p, _p, _p, _sz, _p]),
     "gfx_graph_workspace_bytes": (_sz, [_i64, _i64]),
     "gfx_graph_count": (C.c_int, [_p, _p, _i64, _i64, C.c_int, _p, _p, _p, _sz, _p]),
     "gfx_graph_fill": (C.c_int, [_p, _p, _p, _p, _i64, _i64, _i64, C.c_int, _p, _p, _p, _p, _p,

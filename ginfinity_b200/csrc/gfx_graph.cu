@@ -160,18 +160,32 @@ __global__ void pack_chase_kernel(const int64_t *__restrict__ next_stop, int64_t
 // ---------------------------------------------------------------------------
 constexpr int kSmallRow = 32;
 
-__global__ void csr_count_kernel(const int32_t *__restrict__ dst, int64_t E, int32_t base,
-                                 int *__restrict__ deg) {
-  for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < E;
-       e += int64_t(gridDim.x) * blockDim.x)
-    atomicAdd(&deg[dst[e] - base], 1);
+// An edge whose endpoints do not both lie in [base, base + N) is DROPPED (it would index past the
+// chunk's arrays) and reported through *status; the reference rejects such a shard when it slices
+// it (graph.py:328-330 via GraphShard.slice, "edge index outside shard node range").
+__device__ __forceinline__ bool edge_in_range(int32_t s, int32_t d, int32_t base, uint32_t N) {
+  return uint32_t(s - base) < N && uint32_t(d - base) < N;
 }
 
-__global__ void csr_scatter_kernel(const int32_t *__restrict__ dst, int64_t E, int32_t base,
+__global__ void csr_count_kernel(const int32_t *__restrict__ src, const int32_t *__restrict__ dst,
+                                 int64_t E, int32_t base, uint32_t N, int *__restrict__ deg,
+                                 int32_t *__restrict__ status) {
+  bool bad = false;
+  for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < E;
+       e += int64_t(gridDim.x) * blockDim.x) {
+    const int32_t d = dst[e];
+    if (edge_in_range(src[e], d, base, N)) atomicAdd(&deg[d - base], 1); else bad = true;
+  }
+  if (bad) atomicOr(status, GFX_GRAPH_BAD_EDGE);
+}
+
+__global__ void csr_scatter_kernel(const int32_t *__restrict__ src, const int32_t *__restrict__ dst,
+                                   int64_t E, int32_t base, uint32_t N,
                                    const int32_t *__restrict__ row_ptr, int *__restrict__ cursor,
                                    int32_t *__restrict__ eid) {
   for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < E;
        e += int64_t(gridDim.x) * blockDim.x) {
+    if (!edge_in_range(src[e], dst[e], base, N)) continue;
     int d = dst[e] - base;
     int slot = atomicAdd(&cursor[d], 1);
     eid[row_ptr[d] + slot] = int32_t(e);
@@ -265,7 +279,7 @@ extern "C" int gfx_pack_microbatches(const int64_t *node_ptr, const int64_t *edg
   return GFX_OK;
 }
 
-// workspace layout: deg/cursor int[N+1] | eid int[E] | block_sums | big_rows int[N] | n_big
+// workspace layout: deg/cursor int[N+1] | eid int[E] | block_sums | big_rows int[N] | n_big, status
 extern "C" size_t gfx_csr_workspace_bytes(int64_t N, int64_t E) {
   return align256(size_t(N + 1) * 4) + align256(size_t(E) * 4) +
          align256(size_t(scan_blocks(N + 1) + 1) * 4) + align256(size_t(N) * 4) + 256;
@@ -275,6 +289,15 @@ extern "C" int gfx_csr_build(const int32_t *edge_src, const int32_t *edge_dst,
                              const uint8_t *edge_type, int64_t N, int64_t E, int32_t node_base,
                              int32_t *row_ptr, int32_t *col_src, uint8_t *col_type, void *ws,
                              size_t ws_bytes, void *stream) {
+  return gfx_csr_build_checked(edge_src, edge_dst, edge_type, N, E, node_base, row_ptr, col_src,
+                               col_type, nullptr, ws, ws_bytes, stream);
+}
+
+extern "C" int gfx_csr_build_checked(const int32_t *edge_src, const int32_t *edge_dst,
+                                     const uint8_t *edge_type, int64_t N, int64_t E,
+                                     int32_t node_base, int32_t *row_ptr, int32_t *col_src,
+                                     uint8_t *col_type, int32_t *status, void *ws,
+                                     size_t ws_bytes, void *stream) {
   if (N < 0 || E < 0 || N >= (int64_t(1) << 31) - 1 || E >= (int64_t(1) << 31) - 1)
     return fail(GFX_ERR_ARGUMENT, "gfx_csr_build: sizes must fit int32");
   if (ws_bytes < gfx_csr_workspace_bytes(N, E))
@@ -286,10 +309,13 @@ extern "C" int gfx_csr_build(const int32_t *edge_src, const int32_t *edge_dst,
   int *sums = reinterpret_cast<int *>(p); p += align256(size_t(scan_blocks(N + 1) + 1) * 4);
   int32_t *big_rows = reinterpret_cast<int32_t *>(p); p += align256(size_t(N) * 4);
   int *n_big = reinterpret_cast<int *>(p);
+  if (status == nullptr) status = n_big + 1;     // unobserved: bad edges are still dropped
   StageScope scope(GFX_STAGE_CSR, st, (E > 0 ? 1 : 0) + 3 + ((N == 0 || E == 0) ? 0 : 3));
   GFX_CUDA(cudaMemsetAsync(deg, 0, size_t(N + 1) * 4, st));
-  GFX_CUDA(cudaMemsetAsync(n_big, 0, 4, st));
-  if (E > 0) csr_count_kernel<<<grid_for(E, 256), 256, 0, st>>>(edge_dst, E, node_base, deg);
+  GFX_CUDA(cudaMemsetAsync(n_big, 0, 8, st));
+  if (E > 0)
+    csr_count_kernel<<<grid_for(E, 256), 256, 0, st>>>(edge_src, edge_dst, E, node_base,
+                                                       uint32_t(N), deg, status);
   int rc = exclusive_scan(deg, row_ptr, N + 1, sums, nullptr, st);
   if (rc) return rc;
   if (N == 0 || E == 0) {
@@ -297,7 +323,8 @@ extern "C" int gfx_csr_build(const int32_t *edge_src, const int32_t *edge_dst,
     return GFX_OK;
   }
   GFX_CUDA(cudaMemsetAsync(deg, 0, size_t(N + 1) * 4, st));  // reuse as cursor
-  csr_scatter_kernel<<<grid_for(E, 256), 256, 0, st>>>(edge_dst, E, node_base, row_ptr, deg, eid);
+  csr_scatter_kernel<<<grid_for(E, 256), 256, 0, st>>>(edge_src, edge_dst, E, node_base,
+                                                       uint32_t(N), row_ptr, deg, eid);
   csr_place_kernel<<<grid_for(N, 256), 256, 0, st>>>(edge_src, edge_type, node_base, row_ptr, eid,
                                                      N, col_src, col_type, big_rows, n_big);
   csr_place_big_kernel<<<kNumSMs, 256, 0, st>>>(edge_src, edge_type, node_base, row_ptr, eid,

@@ -156,6 +156,7 @@ def build_device_shard(records: Sequence, device, spec: GraphSpec = None,
                         core_count=N, spec=spec, core_ptr_host=node_ptr)
     shard.residue_index, shard.node_roles_full = residue, roles
     shard.edge_ptr_host = edge_ptr
+    shard.edges_checked = True          # built here: every edge stays inside its record
     return shard
 
 
@@ -235,4 +236,5 @@ def _build_sliced(records: list, device, spec: GraphSpec, keep_paired: bool,
                         core_count=int(core_ptr[-1]), spec=spec, core_ptr_host=core_ptr)
     shard.residue_index, shard.node_roles_full = residue, roles
     shard.node_ptr_host, shard.edge_ptr_host = node_ptr, edge_ptr
+    shard.edges_checked = True
     return shard

@@ -25,7 +25,14 @@ Deviations from the reference, all deliberate:
     floating point), so `allow_nondeterministic_cuda` is accepted but not
     required (reference: api.py:71-74);
   * microbatch boundaries do not change any output bit (graphs never
-    interact), so chunks of several microbatches are launched together.
+    interact), so chunks of several microbatches are launched together; a
+    chunk holds at most CHUNK_MICROBATCHES x max_batch_nodes nodes, so
+    lowering `max_batch_nodes` still lowers device memory in proportion
+    (reference docs/OPERATIONS.md:25-27);
+  * `encode_graphs(..., out=table)` writes into a caller-owned
+    [core_count, 128] table (ideally page-locked, see `pinned_table`) and
+    returns row-range views of it: a caller that keeps every result pays
+    the page-locking cost once, not per call.
 """
 from __future__ import annotations
 
@@ -50,6 +57,11 @@ DEFAULT_CHUNK_NODES = 1 << 20
 # fill and drain of the persistent layer kernel (measured: 2^20 -> 675, 2^21 -> 699 M nt/s with
 # the pair kernel; 2^21 -> 708, 2^22 -> 740, 2^23 -> 739 with the banded kernel)
 RESIDENT_CHUNK_NODES = 1 << 22
+# a chunk never holds more than this many microbatches' worth of nodes (16 x the default 60,000
+# is just under 2^20): device scratch scales with max_batch_nodes when the caller lowers it
+CHUNK_MICROBATCHES = 16
+RESIDENT_CHUNK_MICROBATCHES = 64
+GFX_GRAPH_BAD_EDGE = 16            # include/gfx.h
 _LAYER_KERNEL_CHOICE = {}          # device index -> (gfx_encode `fused` mode, {mode: ms})
 
 
@@ -76,8 +88,37 @@ def default_alignment_parameters(model_dir=None) -> dict:
     return dict(data["scoring_parameters"])
 
 
+def _check_architecture(cfg: EncoderConfig) -> None:
+    """The kernels implement ONE architecture: h + LayerNorm(...) residual layers
+    (_model.py:68-71 with cfg.residual), 7 node features (struct_feature "A",
+    positional), hidden = out_dim = 128.  A checkpoint whose config says otherwise
+    passes the reference's own checks and would be computed WRONGLY here, so it is
+    refused (the reference honours the flags, _model.py:52-60)."""
+    problems = []
+    if not cfg.residual:
+        problems.append("residual=False")
+    if cfg.struct_feature != "A" or not cfg.positional:
+        problems.append(f"struct_feature={cfg.struct_feature!r}, positional={cfg.positional}")
+    if cfg.hidden != 128 or cfg.out_dim != 128:
+        problems.append(f"hidden={cfg.hidden}, out_dim={cfg.out_dim}")
+    if problems:
+        raise ModelIntegrityError(
+            "unsupported encoder architecture for the sm_100a kernels: " + "; ".join(problems))
+
+
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
+
+
+def _as_host_table(out, dtype: np.dtype) -> torch.Tensor:
+    """`encode_graphs(out=...)`: a CPU torch view of a caller-owned table."""
+    t = torch.from_numpy(out) if isinstance(out, np.ndarray) else out
+    if not isinstance(t, torch.Tensor) or t.device.type != "cpu":
+        raise ValueError("`out` must be a NumPy array or a CPU torch tensor")
+    want = torch.float16 if dtype == np.float16 else torch.float32
+    if t.dtype != want or t.dim() != 2 or t.shape[1] != 128 or not t.is_contiguous():
+        raise ValueError(f"`out` must be a C-contiguous [rows, 128] table of {dtype}")
+    return t
 
 
 class DeviceShard:
@@ -102,6 +143,9 @@ class DeviceShard:
         self.core_count = int(core_count)
         self.spec = spec
         self.core_ptr_host = core_ptr_host
+        # set once the shard's edges are known to stay inside their chunks (shards from the
+        # device builder are; others are checked by the first encode_device_shard)
+        self.edges_checked = False
 
     @property
     def device(self):
@@ -154,6 +198,7 @@ class Ginfinity:
 
     def __init__(self, weights: FoldedWeights, metadata: dict, device: str,
                  graph_spec: GraphSpec, *, full_precision: bool):
+        _check_architecture(weights.cfg)
         self._weights = weights
         self._metadata = metadata
         self._graph_spec = graph_spec
@@ -168,14 +213,16 @@ class Ginfinity:
         # dense-stage implementation: 0 auto (tcgen05 for fp16), 1 SIMT
         self.impl = nat.IMPL_AUTO
         # layer kernels: 3 = fused layer on CTA pairs with banded producers, 2 = fused layer on CTA
-        # pairs with CSR-walking producers (gfx_encode falls back where a kernel does not apply),
-        # 0 = K1 + K2, 1 = fused layer with one CTA per SM.  Which of 3, 2
-        # and 0 is faster differs from one B200 to the next (measured on this pool: 690 vs 620
-        # M nt/s on some boards, 607 vs 702 on others), so by default (-1) both are timed once
-        # per device on a fixed synthetic chunk before the first encode and the faster one is
-        # kept (_choose_layer_kernel).  Both pass the same parity tests; GFX_FUSED pins the choice.
-        self.fused = 0 if full_precision else int(os.environ.get("GFX_FUSED", "-1"))
-        self.layer_kernel_times = None    # {2: ms, 0: ms} of the tuning chunk, once chosen
+        # pairs with CSR-walking producers (bit-identical to 3; gfx_encode falls back where a
+        # kernel does not apply), 0 = K1 + K2.  The default is FIXED (3, with 2 for shards that
+        # hold context nodes): every process, rank and run computes with the same kernels, so an
+        # input encodes to the same bits fleet-wide.  K1 + K2 agree with the fused forms only to
+        # fp16 rounding (2e-3), so timing-based selection between them is opt-in:
+        # GFX_FUSED=auto times the forms once per device (_choose_layer_kernel); GFX_FUSED=0|2|3
+        # pins one.
+        env = os.environ.get("GFX_FUSED", "3")
+        self.fused = 0 if full_precision else (-1 if env in ("auto", "-1") else int(env))
+        self.layer_kernel_times = None    # {mode: ms} of the tuning chunk (GFX_FUSED=auto only)
         self.chunk_nodes = DEFAULT_CHUNK_NODES
         self.resident_chunk_nodes = RESIDENT_CHUNK_NODES
         self.device_builder = True       # encode_many builds full-molecule graphs on the GPU
@@ -262,6 +309,8 @@ class Ginfinity:
         records = list(records)
         if not records:
             return []
+        if context_hops < 1:                       # GraphBuilder.__init__ (graph.py:476-477)
+            raise ValueError("context_hops must be >= 1")
         from . import device_builder
         if self.device_builder and device_builder.supports(self._graph_spec, records):
             if device_builder.any_sliced(records):
@@ -304,7 +353,9 @@ class Ginfinity:
         graph) with the banded fused kernel, the fused pair kernel and K1 + K2, timed with CUDA
         events, and keep the fastest.  The choice never depends on user data, so every encoder of a process on a given
         GPU computes with the same kernels."""
-        key = self._torch_device.index or 0
+        key = self._torch_device.index
+        if key is None:
+            key = torch.cuda.current_device()
         if key not in _LAYER_KERNEL_CHOICE:
             _LAYER_KERNEL_CHOICE[key] = self._measure_layer_kernels()
         self.fused, self.layer_kernel_times = _LAYER_KERNEL_CHOICE[key]
@@ -380,9 +431,16 @@ class Ginfinity:
 
     def encode_graphs(self, graphs, *, max_batch_nodes: int = 60_000,
                       max_batch_edges: int = 300_000,
-                      embedding_dtype=np.float16) -> list:
+                      embedding_dtype=np.float16, out=None) -> list:
         """Encode prebuilt graphs; one (core_count_i, 128) array per record,
-        in input order."""
+        in input order.
+
+        `out` (extension; the reference always allocates): a caller-owned
+        C-contiguous [total core nodes, 128] table of `embedding_dtype`
+        (float16 or float32; NumPy array or CPU torch tensor, ideally
+        page-locked: `Ginfinity.pinned_table`).  The embeddings are written
+        into it and the returned per-record arrays are row-range views of it,
+        so keeping results costs no allocation inside the call."""
         if isinstance(graphs, GraphShard):
             shard = graphs
         else:
@@ -397,13 +455,27 @@ class Ginfinity:
                                     int(ecounts.max()), max_batch_nodes,
                                     max_batch_edges, embedding_dtype)
         out_code = nat.GFX_F16 if dtype == np.float16 else nat.GFX_F32
+        host = None
+        if out is not None:
+            if dtype.itemsize > 4:
+                raise ValueError("`out` tables must be float16 or float32")
+            host = _as_host_table(out, dtype)
         with torch.cuda.device(self._torch_device), torch.inference_mode():
             table, core_ptr, rows = self._encode_streaming(
                 shard, int(max_batch_nodes), int(max_batch_edges), out_code,
-                presplit=(dtype.itemsize <= 4))
+                presplit=(dtype.itemsize <= 4), host=host)
         if table.dtype != dtype:
             return split_rows(table.astype(dtype), core_ptr)
         return rows
+
+    @staticmethod
+    def pinned_table(rows: int, dtype=np.float16) -> np.ndarray:
+        """A page-locked [rows, 128] table for `encode_graphs(..., out=)`.
+        Page-locking costs ~0.6 s per GiB (measured, profiles/r01_b_pcie.json):
+        allocate once and reuse, or keep a ring of them."""
+        tdtype = torch.float16 if np.dtype(dtype) == np.float16 else torch.float32
+        t = torch.empty((int(rows), 128), dtype=tdtype, pin_memory=True)
+        return t.numpy()
 
     # -- host shard -> host embeddings, copies overlapped with compute -----------
     def _plan(self, node_ptr_d, edge_ptr_d, B, max_batch_nodes, max_batch_edges,
@@ -424,22 +496,42 @@ class Ginfinity:
         self.last_microbatch_bounds = plan[0].copy()
         return plan
 
-    def _chunks(self, plan: np.ndarray) -> list:
+    def _chunk_limit(self, max_batch_nodes: int, resident: bool = False) -> int:
+        """Nodes per device chunk: the encoder's chunk size, but never more than
+        CHUNK_MICROBATCHES microbatches' worth, so that lowering `max_batch_nodes`
+        (the reference's memory knob, docs/OPERATIONS.md:25-27) lowers device
+        scratch in proportion."""
+        if resident:
+            return min(max(self.chunk_nodes, self.resident_chunk_nodes),
+                       RESIDENT_CHUNK_MICROBATCHES * int(max_batch_nodes))
+        return min(self.chunk_nodes, CHUNK_MICROBATCHES * int(max_batch_nodes))
+
+    def _chunks(self, plan: np.ndarray, limit: int) -> list:
         """Group consecutive microbatches into device chunks of at most
-        `chunk_nodes` nodes (always at least one microbatch)."""
+        `limit` nodes (always at least one microbatch)."""
         node_at, count = plan[1], plan.shape[1]
         out, start = [], 0
         while start < count - 1:
             stop = start + 1
             while (stop < count - 1 and
-                   node_at[stop + 1] - node_at[start] <= self.chunk_nodes):
+                   node_at[stop + 1] - node_at[start] <= limit):
                 stop += 1
             out.append((start, stop))
             start = stop
         return out
 
+    def _new_status(self) -> torch.Tensor:
+        """Device int32 that the CSR builds of one encode OR their complaints into."""
+        return torch.zeros(1, dtype=torch.int32, device=self._torch_device)
+
+    @staticmethod
+    def _raise_on_status(value: int) -> None:
+        if value & GFX_GRAPH_BAD_EDGE:
+            from .graph import GraphValidationError
+            raise GraphValidationError("edge index outside shard node range")
+
     def _encode_streaming(self, shard: GraphShard, max_batch_nodes: int,
-                          max_batch_edges: int, out_code: int, presplit=True):
+                          max_batch_edges: int, out_code: int, presplit=True, host=None):
         """Three-stream pipeline over chunks: while chunk c runs on the compute
         stream, chunk c+1's arrays are copied in and chunk c-1's embeddings
         are copied out into one pinned [core_count, 128] table."""
@@ -455,7 +547,13 @@ class Ginfinity:
         else:
             core_ptr = np.zeros(B + 1, np.int64)
             np.cumsum(shard.core_count_array(), out=core_ptr[1:])
-        host = torch.empty((int(core_ptr[-1]), 128), dtype=tdtype, pin_memory=True)
+        if host is None:
+            host = torch.empty((int(core_ptr[-1]), 128), dtype=tdtype, pin_memory=True)
+        elif tuple(host.shape) != (int(core_ptr[-1]), 128):
+            raise ValueError(f"`out` must have shape ({int(core_ptr[-1])}, 128), "
+                             f"got {tuple(host.shape)}")
+        status = self._new_status()
+        status_host = torch.empty(1, dtype=torch.int32, pin_memory=True)
 
         main = torch.cuda.current_stream()
         if not hasattr(self, "_streams"):
@@ -466,7 +564,7 @@ class Ginfinity:
         edge_ptr_d = as_t(shard.edge_ptr).to(dev, non_blocking=True)
         plan = self._plan(node_ptr_d, edge_ptr_d, B, max_batch_nodes,
                           max_batch_edges, main.cuda_stream)
-        chunks = self._chunks(plan)
+        chunks = self._chunks(plan, self._chunk_limit(max_batch_nodes))
         rec_at, node_at, edge_at = plan[0], plan[1], plan[2]
         out_row = None
         if not all_core:
@@ -530,10 +628,10 @@ class Ginfinity:
             main.wait_event(slot["in_ready"])
             if c >= 2:
                 main.wait_event(slot["out_free"])
-            nat.check(lib.gfx_csr_build(
+            nat.check(lib.gfx_csr_build_checked(
                 slot["src"].data_ptr(), slot["dst"].data_ptr(), slot["typ"].data_ptr(),
                 n, e, n0, row_ptr.data_ptr(), col_src.data_ptr(), col_type.data_ptr(),
-                csr_ws.data_ptr(), csr_ws_bytes, main.cuda_stream))
+                status.data_ptr(), csr_ws.data_ptr(), csr_ws_bytes, main.cuda_stream))
             # ranks in out_row are shard-global: bias the base so rank c0 lands on row 0
             out_base = slot["out"].data_ptr() - (0 if out_row is None else c0 * 128 * esize)
             self._gfx_encode(
@@ -550,11 +648,13 @@ class Ginfinity:
                     src = slot["out"][:rows * 128 * esize].view(tdtype).view(rows, 128)
                     host[c0:c1].copy_(src, non_blocking=True)
                 slot["out_free"].record(s_out)
+        status_host.copy_(status, non_blocking=True)
         main.wait_stream(s_out)
         # the per-record views are built while the device is still working
         table = host.numpy()
         rows = split_rows(table, core_ptr) if presplit else None
         main.synchronize()
+        self._raise_on_status(int(status_host.item()))
         return table, core_ptr, rows
 
     records_group_nodes = 1 << 22      # nucleotides per host-prep / device-build group
@@ -599,7 +699,8 @@ class Ginfinity:
             s_build, s_out = self._streams
             s_build.wait_stream(main)
             s_out.wait_stream(main)
-            state = dict(out_free=[None, None], turn=0, keep=[])
+            state = dict(out_free=[None, None], turn=0, keep=[], status=self._new_status(),
+                         limit=self._chunk_limit(max_batch_nodes))
             bounds = [0]
             table = host.numpy()
             presplit = dtype.itemsize <= 4
@@ -623,8 +724,9 @@ class Ginfinity:
                     rows.extend(split_rows(table, node_ptr[a:b + 1]))
             self.last_microbatch_bounds = np.asarray(bounds, np.int64)
             main.wait_stream(s_out)
-            main.synchronize()
+            bad = int(state["status"].item())           # synchronises
             state["keep"].clear()
+            self._raise_on_status(bad)
         if table.dtype != dtype:
             return split_rows(table.astype(dtype), node_ptr)
         return rows
@@ -676,7 +778,7 @@ class Ginfinity:
         esize = 2 if out_code == nat.GFX_F16 else 4
         main = torch.cuda.current_stream()
         s_out = self._streams[1]
-        chunks = self._chunks(plan)
+        chunks = self._chunks(plan, state["limit"])
         node_at, edge_at = plan[1], plan[2]
         max_n = max(int(node_at[b] - node_at[a]) for a, b in chunks)
         max_e = max(int(edge_at[b] - edge_at[a]) for a, b in chunks)
@@ -699,11 +801,11 @@ class Ginfinity:
             out = outs[turn]
             if state["out_free"][turn] is not None:
                 main.wait_event(state["out_free"][turn])
-            nat.check(lib.gfx_csr_build(
+            nat.check(lib.gfx_csr_build_checked(
                 ei[0, e0:].data_ptr() if e else None, ei[1, e0:].data_ptr() if e else None,
                 ds.edge_types[e0:].data_ptr() if e else None, n, e, n0, row_ptr.data_ptr(),
-                col_src.data_ptr(), col_type.data_ptr(), csr_ws.data_ptr(), csr_ws_bytes,
-                main.cuda_stream))
+                col_src.data_ptr(), col_type.data_ptr(), state["status"].data_ptr(),
+                csr_ws.data_ptr(), csr_ws_bytes, main.cuda_stream))
             self._gfx_encode(
                 n, main.cuda_stream, self._handle, ds.node_features[n0:].data_ptr(),
                 row_ptr.data_ptr(), col_src.data_ptr(), col_type.data_ptr(), None, n,
@@ -723,12 +825,22 @@ class Ginfinity:
                             out: Optional[torch.Tensor] = None,
                             _checked: bool = False) -> torch.Tensor:
         """Device-resident encode: HBM in, HBM out ([core_count, 128] in
-        `out_dtype`).  Everything is enqueued on the current stream; the only
-        host synchronisation is the read-back of the microbatch boundaries."""
+        `out_dtype`).  Everything is enqueued on the current stream of the
+        encoder's device; the only host synchronisation is the read-back of the
+        microbatch boundaries -- and, the FIRST time a shard that did not come
+        out of the device builder is encoded, of the edge-range status word
+        (a shard whose edges leave their chunk raises GraphValidationError, as
+        the reference's GraphShard.slice does; afterwards the shard is known
+        good and later calls do not wait)."""
         if not _checked:
             self._check_request(ds.spec, ds.max_nodes_per_record,
                                 ds.max_edges_per_record, max_batch_nodes,
                                 max_batch_edges, np.float16)
+        with torch.cuda.device(self._torch_device):
+            return self._encode_device_shard(ds, int(max_batch_nodes), int(max_batch_edges),
+                                             out_dtype, out)
+
+    def _encode_device_shard(self, ds, max_batch_nodes, max_batch_edges, out_dtype, out):
         dev = self._torch_device
         stream = torch.cuda.current_stream().cuda_stream
         B, N = ds.record_count, ds.node_count
@@ -737,7 +849,7 @@ class Ginfinity:
         bounds = torch.empty(B + 2, dtype=torch.int64, device=dev)
         nat.check(nat.lib.gfx_pack_microbatches(
             ds.node_ptr.data_ptr(), ds.edge_ptr.data_ptr(), B,
-            int(max_batch_nodes), int(max_batch_edges), next_stop.data_ptr(),
+            max_batch_nodes, max_batch_edges, next_stop.data_ptr(),
             bounds.data_ptr(), bounds[B + 1:].data_ptr(), stream))
         stops = bounds[:B + 1].clamp_(0, B)     # the tail past n_bounds is unset
         packed = torch.stack((stops, ds.node_ptr[stops], ds.edge_ptr[stops]))
@@ -760,7 +872,8 @@ class Ginfinity:
         # ---- chunks of consecutive microbatches ------------------------------
         act = nat.GFX_F32 if self.full_precision else nat.GFX_F16
         node_at, edge_at = plan[1], plan[2]
-        limit = max(self.chunk_nodes, self.resident_chunk_nodes)
+        limit = self._chunk_limit(max_batch_nodes, resident=True)
+        status = self._new_status()
         start = 0
         while start < count - 1:
             stop = start + 1
@@ -770,12 +883,15 @@ class Ginfinity:
             n0, n1 = int(node_at[start]), int(node_at[stop])
             e0, e1 = int(edge_at[start]), int(edge_at[stop])
             self._run_chunk(ds, n0, n1, e0, e1, out_row, out, act, out_dtype,
-                            stream)
+                            stream, status)
             start = stop
+        if not getattr(ds, "edges_checked", False):
+            self._raise_on_status(int(status.item()))     # synchronises, once per shard
+            ds.edges_checked = True
         return out
 
     def _run_chunk(self, ds, n0, n1, e0, e1, out_row, out, act, out_dtype,
-                   stream) -> None:
+                   stream, status) -> None:
         n, e = n1 - n0, e1 - e0
         lib = nat.lib
         csr_ws_bytes = lib.gfx_csr_workspace_bytes(n, e)
@@ -786,12 +902,12 @@ class Ginfinity:
         csr_ws = self._scratch.get("csr_ws", csr_ws_bytes)
         enc_ws = self._scratch.get("enc_ws", enc_ws_bytes)
         ei = ds.edge_index
-        nat.check(lib.gfx_csr_build(
+        nat.check(lib.gfx_csr_build_checked(
             ei[0, e0:].data_ptr() if e else None,
             ei[1, e0:].data_ptr() if e else None,
             ds.edge_types[e0:].data_ptr() if e else None, n, e, n0,
             row_ptr.data_ptr(), col_src.data_ptr(), col_type.data_ptr(),
-            csr_ws.data_ptr(), csr_ws_bytes, stream))
+            status.data_ptr(), csr_ws.data_ptr(), csr_ws_bytes, stream))
         if out_row is None:
             out_base = out[n0:].data_ptr()      # identity map: row i -> n0 + i
             map_ptr = None

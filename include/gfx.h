@@ -120,6 +120,21 @@ int gfx_csr_build(const int32_t *edge_src, const int32_t *edge_dst,
                   int64_t num_edges, int32_t node_base, int32_t *row_ptr,
                   int32_t *col_src, uint8_t *col_type, void *workspace,
                   size_t workspace_bytes, void *stream);
+/* The same, reporting edges that leave the chunk.  An edge with an endpoint
+ * outside [node_base, node_base + num_nodes) is dropped (it would index past
+ * the chunk's arrays) and GFX_GRAPH_BAD_EDGE is OR-ed into *status (device
+ * int32, zeroed by the caller; may be shared by all chunks of a shard).  The
+ * reference raises GraphValidationError("edge index outside shard node
+ * range") for the same shard when GraphShard.slice re-validates the
+ * microbatch (graph.py:328-330, 424-443); the encoder raises it after the
+ * pass when the status word is set.  gfx_csr_build drops silently. */
+enum { GFX_GRAPH_BAD_EDGE = 16 };
+int gfx_csr_build_checked(const int32_t *edge_src, const int32_t *edge_dst,
+                          const uint8_t *edge_type, int64_t num_nodes,
+                          int64_t num_edges, int32_t node_base,
+                          int32_t *row_ptr, int32_t *col_src,
+                          uint8_t *col_type, int32_t *status, void *workspace,
+                          size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------
  * K6  graph construction on the device, for full-molecule records of the
