@@ -13,7 +13,7 @@ import numpy as np
 _LIB_PATH = Path(__file__).resolve().parent / "libgfx.so"
 
 GFX_F16, GFX_F32 = 0, 1
-IMPL_AUTO, IMPL_SIMT, IMPL_UMMA = 0, 1, 2
+IMPL_AUTO, IMPL_SIMT, IMPL_UMMA, IMPL_UMMA_LEAN = 0, 1, 2, 5
 
 
 class NativeError(RuntimeError):
@@ -66,7 +66,6 @@ _SIGNATURES = {
     "gfx_input_linear": (C.c_int, [_p, _p, _i64, _p, C.c_int, _p]),
     "gfx_aggregate": (C.c_int, [_p, C.c_int, _p, _p, _p, _p, _i64, _p, C.c_int, _p]),
     "gfx_mlp_ln_residual": (C.c_int, [_p, C.c_int, _p, _p, _i64, _p, C.c_int, C.c_int, _p]),
-    "gfx_layer_fused": (C.c_int, [_p, C.c_int, _p, _p, _p, _p, _i64, _p, _p]),
     "gfx_layer_fused_pair": (C.c_int, [_p, C.c_int, _p, _p, _p, _p, _i64, _p, _p]),
     "gfx_row_describe": (C.c_int, [_p, _p, _p, _i64, _p, _p]),
     "gfx_layer_fused_banded": (C.c_int, [_p, C.c_int, _p, _p, _p, _p, _p, _i64, _p, _p]),

@@ -249,8 +249,10 @@ extern "C" int gfx_encode(const gfx_model *model, const float *x, const int32_t 
   if (n == 0) return GFX_OK;
   if (ws_bytes < gfx_encode_workspace_bytes(n, dtype))
     return fail(GFX_ERR_WORKSPACE, "gfx_encode: workspace too small");
+  if (fused < 0 || fused > 3) return fail(GFX_ERR_ARGUMENT, "gfx_encode: fused must be 0, 2 or 3");
   if (fused && dtype != GFX_F16)
     return fail(GFX_ERR_UNSUPPORTED, "gfx_encode: fused layers exist for GFX_F16 only");
+  if (fused == 1) fused = 2;   // the one-CTA-per-SM form was removed; 1 is kept as an alias
   // the banded kernel covers >= 6 edge types and <= 2^25 nodes, the CTA-pair kernel <= 10 edge
   // types and <= 2^27 nodes; outside that: K1 + K2
   if (fused == 3 && (model->edge_dim < 6 || n > (int64_t(1) << 25))) fused = 2;
@@ -268,9 +270,8 @@ extern "C" int gfx_encode(const gfx_model *model, const float *x, const int32_t 
     if (fused == 3) {   // CTA pairs, banded producers (gfx_fused7.cu)
       rc = gfx_layer_fused_banded(model, l, h, row_ptr, col_src, col_type, desc, n, h2, stream);
       if (rc) return rc;
-    } else if (fused) {   // 1: one CTA per SM (gfx_fused5.cu); 2: CTA pairs (gfx_fused6.cu)
-      rc = (fused == 2 ? gfx_layer_fused_pair : gfx_layer_fused)(model, l, h, row_ptr, col_src,
-                                                                 col_type, n, h2, stream);
+    } else if (fused) {   // CTA pairs, producers walk the CSR arrays (gfx_fused6.cu)
+      rc = gfx_layer_fused_pair(model, l, h, row_ptr, col_src, col_type, n, h2, stream);
       if (rc) return rc;
     } else {
       rc = gfx_aggregate(model, l, h, row_ptr, col_src, col_type, n, z, dtype, stream);

@@ -619,22 +619,12 @@ static inline int row_grid(int64_t n) {
   return int(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
-// implemented in gfx_umma.cu
+// implemented in gfx_umma2.cu (general tcgen05 kernel) and gfx_umma4.cu (lean TMA kernel)
 int umma_mlp_ln_residual(const gfx_model *m, int layer, const __half *z, const __half *h,
                          int64_t n, __half *h_out, cudaStream_t st);
 int umma_head_l2norm(const gfx_model *m, const __half *h, const int32_t *out_row, int64_t n,
                      void *out, int out_dtype, cudaStream_t st);
-int umma1_mlp_ln_residual(const gfx_model *m, int layer, const __half *z, const __half *h,
-                          int64_t n, __half *h_out, cudaStream_t st);
-int umma1_head_l2norm(const gfx_model *m, const __half *h, const int32_t *out_row, int64_t n,
-                      void *out, int out_dtype, cudaStream_t st);
-int umma3_mlp_ln_residual(const gfx_model *m, int layer, const __half *z, const __half *h,
-                          int64_t n, __half *h_out, cudaStream_t st);
-int umma6_mlp_ln_residual(const gfx_model *m, int layer, const __half *z, const __half *h,
-                          int64_t n, __half *h_out, cudaStream_t st);
 int umma4_mlp_ln_residual(const gfx_model *m, int layer, const __half *z, const __half *h,
-                          int64_t n, __half *h_out, cudaStream_t st);
-int umma7_mlp_ln_residual(const gfx_model *m, int layer, const __half *z, const __half *h,
                           int64_t n, __half *h_out, cudaStream_t st);
 // implemented in gfx_head8.cu: fp16 in, fp16 out, identity row map
 int head8_l2norm(const gfx_model *m, const __half *h, int64_t n, __half *out, cudaStream_t st);
@@ -718,19 +708,15 @@ extern "C" int gfx_mlp_ln_residual(const gfx_model *m, int layer, const void *z,
   const int H = kHidden, M = kMlpHidden;
   StageScope scope(GFX_STAGE_MLP, st, 1);
   if (impl == GFX_IMPL_AUTO) impl = dtype == GFX_F16 ? GFX_IMPL_UMMA_LEAN : GFX_IMPL_SIMT;
-  if (impl == GFX_IMPL_UMMA || impl == GFX_IMPL_UMMA_SERIAL || impl == GFX_IMPL_UMMA_TMA ||
-      impl == GFX_IMPL_UMMA_LEAN || impl == GFX_IMPL_UMMA_STREAM || impl == GFX_IMPL_UMMA_PAIR) {
+  if (impl == GFX_IMPL_UMMA || impl == GFX_IMPL_UMMA_LEAN) {
     if (dtype != GFX_F16)
       return fail(GFX_ERR_UNSUPPORTED, "tcgen05 MLP exists for GFX_F16 only");
-    auto fn = impl == GFX_IMPL_UMMA_PAIR ? umma7_mlp_ln_residual
-              : impl == GFX_IMPL_UMMA_STREAM ? umma6_mlp_ln_residual
-              : impl == GFX_IMPL_UMMA_LEAN ? umma4_mlp_ln_residual
-              : impl == GFX_IMPL_UMMA_TMA ? umma3_mlp_ln_residual
-              : impl == GFX_IMPL_UMMA   ? umma_mlp_ln_residual
-                                        : umma1_mlp_ln_residual;
+    auto fn = impl == GFX_IMPL_UMMA_LEAN ? umma4_mlp_ln_residual : umma_mlp_ln_residual;
     return fn(m, layer, static_cast<const __half *>(z), static_cast<const __half *>(h), n,
               static_cast<__half *>(h_out), st);
   }
+  if (impl != GFX_IMPL_SIMT)
+    return fail(GFX_ERR_ARGUMENT, "gfx_mlp_ln_residual: unknown impl (0 auto, 1 SIMT, 2 tcgen05, 5 lean tcgen05)");
   const int q = dtype == GFX_F16 ? 1 : 0;
   const float *w1t = m->w1t[q] + size_t(layer) * H * M, *b1 = m->b1 + size_t(layer) * M;
   const float *w2t = m->w2t[q] + size_t(layer) * M * H, *b2 = m->b2 + size_t(layer) * H;
@@ -761,15 +747,14 @@ extern "C" int gfx_head_l2norm(const gfx_model *m, const void *h, const int32_t 
       n <= (int64_t(1) << 30) && !((reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(out)) & 15))
     return head8_l2norm(m, static_cast<const __half *>(h), n, static_cast<__half *>(out), st);
   if (impl == GFX_IMPL_AUTO) impl = dtype == GFX_F16 ? GFX_IMPL_UMMA : GFX_IMPL_SIMT;
-  if (impl == GFX_IMPL_UMMA_TMA || impl == GFX_IMPL_UMMA_LEAN || impl == GFX_IMPL_UMMA_STREAM ||
-      impl == GFX_IMPL_UMMA_PAIR)
-    impl = GFX_IMPL_UMMA;  // head: v2 kernel
-  if (impl == GFX_IMPL_UMMA || impl == GFX_IMPL_UMMA_SERIAL) {
+  if (impl == GFX_IMPL_UMMA_LEAN) impl = GFX_IMPL_UMMA;  // head: general tcgen05 kernel
+  if (impl == GFX_IMPL_UMMA) {
     if (dtype != GFX_F16)
       return fail(GFX_ERR_UNSUPPORTED, "tcgen05 head exists for GFX_F16 only");
-    return (impl == GFX_IMPL_UMMA ? umma_head_l2norm : umma1_head_l2norm)(
-        m, static_cast<const __half *>(h), out_row, n, out, out_dtype, st);
+    return umma_head_l2norm(m, static_cast<const __half *>(h), out_row, n, out, out_dtype, st);
   }
+  if (impl != GFX_IMPL_SIMT)
+    return fail(GFX_ERR_ARGUMENT, "gfx_head_l2norm: unknown impl (0 auto, 1 SIMT, 2 tcgen05)");
   const int q = dtype == GFX_F16 ? 1 : 0;
   if (dtype == GFX_F16 && out_dtype == GFX_F16)
     return launch_mlp<__half, __half, kHidden, 1, true>(

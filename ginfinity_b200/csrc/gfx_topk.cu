@@ -21,6 +21,8 @@
 #include <limits.h>
 #include <math.h>
 
+#include <cstdlib>
+
 #include "gfx_common.cuh"
 #include "gfx_tma.cuh"
 #include "gfx_umma.cuh"
@@ -514,7 +516,7 @@ extern "C" int gfx_topk(const void *queries, int64_t num_queries, const void *da
     return fail(GFX_ERR_ARGUMENT, "gfx_topk: null pointer");
   if ((reinterpret_cast<uintptr_t>(queries) | reinterpret_cast<uintptr_t>(database)) & 15)
     return fail(GFX_ERR_ARGUMENT, "gfx_topk: queries and database must be 16-byte aligned");
-  const topk::Plan plan = topk::make_plan(num_queries, num_rows, k);
+  topk::Plan plan = topk::make_plan(num_queries, num_rows, k);
   if (workspace_bytes < plan.total || !workspace)
     return fail(GFX_ERR_WORKSPACE, "gfx_topk: workspace too small");
   cudaStream_t st = as_stream(stream);
@@ -542,6 +544,11 @@ extern "C" int gfx_topk(const void *queries, int64_t num_queries, const void *da
   StageScope scope(GFX_STAGE_TOPK, st, (metric == 1 ? 3 : 2) + (plan.sample_tiles ? 1 : 0));
   const int64_t items = plan.tiles_q * plan.segs;
   topk::Args pre = a;                      // seeding pre-pass over the first rows, one segment
+  static const bool seeding = [] {         // developer switch: GFX_TOPK_SEED=0 scans unseeded
+    const char *v = getenv("GFX_TOPK_SEED");
+    return !(v && v[0] == '0');
+  }();
+  if (!seeding) plan.sample_tiles = 0;
   if (plan.sample_tiles) {
     pre.part_scores = reinterpret_cast<float *>(ws + plan.off_seed_scores);
     pre.part_index = reinterpret_cast<int32_t *>(ws + plan.off_seed_index);

@@ -360,22 +360,3 @@ int umma_head_l2norm(const gfx_model *m, const __half *h, const int32_t *out_row
 }
 
 }  // namespace gfx
-
-namespace gfx {
-int fused5_layer(const gfx_model *m, int layer, const __half *h, const int32_t *row_ptr,
-                 const int32_t *col_src, const uint8_t *col_type, int64_t n, __half *h_out,
-                 cudaStream_t st);
-}
-
-extern "C" int gfx_layer_fused(const gfx_model *m, int layer, const void *h,
-                               const int32_t *row_ptr, const int32_t *col_src,
-                               const uint8_t *col_type, int64_t n, void *h_out, void *stream) {
-  using namespace gfx;
-  if (!m || layer < 0 || layer >= m->layers)
-    return fail(GFX_ERR_ARGUMENT, "gfx_layer_fused: bad model or layer");
-  if (n <= 0) return GFX_OK;
-  cudaStream_t st = as_stream(stream);
-  StageScope scope(GFX_STAGE_FUSED_LAYER, st, 1);
-  return fused5_layer(m, layer, static_cast<const __half *>(h), row_ptr, col_src, col_type, n,
-                      static_cast<__half *>(h_out), st);
-}

@@ -48,12 +48,10 @@ enum { GFX_F16 = 0, GFX_F32 = 1 };
 enum {
   GFX_IMPL_AUTO = 0,  /* tcgen05 for GFX_F16, SIMT for GFX_F32 */
   GFX_IMPL_SIMT = 1,  /* CUDA-core fp32-accumulate kernels */
-  GFX_IMPL_UMMA = 2,  /* tcgen05.mma / TMEM kernels (GFX_F16 only) */
-  GFX_IMPL_UMMA_SERIAL = 3, /* first, un-pipelined tcgen05 kernel (kept as a cross-check) */
-  GFX_IMPL_UMMA_TMA = 4,    /* pipelined tcgen05 with all tile I/O on 2-D tiled TMA (K2) */
-  GFX_IMPL_UMMA_LEAN = 5,   /* TMA I/O + 16 lean epilogue warps, constants as kernel parameters (K2) */
-  GFX_IMPL_UMMA_STREAM = 6, /* three stage buffers cycling z -> residual -> output instead of a separate residual tile (K2) */
-  GFX_IMPL_UMMA_PAIR = 7    /* CTA pairs (tcgen05 cta_group::2): weights split across the pair, five cycling stage buffers (K2) */
+  GFX_IMPL_UMMA = 2,  /* general tcgen05.mma / TMEM kernel (GFX_F16 only; cross-check) */
+  GFX_IMPL_UMMA_LEAN = 5 /* K2 default: TMA tile I/O + 16 lean epilogue warps, constants as
+                            kernel parameters (codes 3, 4, 6, 7 named variants that were
+                            measured in round 1 and removed; they are rejected) */
 };
 
 int gfx_abi_version(void);
@@ -246,13 +244,7 @@ int gfx_mlp_ln_residual(const gfx_model *model, int layer, const void *z,
                         const void *h, int64_t num_nodes, void *h_out,
                         int dtype, int impl, void *stream);
 
-/* K1+K2 in one kernel (z never leaves the SM); GFX_F16 only */
-int gfx_layer_fused(const gfx_model *model, int layer, const void *h,
-                    const int32_t *row_ptr, const int32_t *col_src,
-                    const uint8_t *col_type, int64_t num_nodes, void *h_out,
-                    void *stream);
-
-/* K1+K2 in one kernel on CTA pairs (tcgen05 cta_group::2: the pair shares
+/* K1+K2 in one kernel (z never leaves the SM) on CTA pairs (tcgen05 cta_group::2: the pair shares
  * the weights, each CTA keeps its tile of h resident as neighbour source,
  * residual and output staging); GFX_F16 only, <= 10 edge types, <= 2^27 nodes */
 int gfx_layer_fused_pair(const gfx_model *model, int layer, const void *h,
@@ -287,8 +279,8 @@ int gfx_head_l2norm(const gfx_model *model, const void *h,
  * order).  Replaces Ginfinity._run_graph_shard's device work
  * (api.py:236-252).  workspace holds the activation ping-pong buffers.
  * `impl`: GFX_IMPL_* for the dense stages.  `fused` (GFX_F16 only) selects the
- * layer kernel: 0 = K1 + K2 (gfx_aggregate, gfx_mlp_ln_residual), 1 =
- * gfx_layer_fused, 2 = gfx_layer_fused_pair, 3 = gfx_row_describe once +
+ * layer kernel: 0 = K1 + K2 (gfx_aggregate, gfx_mlp_ln_residual),
+ * 2 (or 1) = gfx_layer_fused_pair, 3 = gfx_row_describe once +
  * gfx_layer_fused_banded per layer (descriptors live in the z buffer, which the
  * fused forms do not use); a form that does not cover the call (edge types,
  * node count) falls back to the next lower one that does.

@@ -120,9 +120,9 @@ def main():
         print(f"aggregate[{name}]: {t * 1e3:.3f} ms  {alg / t / 1e9:.0f} GB/s algorithmic ({alg / N:.0f} B/node)")
         report[f"aggregate_{name}_s"] = t
         report[f"aggregate_{name}_gbs"] = alg / t / 1e9
-        impls = ((1, "simt"), (3, "umma_serial"), (2, "umma"), (4, "umma_tma"), (5, "umma_lean"), (6, "umma_stream"), (7, "umma_pair")) if code == 0 else ((1, "simt"),)
+        impls = ((1, "simt"), (2, "umma"), (5, "umma_lean")) if code == 0 else ((1, "simt"),)
         if os.environ.get("GFX_DIAG_FAST"):
-            impls = ((5, "umma_lean"), (6, "umma_stream"), (7, "umma_pair")) if code == 0 else ()
+            impls = ((5, "umma_lean"),) if code == 0 else ()
         for impl, iname in impls:
             t = timeit(lambda: nat.check(lib.gfx_mlp_ln_residual(handle, 0, zz.data_ptr(), hh.data_ptr(), N, h2.data_ptr(), code, impl, S())), iters=5, warm=2)
             fl = N * 131072.0
@@ -140,7 +140,7 @@ def main():
             print(f"encode[{name},{iname}]: {t * 1e3:.3f} ms  {N / t / 1e6:.1f} M nt/s")
             report[f"encode_{name}_{iname}_nts"] = N / t
         if code == 0:
-            t = timeit(lambda: nat.check(lib.gfx_layer_fused(handle, 0, hh.data_ptr(), row_ptr.data_ptr(), col_src.data_ptr(), col_type.data_ptr(), N, h2.data_ptr(), S())), iters=5, warm=2)
+            t = timeit(lambda: nat.check(lib.gfx_layer_fused_pair(handle, 0, hh.data_ptr(), row_ptr.data_ptr(), col_src.data_ptr(), col_type.data_ptr(), N, h2.data_ptr(), S())), iters=5, warm=2)
             print(f"fused_layer[f16]: {t * 1e3:.3f} ms  {N * 131072.0 / t / 1e12:.1f} TFLOP/s  {N / t / 1e9:.2f} G node-layers/s")
             report["fused_layer_s"] = t
             t = timeit(lambda: nat.check(lib.gfx_encode(handle, x_d.data_ptr(), row_ptr.data_ptr(), col_src.data_ptr(), col_type.data_ptr(), None, N, out.data_ptr(), 0, 0, 2, 1, wse.data_ptr(), need_e, S())), iters=3, warm=1)
