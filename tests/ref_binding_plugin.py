@@ -1,6 +1,6 @@
 """pytest plugin: run the REFERENCE's own tests with libgfx.so under its API.
 
-Loaded with `-p tests.ref_binding_plugin` by tests/test_gpu_reference.py.  It
+Loaded with `-p ref_binding_plugin` (PYTHONPATH=tests) by tests/test_gpu_reference.py.  It
 imports the staged, unmodified reference (oracle/_ref), installs the C-ABI
 binding of INTEGRATION.md (ginfinity_b200/reference_binding.py) over
 `ginfinity.api.Ginfinity._run_graph_shard` -- the one seam of the hot path,

@@ -335,3 +335,83 @@ def test_encode_shard_files_with_prefetch_matches_direct_encoding(gb, syn16, tmp
         want = syn16.encode_graphs(shard)
         assert len(want) == len(seen[p])
         assert all(np.array_equal(a, b) for a, b in zip(want, seen[p]))
+
+
+# ---- round-2 contract additions ------------------------------------------------------------
+def _clone_shard(gb, shard, **replace):
+    fields = {name: getattr(shard, name) for name in (
+        "identifiers", "sequences", "structures", "node_features", "edge_index", "edge_types",
+        "node_ptr", "edge_ptr", "spec", "residue_index", "node_roles")}
+    fields.update(replace)
+    return gb.GraphShard(**fields)
+
+
+def test_edges_that_leave_their_chunk_are_rejected_not_dereferenced(gb, syn16):
+    """A shard that passes construction-time validation (every index in [0, N)) but holds an edge
+    into another microbatch: the reference raises GraphValidationError when GraphShard.slice
+    re-validates the microbatch (graph.py:328-330, 424-443).  Here the CSR build drops the edge
+    (no out-of-range device access) and the encode raises the same error -- on the host path, on
+    the device-resident path (first use of the shard), and nothing is poisoned afterwards.
+    (Like the reference, which only sees an edge that leaves its MICROBATCH, this path only sees
+    an edge that leaves its CHUNK of microbatches; inside one both compute it as given.)"""
+    from ginfinity_b200.encoder import DeviceShard
+    shard = gb.GraphBuilder().build_shard(random_records(71, 60))
+    good = np.concatenate(syn16.encode_graphs(shard, embedding_dtype=np.float32))
+    ei = shard.edge_index.copy()
+    ei[0, 3] = shard.node_count - 1            # source in the LAST record, destination in the first
+    bad = _clone_shard(gb, shard, edge_index=ei)
+    limits = dict(max_batch_nodes=2000, max_batch_edges=10_000)     # several microbatches / chunks
+    keep = syn16.chunk_nodes, syn16.resident_chunk_nodes
+    syn16.chunk_nodes = syn16.resident_chunk_nodes = 4000
+    try:
+        with pytest.raises(gb.GraphValidationError, match="outside shard node range"):
+            syn16.encode_graphs(bad, **limits)
+        with pytest.raises(gb.GraphValidationError, match="outside shard node range"):
+            syn16.encode_device_shard(DeviceShard.from_shard(bad, "cuda:0"), **limits)
+        again = np.concatenate(syn16.encode_graphs(shard, embedding_dtype=np.float32, **limits))
+    finally:
+        syn16.chunk_nodes, syn16.resident_chunk_nodes = keep
+    assert np.array_equal(again, good)
+
+
+def test_caller_owned_result_table(gb, syn16):
+    """encode_graphs(out=table): embeddings land in the caller's (page-locked) table, the returned
+    arrays are views of it, the bits are those of the allocating call; wrong tables are refused
+    before any device work."""
+    shard = gb.GraphBuilder().build_shard(random_records(72, 50))
+    want = syn16.encode_graphs(shard)
+    table = gb.Ginfinity.pinned_table(shard.node_count)
+    assert table.shape == (shard.node_count, 128) and table.dtype == np.float16
+    got = syn16.encode_graphs(shard, out=table)
+    assert all(np.array_equal(a, b) for a, b in zip(got, want))
+    assert all(np.shares_memory(a, table) for a in got)
+    table32 = np.empty((shard.node_count, 128), np.float32)          # pageable memory also works
+    got32 = syn16.encode_graphs(shard, embedding_dtype=np.float32, out=table32)
+    assert np.shares_memory(got32[0], table32)
+    assert np.abs(np.concatenate(got32) - np.concatenate(want).astype(np.float32)).max() <= 1e-3
+    with pytest.raises(ValueError, match="out"):
+        syn16.encode_graphs(shard, out=np.empty((shard.node_count - 1, 128), np.float16))
+    with pytest.raises(ValueError, match="out"):
+        syn16.encode_graphs(shard, out=np.empty((shard.node_count, 128), np.float32))
+    with pytest.raises(ValueError, match="out"):
+        syn16.encode_graphs(shard, embedding_dtype=np.float64,
+                            out=np.empty((shard.node_count, 128), np.float64))
+
+
+def test_lowering_max_batch_nodes_lowers_device_scratch(gb, synthetic_state):
+    """The reference's memory knob (docs/OPERATIONS.md:25-27): a chunk holds at most
+    CHUNK_MICROBATCHES x max_batch_nodes nodes, so the scratch buffers shrink with it; the bits
+    do not change."""
+    from ginfinity_b200 import encoder as E
+    shard = gb.GraphBuilder().build_shard(random_records(73, 400))       # ~80k nodes
+    longest = int(np.diff(shard.node_ptr).max())
+    sizes, outs = {}, {}
+    for limit in (60_000, max(longest, 500)):
+        enc = gb.Ginfinity.from_state(synthetic_state, device="cuda:0")
+        outs[limit] = np.concatenate(enc.encode_graphs(
+            shard, max_batch_nodes=limit, max_batch_edges=5 * limit + 100))
+        sizes[limit] = sum(t.numel() for t in enc._scratch._buf.values())
+        assert enc._chunk_limit(limit) == min(enc.chunk_nodes, E.CHUNK_MICROBATCHES * limit)
+    small = max(longest, 500)
+    assert np.array_equal(outs[60_000], outs[small])
+    assert sizes[small] * 4 < sizes[60_000]

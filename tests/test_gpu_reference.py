@@ -68,10 +68,11 @@ def test_reference_test_suite_passes_through_the_c_abi_binding():
     root = ref_loader.reference_root()
     tests = [str(root / "tests" / name) for name in
              ("test_api.py", "test_graph.py", "test_sliced_graphs.py", "test_encoder_cli.py")]
-    env = dict(os.environ, PYTHONPATH=str(ROOT), PYTHONDONTWRITEBYTECODE="1")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join((str(ROOT / "tests"), str(ROOT))),
+               PYTHONDONTWRITEBYTECODE="1")
     proc = subprocess.run(
         [sys.executable, "-m", "pytest", "-q", "-p", "no:cacheprovider", "-p",
-         "tests.ref_binding_plugin", "--rootdir", str(root), *tests],
+         "ref_binding_plugin", "--rootdir", str(root), *tests],
         cwd=str(ROOT), env=env, capture_output=True, text=True, timeout=900)
     tail = proc.stdout[-3000:] + proc.stderr[-2000:]
     assert proc.returncode == 0, tail

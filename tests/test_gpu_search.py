@@ -167,3 +167,34 @@ def test_seeded_scan_on_a_large_database_with_ties(search, metric):
     np.testing.assert_allclose(got_s, want_s, rtol=1e-6, atol=1e-7)
     assert np.all(got_s[:6, 0] == got_s[:6, 3])            # four copies of each hot row tie
     assert np.all(np.diff(got_i[:6, :4], axis=1) > 0)
+
+
+def test_search_time_is_stable_call_to_call(search):
+    """Regression bound for the round-1 "100x outliers" (profiles/r01_d/f_search_timing.json:
+    14.6 s / 41.8 s).  They were a measurement artefact -- the committed JSON had been written
+    by the SAME command re-run under `ncu --set full`, whose kernel replays sat inside the
+    event-timed region -- but a search that really stalled would show up
+    here: eight consecutive cosine searches, each timed on its own on the device and on the
+    host, must stay within 25 % of their median and finish in well under a second."""
+    import time
+    from ginfinity_b200.search import EmbeddingIndex
+    g = torch.Generator(device="cuda").manual_seed(5)
+    unit = lambda n: torch.nn.functional.normalize(  # noqa: E731
+        torch.randn(n, 128, generator=g, device="cuda"), dim=1).half()
+    q, index = unit(20_000), EmbeddingIndex(unit(1_000_000), device="cuda")
+    index.search(q, 10, "cosine")
+    torch.cuda.synchronize()
+    device_s, host_s = [], []
+    for _ in range(8):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        a.record()
+        index.search(q, 10, "cosine")
+        b.record()
+        torch.cuda.synchronize()
+        host_s.append(time.perf_counter() - t0)
+        device_s.append(a.elapsed_time(b) * 1e-3)
+    med = float(np.median(device_s))
+    assert max(device_s) <= 1.25 * med and min(device_s) >= 0.75 * med, device_s
+    assert max(host_s) <= 1.25 * med + 0.005, (host_s, device_s)
+    assert max(host_s) < 0.5, host_s

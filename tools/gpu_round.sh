@@ -27,6 +27,6 @@ if [ "$1" != "ncu" ]; then
 unset GFX_FUSED
 SEARCH_CMD="python tools/search_bench.py 3"
 timeout 300 $SEARCH_CMD > gpurun_out/search.log 2>&1 && \
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"topk_scan" -s 17 -c 1 -o gpurun_out/prof_search $SEARCH_CMD > gpurun_out/ncu_search.log 2>&1
+SEARCH_BENCH_NO_JSON=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"topk_scan" -s 17 -c 1 -o gpurun_out/prof_search $SEARCH_CMD > gpurun_out/ncu_search.log 2>&1
 fi
 cat gpurun_out/ncu_pin.log; tail -3 gpurun_out/smoke.log; tail -3 gpurun_out/pytest_gpu.log; cat gpurun_out/bench.json | head -c 1500; tail -3 gpurun_out/bench.err; head -c 600 gpurun_out/bench_ref.json

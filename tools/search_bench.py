@@ -1,7 +1,13 @@
 #!/usr/bin/env python
 """Developer timing of K5 (gfx_topk) on one B200: TFLOP/s of the fused
 GEMM + top-k scan at a few shapes, next to torch.matmul + torch.topk on the
-same inputs (library bar).  Prints and writes gpurun_out/search.json."""
+same inputs (library bar).  Prints and writes gpurun_out/search.json -- unless
+SEARCH_BENCH_NO_JSON is set: round 1's tools/gpu_round.sh re-ran this very
+command under `ncu --set full` (to capture topk_scan), and that second run
+overwrote search.json with timings whose event-bracketed region contained
+ncu's kernel replays (the "14.6 s / 41.8 s cosine" rows of
+profiles/r01_d/f_search_timing.json).  A run under a profiler must not write
+the timing file."""
 import json
 import sys
 from pathlib import Path
@@ -58,6 +64,9 @@ def main():
             out.append(row)
         del index, db
         torch.cuda.empty_cache()
+    import os
+    if os.environ.get("SEARCH_BENCH_NO_JSON"):
+        return
     (ROOT / "gpurun_out").mkdir(exist_ok=True)
     (ROOT / "gpurun_out" / "search.json").write_text(json.dumps(out, indent=1))
 
