@@ -47,6 +47,7 @@
 #include "gfx_tma.cuh"
 #include "gfx_pair.cuh"
 #include "gfx_umma.cuh"
+#include "gfx_layer_math.cuh"
 
 namespace gfx {
 
@@ -93,19 +94,16 @@ struct alignas(64) Maps {
   CUtensorMap h, out;        // [n, 128] fp16, box 64 x 128, SWIZZLE_128B
 };
 
-struct Consts {
-  float b1[HID];
-};
+using Consts = lmath::Consts;     // b1, b2, LayerNorm vectors as kernel parameters
 
 struct Args {
   const __half *h;
   const int32_t *row_ptr, *col_src;
   const uint8_t *col_type;
   const __half *table16, *w1_img, *w2_img;
-  const float *b2, *g, *b;   // device vectors of this layer
   int64_t n;
   int edge_dim;
-  float eps1;
+  uint32_t eps1_h2;          // (1 + eps) rounded to fp16, in both halves of the word
   long long *trace;          // developer timeline (tools/fused_trace.py); null in production
 };
 
@@ -136,11 +134,13 @@ __device__ __forceinline__ void add_pair(float &a0, float &a1, uint32_t m) {
       : "+f"(a0), "+f"(a1)
       : "r"(m));
 }
-__device__ __forceinline__ void add_message(float *acc, const uint4 &nb, const uint4 &tb) {
-  add_pair(acc[0], acc[1], hfma2_relu_add(nb.x, tb.x));
-  add_pair(acc[2], acc[3], hfma2_relu_add(nb.y, tb.y));
-  add_pair(acc[4], acc[5], hfma2_relu_add(nb.z, tb.z));
-  add_pair(acc[6], acc[7], hfma2_relu_add(nb.w, tb.w));
+// one message on 8 channels, in packed half like the reference's fp16 path (and gfx_fused8.cu):
+// acc = half(acc + relu(half(x + t)))
+__device__ __forceinline__ void add_message(uint32_t *acc, const uint4 &nb, const uint4 &tb) {
+  acc[0] = lmath::h2_add(acc[0], lmath::h2_relu_add(nb.x, tb.x));
+  acc[1] = lmath::h2_add(acc[1], lmath::h2_relu_add(nb.y, tb.y));
+  acc[2] = lmath::h2_add(acc[2], lmath::h2_relu_add(nb.z, tb.z));
+  acc[3] = lmath::h2_add(acc[3], lmath::h2_relu_add(nb.w, tb.w));
 }
 __device__ __forceinline__ uint4 lds128(uint32_t saddr) {
   uint4 v;
@@ -280,9 +280,6 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Con
     const int quad = warp & 3, g = (warp - kEpiBWarp0) >> 2;
     const uint32_t trow = tmem + (uint32_t(quad * 32) << 16) + kD2Col + uint32_t(g) * kHidden;
     const uint32_t d2e = leader(kBarD2Empty + g);
-    const float4 *b2v = reinterpret_cast<const float4 *>(p.b2);
-    const float4 *gv = reinterpret_cast<const float4 *>(p.g);
-    const float4 *bv = reinterpret_cast<const float4 *>(p.b);
     const int r = quad * 32 + lane;
     uint32_t it = 0;
     for (int pair = cluster_id; pair < pairs; pair += clusters, ++it) {
@@ -291,61 +288,27 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Con
       mbar_wait_c(bar + kBarD2Full + g, (it >> 1) & 1);
       tc_fence_after();
       if (lane == 0 && quad == 0) trace_ev(p, it, 8);
-      // 16 columns at a time, loops NOT unrolled: an unrolled body lets the compiler hoist the
-      // vector loads of several chunks and spill (64 registers per thread)
-      float s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};
+      // the arithmetic of gfx_fused8.cu's epilogue B (gfx_layer_math.cuh), both column halves of
+      // the row on this thread: same operations in the same order, same bits
+      // (the column half is a run-time value here: two unrolled copies with their 384 constant
+      // operands spill under this role's register limit)
+      float2 part[2];
 #pragma unroll 1
-      for (int q = 0; q < 8; ++q) {
-        float u[16];
-        tmem_ld16(trow + 16 * q, u);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) {
-          const float4 bb = __ldg(b2v + 4 * q + j4);
-          const float t0 = u[4 * j4] + bb.x, t1 = u[4 * j4 + 1] + bb.y;
-          const float t2 = u[4 * j4 + 2] + bb.z, t3 = u[4 * j4 + 3] + bb.w;
-          s1[0] += t0; s1[1] += t1; s1[0] += t2; s1[1] += t3;
-          s2[0] = fmaf(t0, t0, s2[0]); s2[1] = fmaf(t1, t1, s2[1]);
-          s2[0] = fmaf(t2, t2, s2[0]); s2[1] = fmaf(t3, t3, s2[1]);
-        }
-      }
-      const float mean = (s1[0] + s1[1]) * (1.f / kHidden);
-      const float var = fmaxf((s2[0] + s2[1]) * (1.f / kHidden) - mean * mean, 0.f);
+      for (int half = 0; half < 2; ++half) part[half] = lmath::epi_b_partial_rt(c, trow + 64 * half, half);
+      const float2 lo = part[0], hi = part[1];
+      const float sum = lo.x + hi.x, sq = lo.y + hi.y;
+      const float mean = sum * (1.f / kHidden);
+      const float var = fmaxf(sq * (1.f / kHidden) - mean * mean, 0.f);
       const float rstd = rsqrtf(var + 1e-5f);
       const float nm = -mean * rstd;
       mbar_wait_c(bar + kBarHFull + hb, (it / kHBufs) & 1);      // long complete: visibility only
       const uint32_t hrow = smem_u32(hs) + hb * kTileBytes;
 #pragma unroll 1
-      for (int q = 0; q < 8; ++q) {
-        float u[16];
-        tmem_ld16(trow + 16 * q, u);
-        tmem_ld_wait();
-        if (q == 7) {                                     // D2 fully read
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(d2e);
-        }
-#pragma unroll
-        for (int gi = 0; gi < 2; ++gi) {
-          const int c16 = q * 2 + gi;                     // 16-byte chunk of the 256-byte row
-          const uint32_t cell = hrow + uint32_t(c16 >> 3) * kKbBytes + sw_off(r, c16 & 7);
-          const uint4 raw = lds128(cell);
-          const __half2 *hp = reinterpret_cast<const __half2 *>(&raw);
-          float o[8];
-#pragma unroll
-          for (int w = 0; w < 2; ++w) {
-            const int j = gi * 8 + 4 * w, c4 = 4 * q + 2 * gi + w;
-            const float4 bb = __ldg(b2v + c4), gg = __ldg(gv + c4), be = __ldg(bv + c4);
-            const float2 ra = __half22float2(hp[2 * w]), rb = __half22float2(hp[2 * w + 1]);
-            o[4 * w] = fmaf(fmaf(u[j] + bb.x, rstd, nm), gg.x, ra.x + be.x);
-            o[4 * w + 1] = fmaf(fmaf(u[j + 1] + bb.y, rstd, nm), gg.y, ra.y + be.y);
-            o[4 * w + 2] = fmaf(fmaf(u[j + 2] + bb.z, rstd, nm), gg.z, rb.x + be.z);
-            o[4 * w + 3] = fmaf(fmaf(u[j + 3] + bb.w, rstd, nm), gg.w, rb.y + be.w);
-          }
-          sts128(cell, make_uint4(pack2(o[0], o[1]), pack2(o[2], o[3]), pack2(o[4], o[5]),
-                                  pack2(o[6], o[7])));
-        }
-      }
+      for (int half = 0; half < 2; ++half)
+        lmath::epi_b_normalise_rt(c, trow + 64 * half, hrow, r, rstd, nm, half);
+      tc_fence_before();                                         // D2 fully read
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(d2e);
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar + kBarOReady + hb);
@@ -415,9 +378,9 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Con
         if (ptid == 0) trace_ev(p, it, 0);
       }
       const int lr = qid + kQuarters * k;
-      float acc[16];
+      uint32_t acc[8];                 // 16 channels as 8 half pairs (+0)
 #pragma unroll
-      for (int ch = 0; ch < 16; ++ch) acc[ch] = 0.f;
+      for (int ch = 0; ch < 8; ++ch) acc[ch] = 0u;
       // Half a row (16 bytes per lane) ahead: the next half row is requested before the current
       // one is summed.  The asm statements are volatile, so this order is the order of the
       // machine code; left to itself the compiler hoists all ten row loads and spills.
@@ -447,7 +410,7 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Con
           cur = edge(u + 1);
           d0 = ld_tile_or_global(cur.in_tile, cur.a, cur.gp);
         }
-        add_message(acc + 8, d1, lds128(t1));
+        add_message(acc + 4, d1, lds128(t1));
       }
       // rare: rows longer than the window (lane kWin of the quarter holds edge kWin, if any)
       if ((__shfl_sync(0xffffffffu, pk, qbase + kWin) >> kSrcBits) != uint32_t(p.edge_dim)) {
@@ -456,22 +419,18 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Con
           const int src = p.col_src[eidx];
           const uint32_t t = tvs + uint32_t(p.col_type[eidx]) * 256u;
           add_message(acc, hv[int64_t(src) * 16], lds128(t));
-          add_message(acc + 8, hv[int64_t(src) * 16 + 8], lds128(t + 128u));
+          add_message(acc + 4, hv[int64_t(src) * 16 + 8], lds128(t + 128u));
         }
       }
       uint4 o0 = make_uint4(0, 0, 0, 0), o1 = make_uint4(0, 0, 0, 0);
       const uint32_t so = sw_off(lr, sub);
       if (row0 + lr < n) {
         const uint4 self0 = lds128(hbase + so), self1 = lds128(hbase + so + kKbBytes);
-        const __half2 *s0 = reinterpret_cast<const __half2 *>(&self0);
-        const __half2 *s1 = reinterpret_cast<const __half2 *>(&self1);
-        uint32_t *p0 = reinterpret_cast<uint32_t *>(&o0), *p1 = reinterpret_cast<uint32_t *>(&o1);
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          const float2 f0 = __half22float2(s0[ch]), f1 = __half22float2(s1[ch]);
-          p0[ch] = pack2(fmaf(p.eps1, f0.x, acc[2 * ch]), fmaf(p.eps1, f0.y, acc[2 * ch + 1]));
-          p1[ch] = pack2(fmaf(p.eps1, f1.x, acc[8 + 2 * ch]), fmaf(p.eps1, f1.y, acc[8 + 2 * ch + 1]));
-        }
+        const uint32_t e1 = p.eps1_h2;
+        o0 = make_uint4(lmath::h2_fma(e1, self0.x, acc[0]), lmath::h2_fma(e1, self0.y, acc[1]),
+                        lmath::h2_fma(e1, self0.z, acc[2]), lmath::h2_fma(e1, self0.w, acc[3]));
+        o1 = make_uint4(lmath::h2_fma(e1, self1.x, acc[4]), lmath::h2_fma(e1, self1.y, acc[5]),
+                        lmath::h2_fma(e1, self1.z, acc[6]), lmath::h2_fma(e1, self1.w, acc[7]));
       }
       sts128(zbase + so, o0);
       sts128(zbase + so + kKbBytes, o1);
@@ -636,15 +595,19 @@ int fused6_layer(const gfx_model *m, int layer, const __half *h, const int32_t *
   v6::Consts c;
   const gfx_host_vectors &hv = m->host;
   for (int i = 0; i < kMlpHidden; ++i) c.b1[i] = hv.b1[size_t(layer) * kMlpHidden + i];
+  for (int i = 0; i < kHidden; ++i) {
+    c.b2[i] = hv.b2[size_t(layer) * kHidden + i];
+    c.g[i] = hv.ln_g[size_t(layer) * kHidden + i];
+    c.be[i] = hv.ln_b[size_t(layer) * kHidden + i];
+  }
   const size_t wi = size_t(layer) * kMlpHidden * kHidden;
   v6::Args a{};
   a.h = h; a.row_ptr = row_ptr; a.col_src = col_src; a.col_type = col_type;
   a.table16 = m->table16 + size_t(layer) * m->edge_dim * kHidden;
   a.w1_img = m->w1_img + wi; a.w2_img = m->w2_img + wi;
-  a.b2 = m->b2 + size_t(layer) * kHidden;
-  a.g = m->ln_g + size_t(layer) * kHidden;
-  a.b = m->ln_b + size_t(layer) * kHidden;
-  a.n = n; a.edge_dim = m->edge_dim; a.eps1 = m->eps1[layer];
+  a.n = n; a.edge_dim = m->edge_dim;
+  const uint32_t e16 = __half_as_ushort(__float2half_rn(m->eps1[layer]));
+  a.eps1_h2 = e16 | (e16 << 16);
   a.trace = g_trace;
   static const bool wide = [] {
     const char *v = getenv("GFX_FUSED_WIDE");      // developer switch: "0" = GEMM 1 as two N = 128 halves

@@ -817,10 +817,59 @@ def save_graph_shard(shard: GraphShard, tensor_path, *, metadata_path=None,
     return tensor_path, metadata_path
 
 
+_SAFETENSORS_DTYPES = {"F32": np.float32, "I32": np.int32, "U8": np.uint8, "I64": np.int64}
+
+
+def _read_safetensors_into(path: Path, allocate) -> tuple:
+    """(header metadata, {name: array}) of a safetensors file, every tensor copied ONCE from the
+    memory-mapped file into `allocate(name, shape, dtype)` (e.g. page-locked buffers).  The format
+    is an 8-byte little-endian header length, a JSON header {name: {dtype, shape, data_offsets}}
+    and the raw tensor bytes; only the dtypes a graph shard uses are accepted."""
+    import mmap
+    with open(path, "rb") as fh:
+        size = fh.seek(0, 2)
+        if size < 8:
+            raise ValueError("file too short for a safetensors header")
+        with mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ) as mm:
+            header_len = int.from_bytes(mm[:8], "little")
+            if header_len <= 0 or 8 + header_len > size:
+                raise ValueError("invalid safetensors header length")
+            header = json.loads(mm[8:8 + header_len].decode("utf-8"))
+            base = 8 + header_len
+            arrays = {}
+            view = memoryview(mm)
+            try:
+                for name, info in header.items():
+                    if name == "__metadata__":
+                        continue
+                    dtype = _SAFETENSORS_DTYPES.get(info["dtype"])
+                    if dtype is None:
+                        raise ValueError(f"unexpected dtype {info['dtype']!r} for {name}")
+                    begin, end = (int(v) for v in info["data_offsets"])
+                    shape = tuple(int(v) for v in info["shape"])
+                    count = int(np.prod(shape, dtype=np.int64)) if shape else 1
+                    if (begin < 0 or end < begin or base + end > size
+                            or end - begin != count * np.dtype(dtype).itemsize):
+                        raise ValueError(f"invalid data offsets for {name}")
+                    source = np.frombuffer(view[base + begin:base + end], dtype=dtype).reshape(shape)
+                    target = allocate(name, shape, np.dtype(dtype))
+                    np.copyto(target, source)
+                    del source
+                    arrays[name] = target
+            finally:
+                view.release()
+    return header.get("__metadata__") or {}, arrays
+
+
 def load_graph_shard(tensor_path, *, metadata_path=None,
                      expected_spec: Optional[GraphSpec] = None,
                      verify_checksum: bool = False,
-                     validation: str = "metadata") -> GraphShard:
+                     validation: str = "metadata", allocate=None) -> GraphShard:
+    """Load and validate a graph shard (reference graph.py:826-923).
+
+    `allocate(name, shape, dtype) -> ndarray` (extension): where each tensor is
+    to live, e.g. page-locked buffers of a pool; the file is then memory-mapped
+    and every tensor copied once, straight into its destination."""
     from safetensors import safe_open
     from safetensors.numpy import load_file
 
@@ -856,13 +905,17 @@ def load_graph_shard(tensor_path, *, metadata_path=None,
         if _file_sha256(tensor_path) != stored:
             raise GraphValidationError("graph shard checksum mismatch")
     try:
-        with safe_open(str(tensor_path), framework="np") as fh:
-            header = fh.metadata() or {}
+        if allocate is not None:
+            header, arrays = _read_safetensors_into(tensor_path, allocate)
+        else:
+            with safe_open(str(tensor_path), framework="np") as fh:
+                header = fh.metadata() or {}
         if (header.get("format") != GRAPH_SHARD_FORMAT
                 or header.get("format_version") != str(GRAPH_SHARD_FORMAT_VERSION)
                 or header.get("graph_spec_sha256") != spec.sha256):
             raise GraphValidationError("tensor header metadata mismatch")
-        arrays = load_file(str(tensor_path))
+        if allocate is None:
+            arrays = load_file(str(tensor_path))
     except GraphValidationError:
         raise
     except Exception as exc:

@@ -85,49 +85,98 @@ def assign_shards(node_counts: Sequence[int], world_size: int) -> List[List[int]
     return [sorted(m) for m in mine]
 
 
-class ShardPrefetcher:
-    """Iterate over shard files with the NEXT file being read (and, when
-    `pin` is set, copied into page-locked memory) on a background thread while
-    the caller works on the current one (shard I/O that
-    keeps a GPU fed).  At most `depth` loaded shards wait in the queue."""
+class _PinnedSet:
+    """One shard's worth of page-locked buffers, grown on demand and reused file after file
+    (page-locking costs ~0.6 s per GiB: it must not be paid per shard)."""
 
-    def __init__(self, paths: Sequence, *, pin: bool = True, depth: int = 1, load=None,
-                 device_index: int = None):
-        import queue
+    def __init__(self):
+        self._buffers = {}
+
+    def allocate(self, name, shape, dtype):
+        import numpy as np
+        import torch
+        nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize if shape else dtype.itemsize
+        have = self._buffers.get(name)
+        if have is None or have.numel() < nbytes:
+            grow = max(nbytes + nbytes // 8, 4096)
+            have = torch.empty((grow + 63) & ~63, dtype=torch.uint8, pin_memory=True)
+            self._buffers[name] = have
+        return have.numpy()[:nbytes].view(dtype).reshape(shape)
+
+
+class ShardPrefetcher:
+    """Iterate over shard files in order while `workers` background threads read the NEXT files:
+    each file is memory-mapped and its tensors are copied once into a reusable set of page-locked
+    buffers (`pin`), validated, and handed over in file order (shard I/O that
+    keeps a GPU fed).  At most `depth` loaded shards wait; a shard's buffers are recycled when the
+    consumer asks for the next one, so a yielded shard must not be kept across iterations."""
+
+    def __init__(self, paths: Sequence, *, pin: bool = True, depth: int = 2, load=None,
+                 device_index: int = None, workers: int = 4):
         import threading
         self._paths = [str(p) for p in paths]
         self._pin, self._load, self._device_index = pin, load, device_index
-        self._queue = queue.Queue(maxsize=max(1, int(depth)))
-        self._thread = threading.Thread(target=self._work, name="gfx-shard-prefetch", daemon=True)
-        self._thread.start()
+        self._cond = threading.Condition()
+        self._next = 0                     # next file index to hand to a worker
+        self._done = {}                    # index -> (shard, buffer set, exception)
+        workers = max(1, min(int(workers), len(self._paths) or 1))
+        self._free = [_PinnedSet() for _ in range(workers + max(1, int(depth)) + 1)] if pin else None
+        self._threads = [threading.Thread(target=self._work, name=f"gfx-shard-prefetch-{k}",
+                                          daemon=True) for k in range(workers)]
+        for t in self._threads:
+            t.start()
 
     def _work(self) -> None:
-        try:
-            load = self._load
-            if load is None:
-                from .graph import load_graph_shard as load
-            pin = None
-            if self._pin:
-                import torch
-                from .encoder import pin_shard as pin
-                if self._device_index is not None:
-                    torch.cuda.set_device(self._device_index)
-            for path in self._paths:
-                shard = load(path)
-                self._queue.put((path, pin(shard) if pin else shard, None))
-        except BaseException as exc:                  # surfaced on the consumer's thread
-            self._queue.put((None, None, exc))
-            return
-        self._queue.put((None, None, None))
+        load = self._load
+        if load is None:
+            from .graph import load_graph_shard as load
+        if self._pin and self._device_index is not None:
+            import torch
+            torch.cuda.set_device(self._device_index)
+        while True:
+            with self._cond:
+                # indices and buffer sets are handed out together, in order: the lowest outstanding
+                # file always owns a set, so the consumer can always make progress
+                while self._next < len(self._paths) and self._pin and not self._free:
+                    self._cond.wait()
+                if self._next >= len(self._paths):
+                    return
+                index = self._next
+                self._next += 1
+                buffers = self._free.pop() if self._pin else None
+            try:
+                if buffers is not None and self._load is None:
+                    shard = load(self._paths[index], allocate=buffers.allocate)
+                else:
+                    shard = load(self._paths[index])
+                    if self._pin:
+                        from .encoder import pin_shard
+                        shard = pin_shard(shard)
+                result = (shard, buffers, None)
+            except BaseException as exc:              # surfaced on the consumer's thread
+                result = (None, buffers, exc)
+            with self._cond:
+                self._done[index] = result
+                self._cond.notify_all()
 
     def __iter__(self):
-        while True:
-            path, shard, exc = self._queue.get()
+        held = None
+        for index, path in enumerate(self._paths):
+            with self._cond:
+                if held is not None:                  # the previous shard's buffers go back
+                    self._free.append(held)
+                    held = None
+                    self._cond.notify_all()
+                while index not in self._done:
+                    self._cond.wait()
+                shard, held, exc = self._done.pop(index)
             if exc is not None:
                 raise exc
-            if path is None:
-                return
             yield path, shard
+        with self._cond:
+            if held is not None:
+                self._free.append(held)
+                self._cond.notify_all()
 
 
 def encode_shard_files(encoder, paths: Sequence, *, rank: int, world_size: int,

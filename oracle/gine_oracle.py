@@ -260,8 +260,15 @@ def _h(a):
 
 
 def forward_folded(fw, x, row_ptr, col_src, col_type, *, half_storage=False,
-                   layers=4, return_intermediates=False):
+                   layers=4, return_intermediates=False, half_sums=False):
     """Folded forward over a destination-CSR graph, float32 arithmetic.
+
+    ``half_sums=True`` (with ``half_storage``) additionally models what the
+    reference's fp16 path does on a ``.half()`` module (_model.py:42-46, 68-71)
+    and what the fused sm_100a layer kernels compute: the neighbour sum is a
+    chain of fp16 additions in CSR order, the self term one fp16 fused
+    multiply-add with (1 + eps) rounded to fp16, and the LayerNorm output is
+    rounded to fp16 before the fp16 residual addition.
 
     ``half_storage=True`` models the device fp16 path: weights, tables and
     every tensor that the kernels store between stages (h, z, the hidden
@@ -281,15 +288,22 @@ def forward_folded(fw, x, row_ptr, col_src, col_type, *, half_storage=False,
     for l in range(layers):
         m = q(np.maximum(h[src] + q(fw["table"][l])[typ], 0))
         agg = np.zeros_like(h)
-        np.add.at(agg, dst, m)                       # CSR order per row
-        z = q(fw["eps1"][l] * h + agg)
+        if half_sums:
+            for k in range(int(deg.max()) if n else 0):   # k-th edge of every row that has one
+                rows = np.flatnonzero(deg > k)
+                agg[rows] = q(agg[rows] + m[row_ptr[rows] + k])
+            e16 = np.float64(np.float16(fw["eps1"][l]))
+            z = q((e16 * h.astype(np.float64) + agg.astype(np.float64)).astype(np.float32))
+        else:
+            np.add.at(agg, dst, m)                   # CSR order per row
+            z = q(fw["eps1"][l] * h + agg)
         a = q(np.maximum(z @ q(fw["w1"][l]).T + fw["b1"][l], 0))
         u = a @ q(fw["w2"][l]).T + fw["b2"][l]
         mu = u.mean(axis=1, keepdims=True)
         var = ((u - mu) ** 2).mean(axis=1, keepdims=True)
         u = (u - mu) / np.sqrt(var + np.float32(LN_EPS)) * fw["ln_g"][l] + fw["ln_b"][l]
         keep[f"z{l}"] = z
-        h = q(h + u)
+        h = q(h + q(u)) if half_sums else q(h + u)
         keep[f"h{l + 1}"] = h
     t = q(np.maximum(h @ q(fw["wa"]).T + fw["ba"], 0))
     y = t @ q(fw["wb"]).T + fw["bb"]

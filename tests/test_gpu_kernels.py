@@ -184,8 +184,11 @@ def problem(nat, dev, synthetic_state):
                                    return_intermediates=True)
     y16, keep16 = O.forward_folded(fw, shard.node_features, erp, ecs, ect,
                                    half_storage=True, return_intermediates=True)
+    # the fused layer kernels' arithmetic: fp16 sum chain, fp16 self term, fp16 residual add
+    y16s, keep16s = O.forward_folded(fw, shard.node_features, erp, ecs, ect, half_storage=True,
+                                     half_sums=True, return_intermediates=True)
     yield dict(shard=shard, fw=fw, handle=handle, csr=(rp, cs, ct),
-               y32=y32, keep32=keep32, y16=y16, keep16=keep16)
+               y32=y32, keep32=keep32, y16=y16, keep16=keep16, y16s=y16s, keep16s=keep16s)
     nat.model_destroy(handle)
 
 
@@ -370,6 +373,43 @@ def test_fused_layer_matches_oracle(nat, dev, problem, entry):
                     cs.data_ptr(), ct.data_ptr(), n, out2.data_ptr(), _stream()))
     torch.cuda.synchronize()
     assert torch.equal(out, out2)          # deterministic
+
+
+def test_fused_layers_follow_the_half_precision_chain_of_the_reference(nat, dev, problem):
+    """Both fused layer kernels against the oracle restatement of THEIR arithmetic (the reference's
+    fp16 path: fp16 message, fp16 sum chain in CSR order, fp16 fused self term, LayerNorm output
+    rounded to fp16 before the fp16 residual add; oracle.forward_folded(half_sums=True)), layer by
+    layer from the oracle's own inputs.  What may still differ is the fp32 summation order inside
+    the tensor-core GEMMs: an occasional hidden activation or LayerNorm output that sits on a
+    rounding boundary flips by one fp16 ulp, i.e. the result is within 2 ulp everywhere and equal
+    almost everywhere."""
+    keep = problem["keep16s"]
+    rp, cs, ct = problem["csr"]
+    n = keep["h0"].shape[0]
+    desc = torch.empty(n, dtype=torch.int32, device=dev)
+    nat.check(nat.lib.gfx_row_describe(rp.data_ptr(), cs.data_ptr(), ct.data_ptr(), n,
+                                       desc.data_ptr(), _stream()))
+    for layer in range(4):
+        h = _up(keep[f"h{layer}"], dev).to(torch.float16)
+        want = keep[f"h{layer + 1}"]
+        outs = []
+        for banded in (False, True):
+            out = _buf(n, 0, dev)
+            if banded:
+                nat.check(nat.lib.gfx_layer_fused_banded(
+                    problem["handle"], layer, h.data_ptr(), rp.data_ptr(), cs.data_ptr(),
+                    ct.data_ptr(), desc.data_ptr(), n, out.data_ptr(), _stream()))
+            else:
+                nat.check(nat.lib.gfx_layer_fused_pair(
+                    problem["handle"], layer, h.data_ptr(), rp.data_ptr(), cs.data_ptr(),
+                    ct.data_ptr(), n, out.data_ptr(), _stream()))
+            torch.cuda.synchronize()
+            got = out.float().cpu().numpy()
+            err = np.abs(got - want)
+            assert (err <= 2.0 ** -9 * np.maximum(1.0, np.abs(want))).all(), (layer, banded, err.max())
+            assert (got != want).mean() < 0.02, (layer, banded, (got != want).mean())
+            outs.append(out)
+        assert torch.equal(outs[0], outs[1]), layer        # the two kernels: the same bits
 
 
 @pytest.mark.parametrize("seed,count", [(41, 1), (42, 2), (43, 3), (44, 7), (45, 40), (46, 333)])
