@@ -31,7 +31,8 @@
 //    order, so the two kernels still agree bit for bit.
 //
 // Warps per CTA (24; 80 registers per thread at launch = 61,440 for the CTA, re-balanced with
-// setmaxnreg within that allocation: epilogue A 64, epilogue B 80, producers 104, utility 40):
+// setmaxnreg within that allocation: epilogue A 56, epilogue B 88, producers 104, utility 40 --
+// 128 x 56 + 256 x 88 + 256 x 104 + 128 x 40 = 61,440 exactly):
 //    0-3   epilogue A   D1 -> + b1, ReLU, fp16 -> A2 (in place)
 //    4-11  epilogue B   warp = 4 + 4 half + quad, every tile
 //   12-19  producers    warp w owns tile rows [16 w, 16 w + 16), two runs of 8 rows
@@ -200,7 +201,7 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
 
   if (warp < kEpiBWarp0) {
     // ================= epilogue A =================================================
-    reg_dec<64>();
+    reg_dec<56>();
     const uint32_t trow = tmem + (uint32_t(warp * 32) << 16);
     const uint32_t a2a = leader(kBarA2aFull), a2b = leader(kBarA2bFull);
     uint32_t it = 0;
@@ -217,6 +218,8 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
     const uint32_t xme = smem_u32(smem + L::off_x) + uint32_t(half * kTileM + r) * 8u;
     const uint32_t xother = smem_u32(smem + L::off_x) + uint32_t((half ^ 1) * kTileM + r) * 8u;
     const uint32_t named = 1u + uint32_t(quad);                    // bar.sync id of this row group
+    const uint32_t d2e[2] = {leader(kBarD2Empty), leader(kBarD2Empty + 1)};
+    reg_inc<88>();
     uint32_t it = 0;
     for (int pair = cluster_id; pair < pairs; pair += clusters, ++it) {
       const uint32_t g = it & 1, hb = it % kHBufs;
@@ -224,7 +227,13 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
       mbar_wait_s(bar + kBarD2Full + g, (it >> 1) & 1, p.sleep_ns);
       tc_fence_after();
       if (lane == 0 && warp == kEpiBWarp0) trace_ev(p, it, 8);
-      const float2 mine = half ? epi_b_partial<1>(c, tcol) : epi_b_partial<0>(c, tcol);
+      // one pass over TMEM: the 64 columns stay in registers, D2[g] is released at once
+      float t[64];
+      if (half) epi_b_load<1>(c, tcol, t); else epi_b_load<0>(c, tcol, t);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(d2e[g]);
+      const float2 mine = epi_b_stats(t);
       sts_f2(xme, mine);
       named_bar_sync(named, 64);
       const float2 other = lds_f2(xother);
@@ -237,15 +246,10 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
       const float nm = -mean * rstd;
       mbar_wait_s(bar + kBarHFull + hb, (it / kHBufs) & 1, 0);   // long complete: visibility only
       const uint32_t hrow = smem_u32(hs) + hb * kTileBytes;
-      if (half) epi_b_normalise<1>(c, tcol, hrow, r, rstd, nm);
-      else epi_b_normalise<0>(c, tcol, hrow, r, rstd, nm);
-      tc_fence_before();                         // D2[g] fully read by this warp
+      if (half) epi_b_store<1>(c, t, hrow, r, rstd, nm); else epi_b_store<0>(c, t, hrow, r, rstd, nm);
       fence_async_smem();
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive_cluster(leader(kBarD2Empty + g));
-        mbar_arrive(bar + kBarOReady + hb);
-      }
+      if (lane == 0) mbar_arrive(bar + kBarOReady + hb);
       if (lane == 0 && warp == kEpiBWarp0) trace_ev(p, it, 9);
     }
   } else if (warp < kMmaWarp) {
@@ -273,48 +277,53 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
       const int row = (2 * pr + int(rank)) * kTileM + kRowsPerWarp * pw + lane;
       return row < n ? p.desc[row] : 0u;
     };
-    // the two rows just outside the tile that the first / last warp's windows reach (global memory)
-    auto fetch_halo = [&](int pr, uint2 &x0, uint2 &x1) {
-      x0 = x1 = make_uint2(0u, 0u);
-      if (pr >= pairs || (pw != 0 && pw != kProdWarps - 1)) return;
-      const int r0 = (2 * pr + int(rank)) * kTileM;
-      const int g0 = pw == 0 ? r0 - 2 : r0 + kTileM, g1 = g0 + 1;
-      if (g0 >= 0 && g0 < n) x0 = __ldg(hg + int64_t(g0) * 32);
-      if (g1 >= 0 && g1 < n) x1 = __ldg(hg + int64_t(g1) * 32);
-    };
+    // Loads that leave the SM (the two halo rows just outside the tile that the first / last
+    // warp's windows reach, and pairing partners in other tiles) are issued a whole run (8 rows,
+    // ~250 instructions) before their first use and never carried across tile iterations: round
+    // 1's kernel prefetched the halo rows one TILE ahead, the compiler spilled them, and the
+    // spill store waited ~1.4 k cycles for the load it was meant to hide (timeline of r02_b).
     uint32_t dnext = fetch_desc(cluster_id);
-    uint2 hx0, hx1;
-    fetch_halo(cluster_id, hx0, hx1);
     uint32_t it = 0;
     for (int pair = cluster_id; pair < pairs; pair += clusters, ++it) {
       const uint32_t s = it & 1, hb = it % kHBufs;
       const int row0 = (2 * pair + int(rank)) * kTileM;
       const uint32_t d = dnext;
-      const uint2 halo0 = hx0, halo1 = hx1;
-      dnext = fetch_desc(pair + clusters);
-      fetch_halo(pair + clusters, hx0, hx1);
       const uint32_t hbase = smem_u32(hs) + hb * kTileBytes;
       const uint32_t zbase = smem_u32(zs) + s * kTileBytes;
       mbar_wait_s(bar + kBarHFull + hb, (it / kHBufs) & 1, p.sleep_ns);
       mbar_wait_s(bar + kBarA1Empty + s, ((it >> 1) & 1) ^ 1, p.sleep_ns);
       if (warp == kProdWarp0 && lane == 0) trace_ev(p, it, 0);
-      // partner row of a row with descriptor dj (a row without a pair reads itself; its message is +0)
-      auto partner = [&](uint32_t dj, int idx) -> uint2 {
+      uint2 halo0 = make_uint2(0u, 0u), halo1 = make_uint2(0u, 0u);
+      if (pw == 0 || pw == kProdWarps - 1) {               // warp-uniform
+        const int g0 = pw == 0 ? row0 - 2 : row0 + kTileM, g1 = g0 + 1;
+        if (g0 >= 0 && g0 < n) halo0 = __ldg(hg + int64_t(g0) * 32);
+        if (g1 >= 0 && g1 < n) halo1 = __ldg(hg + int64_t(g1) * 32);
+      }
+      // partner row of tile row `idx` of this warp (a row without a pair reads itself; its message is +0)
+      auto partner = [&](int idx) -> uint2 {
+        const uint32_t dj = __shfl_sync(0xffffffffu, d, idx);
         const int self = kRowsPerWarp * pw + idx;
         const int src = (dj & kDescPair) ? int((dj >> kDescPartnerShift) & kDescPartnerMask) : row0 + self;
         const uint32_t local = uint32_t(src - row0);
         const uint32_t in_tile = local < uint32_t(kTileM) ? 1u : 0u;
         return ld_tile_or_global8(in_tile, hbase + cell(int(local & (kTileM - 1))), hg + int64_t(src) * 32);
       };
+      // the first warp takes its runs in reverse: the run that needs the halo rows comes last
+      const int first_run = pw == 0 ? 1 : 0;
+      uint2 pnext[kRun];
+#pragma unroll
+      for (int q = 0; q < kRun; ++q) pnext[q] = partner(kRun * first_run + q);
 #pragma unroll 1
-      for (int run = 0; run < kRowsPerWarp / kRun; ++run) {
+      for (int step = 0; step < kRowsPerWarp / kRun; ++step) {
+        static_assert(kRowsPerWarp / kRun == 2, "two runs per warp and tile");
+        const int run = first_run ^ step;
         const int base = kRowsPerWarp * pw + kRun * run;   // first tile row of the run
         uint32_t dj[kRun];                                 // the run's descriptors, warp-uniform
 #pragma unroll
         for (int j = 0; j < kRun; ++j) dj[j] = __shfl_sync(0xffffffffu, d, kRun * run + j);
-        uint2 pr[2][4];
+        uint2 pr[kRun];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) pr[0][q] = partner(dj[q], kRun * run + q);
+        for (int q = 0; q < kRun; ++q) pr[q] = pnext[q];
         // window: tile rows base - 2 .. base + kRun + 1.  base is a multiple of 8, so the swizzle
         // term of row base - 2 + k depends on k only: one XOR with an immediate per row.  Only
         // the first two / last two rows of the window can lie outside the tile (first / last run
@@ -341,6 +350,10 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
           w[kRun + 2] = wrow(kRun + 2);
           w[kRun + 3] = wrow(kRun + 3);
         }
+        if (step == 0) {                                   // the other run's partners, a run ahead
+#pragma unroll
+          for (int q = 0; q < kRun; ++q) pnext[q] = partner(kRun * (run ^ 1) + q);
+        }
         // z = fma(1+eps, h, ((((m_prev + m_next) + m_pair) + m_prev2) + m_next2)) in fp16, the CSR
         // order of a banded row; a missing edge contributes relu(x - 65504) = +0 exactly.
         // INTERIOR: every row of the run has its four backbone / skip neighbours (all but the runs
@@ -349,11 +362,6 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
           constexpr bool INTERIOR = decltype(interior_c)::value;
 #pragma unroll
           for (int j = 0; j < kRun; ++j) {
-            if ((j & 3) == 0 && j + 4 < kRun) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q)
-                pr[((j >> 2) + 1) & 1][q] = partner(dj[j + 4 + q], kRun * run + j + 4 + q);
-            }
             const uint32_t dd = dj[j];
             uint2 t0 = INTERIOR || (dd & kDescPrev) ? tb[0] : kNone;
             uint2 t1 = INTERIOR || (dd & kDescNext) ? tb[1] : kNone;
@@ -361,7 +369,7 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
             tp = (dd & kDescPair) ? tp : kNone;
             uint2 t4 = INTERIOR || (dd & kDescPrev2) ? tb[4] : kNone;
             uint2 t5 = INTERIOR || (dd & kDescNext2) ? tb[5] : kNone;
-            const uint2 pp = pr[(j >> 2) & 1][j & 3];
+            const uint2 pp = pr[j];
             uint2 acc;
             acc.x = h2_relu_add(w[j + 1].x, t0.x);
             acc.y = h2_relu_add(w[j + 1].y, t0.y);
@@ -412,6 +420,9 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
           sts64(zbase + cell(lr), o);
         }
       }
+      // the next tile's descriptors: requested here so that nothing is live across the run loop;
+      // the load completes during the hand-over and the waits of the next iteration
+      dnext = fetch_desc(pair + clusters);
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(a1f[s]);
@@ -440,11 +451,16 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
       if (rank == 0) {
         mbar_wait_c(bar + kBarWReady, 0);
         constexpr uint32_t idesc = idesc_f16(2 * kTileM, H);     // M = 256 over the pair, N = 128
-        const uint32_t w1a = smem_u32(w1s), w2a = smem_u32(w2s);
+        // descriptors = one 64-bit base per operand + a small immediate per MMA.  The bases are
+        // laundered through an empty asm inside the tile loop: otherwise the compiler hoists all
+        // 32 descriptors of the two unrolled GEMMs out of the loop and spills them (this role
+        // runs on 40 registers).
+        uint64_t w1d = smem_desc_sw128(smem_u32(w1s)), w2d = smem_desc_sw128(smem_u32(w2s));
         uint32_t it = 0;
         for (int pair = cluster_id; pair < pairs; pair += clusters, ++it) {
           const uint32_t s = it & 1, g = it & 1, ph2 = (it >> 1) & 1, ph = it & 1;
-          const uint32_t za = smem_u32(zs) + s * kTileBytes;
+          uint64_t zd = smem_desc_sw128(smem_u32(zs) + s * kTileBytes);
+          asm volatile("" : "+l"(w1d), "+l"(w2d), "+l"(zd));
           mbar_wait_c(bar + kBarA1Full + s, ph2);
           tc_fence_after();
           trace_ev(p, it, 2);
@@ -452,9 +468,8 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk) {
             const int kb = kk >> 2, k = kk & 3;
-            const uint64_t da = smem_desc_sw128(za + kb * kKbBytes + k * 32);
-            const uint64_t db = smem_desc_sw128(w1a + kb * 2 * kWPiece + k * 32);
-            mma2_f16_ss(tmem, da, db, idesc_w, kk != 0);
+            mma2_f16_ss(tmem, zd + uint64_t((kb * kKbBytes + k * 32) >> 4),
+                        w1d + uint64_t((kb * 2 * kWPiece + k * 32) >> 4), idesc_w, kk != 0);
           }
           mma2_commit(bar + kBarD1aFull);
           mma2_commit(bar + kBarD1bFull);
@@ -464,14 +479,15 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
           mbar_wait_c(bar + kBarD2Empty + g, ph2 ^ 1);
           tc_fence_after();
           trace_ev(p, it, 4);
+          const uint32_t d2 = tmem + kD2Col + g * kHidden;
 #pragma unroll
           for (int kk = 0; kk < HID / 16; ++kk) {
             if (kk == H / 16) {
               mbar_wait_c(bar + kBarA2bFull, ph);
               tc_fence_after();
             }
-            const uint64_t db = smem_desc_sw128(w2a + (kk >> 2) * kWPiece + (kk & 3) * 32);
-            mma2_f16_ts(tmem + kD2Col + g * kHidden, tmem + kk * 8, db, idesc, kk != 0);
+            mma2_f16_ts(d2, tmem + kk * 8, w2d + uint64_t(((kk >> 2) * kWPiece + (kk & 3) * 32) >> 4),
+                        idesc, kk != 0);
           }
           mma2_commit(bar + kBarD2Full + g);
           trace_ev(p, it, 5);

@@ -194,5 +194,53 @@ __device__ __forceinline__ void epi_b_normalise_rt(const Consts &c, uint32_t tco
   epi_b_normalise_any<-1>(c, tcol, hrow, r, rstd, nm, half);
 }
 
+// ---- single pass over TMEM: the thread keeps its 64 columns in registers -------------------------
+// (TMEM reads run at ~64 B per cycle and SM: the accumulators of a tile are worth reading once.)
+// Same operations in the same order as epi_b_partial / epi_b_normalise above.
+template <int HALF>
+__device__ __forceinline__ void epi_b_load(const Consts &c, uint32_t tcol, float (&t)[64]) {
+  tmem_ld32(tcol, t);
+  tmem_ld32(tcol + 32, t + 32);
+  tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const int col = HALF * 64 + 2 * j;
+    const float2 v = f2_add(make_float2(t[2 * j], t[2 * j + 1]), make_float2(c.b2[col], c.b2[col + 1]));
+    t[2 * j] = v.x;
+    t[2 * j + 1] = v.y;
+  }
+}
+__device__ __forceinline__ float2 epi_b_stats(const float (&t)[64]) {
+  float2 s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float2 v = make_float2(t[2 * j], t[2 * j + 1]);
+    s1 = f2_add(s1, v);
+    s2 = f2_fma(v, v, s2);
+  }
+  return make_float2(s1.x + s1.y, s2.x + s2.y);
+}
+template <int HALF>
+__device__ __forceinline__ void epi_b_store(const Consts &c, const float (&t)[64], uint32_t hrow, int r,
+                                            float rstd, float nm) {
+  const float2 rs = make_float2(rstd, rstd), nmv = make_float2(nm, nm);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {                               // 16-byte chunks of this half row
+    const int c16 = HALF * 8 + k;
+    const uint32_t cell = hrow + uint32_t(c16 >> 3) * kKbBytes + sw_off(r, c16 & 7);
+    const uint4 raw = lds128(cell);
+    const uint32_t hin[4] = {raw.x, raw.y, raw.z, raw.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const int j = 8 * k + 2 * w, col = HALF * 64 + j;
+      const float2 y = f2_fma(f2_fma(make_float2(t[j], t[j + 1]), rs, nmv),
+                              make_float2(c.g[col], c.g[col + 1]), make_float2(c.be[col], c.be[col + 1]));
+      o[w] = h2_add(pack2(y.x, y.y), hin[w]);
+    }
+    sts128(cell, make_uint4(o[0], o[1], o[2], o[3]));
+  }
+}
+
 }  // namespace lmath
 }  // namespace gfx
