@@ -553,15 +553,33 @@ def c4_files(encoder, device, rank, world, barrier, files: int, records_per_file
     import ginfinity_b200 as g
     from ginfinity_b200.multi_gpu import encode_shard_files
     from ginfinity_b200.synthetic import synthetic_shard
-    root = Path(tempfile.mkdtemp(prefix=f"gfx_c4_r{rank}_", dir="/dev/shm" if Path("/dev/shm").is_dir() else None))
+    import shutil
+    need = files * records_per_file * 15_000 * world          # ~14 KB of shard file per record
+    base = None
+    for candidate in ("/dev/shm", tempfile.gettempdir()):
+        try:
+            if Path(candidate).is_dir() and shutil.disk_usage(candidate).free > 2 * need:
+                base = candidate
+                break
+        except OSError:
+            continue
+    root = Path(tempfile.mkdtemp(prefix=f"gfx_c4_r{rank}_", dir=base))
     try:
-        paths, nodes, t0 = [], 0, time.perf_counter()
-        for k in range(files):
-            shard = synthetic_shard(1000 * (rank + 1) + k, records_per_file, prefix=f"r{rank}f{k}_")
-            path = root / f"shard_{k:03d}.safetensors"
-            g.save_graph_shard(shard, path)
-            paths.append(path)
-            nodes += shard.node_count
+        paths, nodes, t0, failure = [], 0, time.perf_counter(), None
+        try:
+            for k in range(files):
+                shard = synthetic_shard(1000 * (rank + 1) + k, records_per_file, prefix=f"r{rank}f{k}_")
+                path = root / f"shard_{k:03d}.safetensors"
+                g.save_graph_shard(shard, path)
+                paths.append(path)
+                nodes += shard.node_count
+        except Exception as exc:  # noqa: BLE001 -- every rank must reach the collective below
+            failure = f"{type(exc).__name__}: {exc}"[:200]
+        ok = torch.tensor([0.0 if failure else 1.0], device=device)
+        if world > 1:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() != 1.0:
+            return {"error": failure or "another rank could not write its shard files"}
         write_s = time.perf_counter() - t0
         nbytes = sum(p.stat().st_size for p in paths)
         barrier()
@@ -583,7 +601,6 @@ def c4_files(encoder, device, rank, world, barrier, files: int, records_per_file
                 "where": str(root.parent), "seconds": secs.item(),
                 "nt_per_s": total.item() / secs.item(), "generation_and_write_s": write_s}
     finally:
-        import shutil
         shutil.rmtree(root, ignore_errors=True)
 
 

@@ -13,7 +13,7 @@ import numpy as np
 _LIB_PATH = Path(__file__).resolve().parent / "libgfx.so"
 
 GFX_F16, GFX_F32 = 0, 1
-IMPL_AUTO, IMPL_SIMT, IMPL_UMMA, IMPL_UMMA_LEAN = 0, 1, 2, 5
+IMPL_AUTO, IMPL_SIMT, IMPL_UMMA, IMPL_UMMA_LEAN, IMPL_SPLIT = 0, 1, 2, 5, 8
 
 
 class NativeError(RuntimeError):

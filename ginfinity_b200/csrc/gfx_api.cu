@@ -89,7 +89,8 @@ static std::vector<float> copy(const float *w, size_t n, bool quantise) {
 // is k/64 consecutive tiles; tile kb holds columns [64kb, 64kb+64) as `rows`
 // rows of 128 bytes whose eight 16-byte chunks are XOR-swizzled with (row&7)
 // (the SWIZZLE_128B canonical layout; 8-row groups are 1024 bytes apart).
-static void append_umma_image(std::vector<__half> &img, const float *w, int rows, int k) {
+// `lo` selects the second part of the fp16 split w = hi + lo (hi = fp16(w), lo = fp16(w - hi)).
+static void append_umma_image(std::vector<__half> &img, const float *w, int rows, int k, bool lo = false) {
   size_t base = img.size();
   img.resize(base + size_t(rows) * k);
   for (int kb = 0; kb < k / 64; ++kb)
@@ -97,7 +98,9 @@ static void append_umma_image(std::vector<__half> &img, const float *w, int rows
       for (int c = 0; c < 8; ++c)
         for (int j = 0; j < 8; ++j) {
           size_t dst = base + size_t(kb) * rows * 64 + size_t(r) * 64 + size_t((c ^ (r & 7)) * 8 + j);
-          img[dst] = __float2half_rn(w[size_t(r) * k + kb * 64 + c * 8 + j]);
+          const float v = w[size_t(r) * k + kb * 64 + c * 8 + j];
+          const __half hi = __float2half_rn(v);
+          img[dst] = lo ? __float2half_rn(v - __half2float(hi)) : hi;
         }
 }
 
@@ -185,6 +188,14 @@ extern "C" int gfx_model_create(const gfx_folded_weights *w, gfx_model **out) {
   append_umma_image(ia, w->wa_host, H, H);
   append_umma_image(ib, w->wb_host, H, H);
   size_t o_i1 = ab.put(i1), o_i2 = ab.put(i2), o_ia = ab.put(ia), o_ib = ab.put(ib);
+  std::vector<__half> l1, l2, la, lb;
+  for (int l = 0; l < L; ++l) {
+    append_umma_image(l1, w->w1_host + size_t(l) * M * H, M, H, true);
+    append_umma_image(l2, w->w2_host + size_t(l) * H * M, H, M, true);
+  }
+  append_umma_image(la, w->wa_host, H, H, true);
+  append_umma_image(lb, w->wb_host, H, H, true);
+  size_t o_l1 = ab.put(l1), o_l2 = ab.put(l2), o_la = ab.put(la), o_lb = ab.put(lb);
   std::vector<__half> t16(size_t(L) * ED * H);
   for (size_t i = 0; i < t16.size(); ++i) t16[i] = __float2half_rn(w->table_host[i]);
   size_t o_t16 = ab.put(t16);
@@ -216,6 +227,7 @@ extern "C" int gfx_model_create(const gfx_folded_weights *w, gfx_model **out) {
   m->b_in = f(o_b_in); m->b1 = f(o_b1); m->b2 = f(o_b2); m->ln_g = f(o_g); m->ln_b = f(o_b);
   m->ba = f(o_ba); m->bb = f(o_bb);
   m->w1_img = h(o_i1); m->w2_img = h(o_i2); m->wa_img = h(o_ia); m->wb_img = h(o_ib); m->table16 = h(o_t16);
+  m->w1_lo_img = h(o_l1); m->w2_lo_img = h(o_l2); m->wa_lo_img = h(o_la); m->wb_lo_img = h(o_lb);
   *out = m;
   return GFX_OK;
 }

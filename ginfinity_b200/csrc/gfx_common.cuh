@@ -96,5 +96,8 @@ struct gfx_model {
   const __half *wa_img;   //       (2 kblocks x 128 rows x 64)   = 32 KB
   const __half *wb_img;   //       (2 kblocks x 128 rows x 64)   = 32 KB
   const __half *table16;  // [L][edge_dim][H] fp16 (fused layer kernel)
+  // lo parts of the same images, lo = fp16(w - fp16(w)): the split-fp16 tensor-core kernels of
+  // the fp32 path (gfx_split9.cu) multiply by hi + lo
+  const __half *w1_lo_img, *w2_lo_img, *wa_lo_img, *wb_lo_img;
   gfx_host_vectors host;
 };

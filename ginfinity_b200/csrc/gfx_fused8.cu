@@ -105,6 +105,7 @@ struct Args {
   int edge_dim;
   uint32_t eps1_h2;          // (1 + eps) rounded to fp16, in both halves of the word
   long long *trace;          // developer timeline (tools/fused_trace.py); null in production
+  uint32_t dbg;              // developer experiments (GFX_DBG): timing only, results are wrong
 };
 
 __device__ __forceinline__ void mbar_wait_c(uint64_t *bar, uint32_t parity) {
@@ -119,12 +120,12 @@ __device__ __forceinline__ void mbar_wait_s(uint64_t *bar, uint32_t parity, uint
 // ---- epilogue A: D1[:, HALF*128 .. +128) -> + b1, ReLU -> fp16 -> A2[:, HALF*64 .. +64) ---------
 template <int HALF>
 __device__ __forceinline__ void epi_a(const Consts &c, uint32_t trow, uint64_t *bar, uint32_t ph,
-                                      int lane, uint32_t leader_bar, uint32_t sleep_ns) {
+                                      int lane, uint32_t leader_bar, uint32_t sleep_ns, bool skip) {
   constexpr int col0 = HALF * H;
   mbar_wait_s(bar + (HALF ? kBarD1bFull : kBarD1aFull), ph, sleep_ns);
   tc_fence_after();
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
+  for (int q = 0; q < (skip ? 0 : 4); ++q) {
     float v[32];
     tmem_ld32(trow + col0 + 32 * q, v);
     tmem_ld_wait();
@@ -207,8 +208,8 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
     uint32_t it = 0;
     for (int pair = cluster_id; pair < pairs; pair += clusters, ++it) {
       if (tid == 0) trace_ev(p, it, 6);
-      epi_a<0>(c, trow, bar, it & 1, lane, a2a, p.sleep_ns);
-      epi_a<1>(c, trow, bar, it & 1, lane, a2b, p.sleep_ns);
+      epi_a<0>(c, trow, bar, it & 1, lane, a2a, p.sleep_ns, (p.dbg & 16u) != 0u);
+      epi_a<1>(c, trow, bar, it & 1, lane, a2b, p.sleep_ns, (p.dbg & 16u) != 0u);
       if (tid == 0) trace_ev(p, it, 7);
     }
   } else if (warp < kProdWarp0) {
@@ -229,7 +230,10 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
       if (lane == 0 && warp == kEpiBWarp0) trace_ev(p, it, 8);
       // one pass over TMEM: the 64 columns stay in registers, D2[g] is released at once
       float t[64];
-      if (half) epi_b_load<1>(c, tcol, t); else epi_b_load<0>(c, tcol, t);
+      if (p.dbg & 8u) {
+#pragma unroll
+        for (int j = 0; j < 64; ++j) t[j] = 1.f;
+      } else if (half) epi_b_load<1>(c, tcol, t); else epi_b_load<0>(c, tcol, t);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(d2e[g]);
@@ -246,7 +250,8 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
       const float nm = -mean * rstd;
       mbar_wait_s(bar + kBarHFull + hb, (it / kHBufs) & 1, 0);   // long complete: visibility only
       const uint32_t hrow = smem_u32(hs) + hb * kTileBytes;
-      if (half) epi_b_store<1>(c, t, hrow, r, rstd, nm); else epi_b_store<0>(c, t, hrow, r, rstd, nm);
+      if (p.dbg & 8u) {
+      } else if (half) epi_b_store<1>(c, t, hrow, r, rstd, nm); else epi_b_store<0>(c, t, hrow, r, rstd, nm);
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar + kBarOReady + hb);
@@ -293,8 +298,9 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
       mbar_wait_s(bar + kBarHFull + hb, (it / kHBufs) & 1, p.sleep_ns);
       mbar_wait_s(bar + kBarA1Empty + s, ((it >> 1) & 1) ^ 1, p.sleep_ns);
       if (warp == kProdWarp0 && lane == 0) trace_ev(p, it, 0);
+      if (warp == kProdWarp0 + 3 && lane == 0) trace_ev(p, it, 13);
       uint2 halo0 = make_uint2(0u, 0u), halo1 = make_uint2(0u, 0u);
-      if (pw == 0 || pw == kProdWarps - 1) {               // warp-uniform
+      if ((pw == 0 || pw == kProdWarps - 1) && !(p.dbg & 2u)) {               // warp-uniform
         const int g0 = pw == 0 ? row0 - 2 : row0 + kTileM, g1 = g0 + 1;
         if (g0 >= 0 && g0 < n) halo0 = __ldg(hg + int64_t(g0) * 32);
         if (g1 >= 0 && g1 < n) halo1 = __ldg(hg + int64_t(g1) * 32);
@@ -305,7 +311,7 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
         const int self = kRowsPerWarp * pw + idx;
         const int src = (dj & kDescPair) ? int((dj >> kDescPartnerShift) & kDescPartnerMask) : row0 + self;
         const uint32_t local = uint32_t(src - row0);
-        const uint32_t in_tile = local < uint32_t(kTileM) ? 1u : 0u;
+        const uint32_t in_tile = (local < uint32_t(kTileM) || (p.dbg & 1u)) ? 1u : 0u;
         return ld_tile_or_global8(in_tile, hbase + cell(int(local & (kTileM - 1))), hg + int64_t(src) * 32);
       };
       // the first warp takes its runs in reverse: the run that needs the halo rows comes last
@@ -314,7 +320,7 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
 #pragma unroll
       for (int q = 0; q < kRun; ++q) pnext[q] = partner(kRun * first_run + q);
 #pragma unroll 1
-      for (int step = 0; step < kRowsPerWarp / kRun; ++step) {
+      for (int step = 0; step < ((p.dbg & 32u) ? 0 : kRowsPerWarp / kRun); ++step) {
         static_assert(kRowsPerWarp / kRun == 2, "two runs per warp and tile");
         const int run = first_run ^ step;
         const int base = kRowsPerWarp * pw + kRun * run;   // first tile row of the run
@@ -423,7 +429,9 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
       // the next tile's descriptors: requested here so that nothing is live across the run loop;
       // the load completes during the hand-over and the waits of the next iteration
       dnext = fetch_desc(pair + clusters);
-      fence_async_smem();
+      if (warp == kProdWarp0 && lane == 0) trace_ev(p, it, 15);
+      if (warp == kProdWarp0 + 3 && lane == 0) trace_ev(p, it, 14);
+      if (!(p.dbg & 4u)) fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(a1f[s]);
       if (warp == kProdWarp0 && lane == 0) trace_ev(p, it, 1);
@@ -591,6 +599,11 @@ int fused8_layer(const gfx_model *m, int layer, const __half *h, const int32_t *
     return uint32_t(v ? atoi(v) : 64);
   }();
   a.sleep_ns = sleep_ns;
+  static const uint32_t dbg = [] {
+    const char *v = getenv("GFX_DBG");
+    return uint32_t(v ? atoi(v) : 0);
+  }();
+  a.dbg = dbg;
   auto kernel = v8::fused_banded8_kernel;
   GFX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v8::Smem::total));
   const int64_t tiles = (n + v8::kTileM - 1) / v8::kTileM;

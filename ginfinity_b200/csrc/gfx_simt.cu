@@ -626,6 +626,11 @@ int umma_head_l2norm(const gfx_model *m, const __half *h, const int32_t *out_row
                      void *out, int out_dtype, cudaStream_t st);
 int umma4_mlp_ln_residual(const gfx_model *m, int layer, const __half *z, const __half *h,
                           int64_t n, __half *h_out, cudaStream_t st);
+// implemented in gfx_split9.cu: fp32 storage on the tensor cores (split-fp16 GEMMs)
+int split9_mlp_ln_residual(const gfx_model *m, int layer, const float *z, const float *h, int64_t n,
+                           float *h_out, cudaStream_t st);
+int split9_head_l2norm(const gfx_model *m, const float *h, const int32_t *out_row, int64_t n, void *out,
+                       int out_dtype, cudaStream_t st);
 // implemented in gfx_head8.cu: fp16 in, fp16 out, identity row map
 int head8_l2norm(const gfx_model *m, const __half *h, int64_t n, __half *out, cudaStream_t st);
 
@@ -707,7 +712,15 @@ extern "C" int gfx_mlp_ln_residual(const gfx_model *m, int layer, const void *z,
   cudaStream_t st = as_stream(stream);
   const int H = kHidden, M = kMlpHidden;
   StageScope scope(GFX_STAGE_MLP, st, 1);
-  if (impl == GFX_IMPL_AUTO) impl = dtype == GFX_F16 ? GFX_IMPL_UMMA_LEAN : GFX_IMPL_SIMT;
+  if (impl == GFX_IMPL_AUTO) impl = dtype == GFX_F16 ? GFX_IMPL_UMMA_LEAN : GFX_IMPL_SPLIT;
+  if (impl == GFX_IMPL_SPLIT) {
+    if (dtype != GFX_F32)
+      return fail(GFX_ERR_UNSUPPORTED, "split-fp16 tcgen05 MLP is the GFX_F32 path");
+    if (n >= (int64_t(1) << 31) - 256)
+      return fail(GFX_ERR_ARGUMENT, "split-fp16 tcgen05 MLP: node count must fit int32");
+    return split9_mlp_ln_residual(m, layer, static_cast<const float *>(z), static_cast<const float *>(h),
+                                  n, static_cast<float *>(h_out), st);
+  }
   if (impl == GFX_IMPL_UMMA || impl == GFX_IMPL_UMMA_LEAN) {
     if (dtype != GFX_F16)
       return fail(GFX_ERR_UNSUPPORTED, "tcgen05 MLP exists for GFX_F16 only");
@@ -716,7 +729,7 @@ extern "C" int gfx_mlp_ln_residual(const gfx_model *m, int layer, const void *z,
               static_cast<__half *>(h_out), st);
   }
   if (impl != GFX_IMPL_SIMT)
-    return fail(GFX_ERR_ARGUMENT, "gfx_mlp_ln_residual: unknown impl (0 auto, 1 SIMT, 2 tcgen05, 5 lean tcgen05)");
+    return fail(GFX_ERR_ARGUMENT, "gfx_mlp_ln_residual: unknown impl (0 auto, 1 SIMT, 2 tcgen05, 5 lean tcgen05, 8 split tcgen05)");
   const int q = dtype == GFX_F16 ? 1 : 0;
   const float *w1t = m->w1t[q] + size_t(layer) * H * M, *b1 = m->b1 + size_t(layer) * M;
   const float *w2t = m->w2t[q] + size_t(layer) * M * H, *b2 = m->b2 + size_t(layer) * H;
@@ -746,7 +759,14 @@ extern "C" int gfx_head_l2norm(const gfx_model *m, const void *h, const int32_t 
   if (impl == GFX_IMPL_AUTO && dtype == GFX_F16 && out_dtype == GFX_F16 && out_row == nullptr &&
       n <= (int64_t(1) << 30) && !((reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(out)) & 15))
     return head8_l2norm(m, static_cast<const __half *>(h), n, static_cast<__half *>(out), st);
-  if (impl == GFX_IMPL_AUTO) impl = dtype == GFX_F16 ? GFX_IMPL_UMMA : GFX_IMPL_SIMT;
+  if (impl == GFX_IMPL_AUTO) impl = dtype == GFX_F16 ? GFX_IMPL_UMMA : GFX_IMPL_SPLIT;
+  if (impl == GFX_IMPL_SPLIT) {
+    if (dtype != GFX_F32)
+      return fail(GFX_ERR_UNSUPPORTED, "split-fp16 tcgen05 head is the GFX_F32 path");
+    if (n >= (int64_t(1) << 31) - 256)
+      return fail(GFX_ERR_ARGUMENT, "split-fp16 tcgen05 head: node count must fit int32");
+    return split9_head_l2norm(m, static_cast<const float *>(h), out_row, n, out, out_dtype, st);
+  }
   if (impl == GFX_IMPL_UMMA_LEAN) impl = GFX_IMPL_UMMA;  // head: general tcgen05 kernel
   if (impl == GFX_IMPL_UMMA) {
     if (dtype != GFX_F16)
@@ -754,7 +774,7 @@ extern "C" int gfx_head_l2norm(const gfx_model *m, const void *h, const int32_t 
     return umma_head_l2norm(m, static_cast<const __half *>(h), out_row, n, out, out_dtype, st);
   }
   if (impl != GFX_IMPL_SIMT)
-    return fail(GFX_ERR_ARGUMENT, "gfx_head_l2norm: unknown impl (0 auto, 1 SIMT, 2 tcgen05)");
+    return fail(GFX_ERR_ARGUMENT, "gfx_head_l2norm: unknown impl (0 auto, 1 SIMT, 2 tcgen05, 8 split tcgen05)");
   const int q = dtype == GFX_F16 ? 1 : 0;
   if (dtype == GFX_F16 && out_dtype == GFX_F16)
     return launch_mlp<__half, __half, kHidden, 1, true>(

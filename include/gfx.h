@@ -46,12 +46,15 @@ enum { GFX_F16 = 0, GFX_F32 = 1 };
 
 /* which implementation runs the dense stages */
 enum {
-  GFX_IMPL_AUTO = 0,  /* tcgen05 for GFX_F16, SIMT for GFX_F32 */
+  GFX_IMPL_AUTO = 0,  /* tcgen05 for GFX_F16, split-fp16 tcgen05 for GFX_F32 */
   GFX_IMPL_SIMT = 1,  /* CUDA-core fp32-accumulate kernels */
   GFX_IMPL_UMMA = 2,  /* general tcgen05.mma / TMEM kernel (GFX_F16 only; cross-check) */
-  GFX_IMPL_UMMA_LEAN = 5 /* K2 default: TMA tile I/O + 16 lean epilogue warps, constants as
-                            kernel parameters (codes 3, 4, 6, 7 named variants that were
-                            measured in round 1 and removed; they are rejected) */
+  GFX_IMPL_UMMA_LEAN = 5, /* K2 default: TMA tile I/O + 16 lean epilogue warps, constants as
+                             kernel parameters (codes 3, 4, 6, 7 named variants that were
+                             measured in round 1 and removed; they are rejected) */
+  GFX_IMPL_SPLIT = 8      /* GFX_F32 default for K2 / K3: every fp32 operand as fp16 hi + lo, three
+                             tcgen05 MMAs per product on CTA pairs (fp32-grade results: the
+                             reference's full_precision path on the tensor cores) */
 };
 
 int gfx_abi_version(void);

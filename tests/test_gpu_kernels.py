@@ -296,9 +296,10 @@ def test_aggregate_irregular_rows(nat, dev, problem, n):
     assert (got != want).mean() < 0.02
 
 
-@pytest.mark.parametrize("code,impl", [(1, 1), (0, 1), (0, 2), (0, 5)])
+@pytest.mark.parametrize("code,impl", [(1, 1), (1, 0), (1, 8), (0, 1), (0, 2), (0, 5)])
 def test_mlp_layernorm_residual_layer0(nat, dev, problem, code, impl):
-    """K2 (SIMT fp32, SIMT fp16-storage, general tcgen05, lean tcgen05 + TMA) against the oracle's h1."""
+    """K2 (SIMT fp32, split-fp16 tcgen05 for fp32 storage -- the GFX_F32 default --, SIMT fp16-storage,
+    general tcgen05, lean tcgen05 + TMA) against the oracle's h1."""
     keep = problem["keep32" if code == 1 else "keep16"]
     tdt = torch.float32 if code == 1 else torch.float16
     n = keep["h0"].shape[0]
@@ -316,7 +317,7 @@ def test_mlp_layernorm_residual_layer0(nat, dev, problem, code, impl):
     assert err <= (2e-5 if code == 1 else 4e-3) * scale, (err, scale)
 
 
-@pytest.mark.parametrize("code,impl,out_code", [(1, 1, 1), (0, 1, 0), (0, 2, 0), (0, 2, 1), (0, 0, 0), (0, 0, 1)])
+@pytest.mark.parametrize("code,impl,out_code", [(1, 1, 1), (1, 0, 1), (1, 8, 0), (0, 1, 0), (0, 2, 0), (0, 2, 1), (0, 0, 0), (0, 0, 1)])
 def test_head_l2norm(nat, dev, problem, code, impl, out_code):
     keep = problem["keep32" if code == 1 else "keep16"]
     y = problem["y32" if code == 1 else "y16"]
@@ -564,7 +565,45 @@ def test_mlp_lean_kernel_many_tiles(nat, dev, problem, n):
     assert diff <= 4e-3 * max(1.0, outs[0][:n].float().abs().max().item()), (n, diff)
 
 
-@pytest.mark.parametrize("code,impl,fused", [(1, 1, 0), (0, 1, 0), (0, 2, 0), (0, 5, 0), (0, 5, 2), (0, 5, 3)])
+@pytest.mark.parametrize("n", [1, 127, 129, 128 * 3 + 5, 128 * 148 * 2 + 128 + 17])
+def test_split_tensor_core_kernels_for_fp32_storage(nat, dev, problem, n):
+    """full_precision on the tensor cores (gfx_split9.cu: every fp32 operand as fp16 hi + lo, three
+    MMAs per product) against the CUDA-core fp32 kernels on the same inputs: ragged sizes, odd tile
+    counts (rank 1 of the last pair idle), several tiles per CTA pair, rows past n untouched, the
+    core-row map of the head.  The split is good to 2^-22 per operand: the two paths agree to
+    fp32 summation-order noise."""
+    g = torch.Generator(device="cpu").manual_seed(n)
+    z = (torch.randn(n, 128, generator=g) * 6).to(dev)
+    h = (torch.randn(n, 128, generator=g) * 3).to(dev)
+    for layer in (0, 3):
+        want = torch.empty((n, 128), dtype=torch.float32, device=dev)
+        got = torch.full((n + 256, 128), 7.0, dtype=torch.float32, device=dev)
+        nat.check(nat.lib.gfx_mlp_ln_residual(problem["handle"], layer, z.data_ptr(), h.data_ptr(), n,
+                                              want.data_ptr(), 1, 1, _stream()))
+        nat.check(nat.lib.gfx_mlp_ln_residual(problem["handle"], layer, z.data_ptr(), h.data_ptr(), n,
+                                              got.data_ptr(), 1, 8, _stream()))
+        torch.cuda.synchronize()
+        assert torch.all(got[n:] == 7.0)
+        assert (got[:n] - want).abs().max().item() <= 2e-5 * max(1.0, want.abs().max().item()), layer
+    # head with a core-row map that drops every third row
+    keep = torch.arange(n, device=dev) % 3 != 0
+    out_row = torch.where(keep, torch.cumsum(keep.int(), 0) - 1, torch.full((n,), -1, device=dev)).int()
+    rows = int(keep.sum().item())
+    for out_code, tdt in ((1, torch.float32), (0, torch.float16)):
+        want = torch.full((rows + 8, 128), 7.0, dtype=tdt, device=dev)
+        got = torch.full((rows + 8, 128), 7.0, dtype=tdt, device=dev)
+        nat.check(nat.lib.gfx_head_l2norm(problem["handle"], h.data_ptr(), out_row.data_ptr(), n,
+                                          want.data_ptr(), 1, out_code, 1, _stream()))
+        nat.check(nat.lib.gfx_head_l2norm(problem["handle"], h.data_ptr(), out_row.data_ptr(), n,
+                                          got.data_ptr(), 1, out_code, 8, _stream()))
+        torch.cuda.synchronize()
+        assert torch.all(got[rows:] == 7.0)
+        tol = 2e-6 if out_code == 1 else 1e-3
+        if rows:
+            assert (got[:rows].float() - want[:rows].float()).abs().max().item() <= tol, out_code
+
+
+@pytest.mark.parametrize("code,impl,fused", [(1, 1, 0), (1, 0, 0), (0, 1, 0), (0, 2, 0), (0, 5, 0), (0, 5, 2), (0, 5, 3)])
 def test_whole_forward(nat, dev, problem, code, impl, fused):
     """gfx_encode (all stages chained on device) against the oracle."""
     x = _up(problem["shard"].node_features, dev)

@@ -64,13 +64,13 @@ t = full[:1024].reshape(64, 16)
 spans = full[1024:].reshape(-1, 2)
 t0 = t[t > 0].min()
 names = ["prodS", "prodE", "A1full", "mma1", "A2+D2e", "mma2", "epiA_S", "epiA_E", "epiB_S", "epiB_E",
-         "stO", "stE", "load"]
+         "stO", "stE", "load", "w15S", "w15E", "w12E"]
 print("cycles since first stamp (CTA 0); tile iterations down")
 print("it   " + " ".join(f"{n:>7}" for n in names))
 for it in range(40):
     if not t[it].any():
         break
-    print(f"{it:3d}  " + " ".join(f"{(t[it, k] - t0) if t[it, k] else -1:7d}" for k in range(13)))
+    print(f"{it:3d}  " + " ".join(f"{(t[it, k] - t0) if t[it, k] else -1:7d}" for k in range(16)))
 live = spans[spans[:, 0] > 0]
 if len(live):
     s0 = live[:, 0].min()
