@@ -279,7 +279,7 @@ extern "C" int gfx_encode(const gfx_model *model, const float *x, const int32_t 
     if (rc) return rc;
   }
   for (int l = 0; l < model->layers; ++l) {
-    if (fused == 3) {   // CTA pairs, banded producers (gfx_fused7.cu)
+    if (fused == 3) {   // CTA pairs, banded producers (gfx_fused8.cu)
       rc = gfx_layer_fused_banded(model, l, h, row_ptr, col_src, col_type, desc, n, h2, stream);
       if (rc) return rc;
     } else if (fused) {   // CTA pairs, producers walk the CSR arrays (gfx_fused6.cu)

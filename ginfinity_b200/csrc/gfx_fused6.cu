@@ -576,7 +576,7 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Con
 
 }  // namespace v6
 
-long long *g_trace = nullptr;       // shared with gfx_fused7.cu
+long long *g_trace = nullptr;       // shared with gfx_fused8.cu
 
 int fused6_layer(const gfx_model *m, int layer, const __half *h, const int32_t *row_ptr,
                  const int32_t *col_src, const uint8_t *col_type, int64_t n, __half *h_out,

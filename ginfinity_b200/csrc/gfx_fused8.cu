@@ -3,7 +3,7 @@
 //   h_out = h + LayerNorm(W2 relu(W1' z + b1') + b2),
 //   z_i   = (1+eps) h_i + sum_{e: dst=i} relu(h[src_e] + table[type_e])
 //
-// The skeleton is gfx_fused7.cu's (CTA pairs, tcgen05 cta_group::2, weights split across the pair,
+// The skeleton is round 1's (gfx_fused7.cu in the history: CTA pairs, tcgen05 cta_group::2, weights split across the pair,
 // three resident h-tile buffers that are neighbour source + residual + output staging, two z
 // stages, D1 overwritten in place by the fp16 hidden activation, D2 double-buffered).  Round 1's
 // captures said what bounded it (profiles/r01_j_full_encoder_kernels.txt): 170 warp
@@ -66,7 +66,7 @@ constexpr int kEpiBWarp0 = 4, kEpiBWarps = 8, kProdWarp0 = 12, kProdWarps = 8, k
 constexpr int kRowsPerWarp = kTileM / kProdWarps;     // 16 consecutive rows of a tile per producer warp
 constexpr int kRun = 8;                               // rows per register window
 static_assert(kRowsPerWarp % kRun == 0 && kRun % 4 == 0, "runs of whole partner groups");
-// row descriptor (gfx_row_describe, gfx_fused7.cu)
+// row descriptor (gfx_row_describe, below)
 constexpr uint32_t kDescPrev = 1u, kDescNext = 2u, kDescPair = 4u, kDescPairRev = 8u, kDescPrev2 = 16u,
                    kDescNext2 = 32u, kDescGeneric = 0x80000000u;
 constexpr int kDescPartnerShift = 6, kDescPartnerBits = 25;
@@ -561,6 +561,31 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
 
 }  // namespace v8
 
+// ---- row descriptors ---------------------------------------------------------------------------
+// One thread per CSR row: does the row read, in order, (i-1, type 0) (i+1, type 1)
+// [(any, type 2|3)] (i-2, type 4) (i+2, type 5), each optional, and nothing else?
+__global__ void __launch_bounds__(256)
+row_describe_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col_src,
+                    const uint8_t *__restrict__ col_type, int64_t n, uint32_t *__restrict__ desc) {
+  using namespace v8;
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int end = row_ptr[i + 1];
+  int k = row_ptr[i];
+  uint32_t d = 0;
+  auto is = [&](int64_t src, int type) { return k < end && col_src[k] == src && col_type[k] == type; };
+  if (is(i - 1, 0)) { d |= kDescPrev; ++k; }
+  if (is(i + 1, 1)) { d |= kDescNext; ++k; }
+  if (k < end && (col_type[k] == 2 || col_type[k] == 3) && col_src[k] >= 0 &&
+      uint32_t(col_src[k]) <= kDescPartnerMask) {
+    d |= kDescPair | (col_type[k] == 3 ? kDescPairRev : 0u) | (uint32_t(col_src[k]) << kDescPartnerShift);
+    ++k;
+  }
+  if (is(i - 2, 4)) { d |= kDescPrev2; ++k; }
+  if (is(i + 2, 5)) { d |= kDescNext2; ++k; }
+  desc[i] = k == end ? d : kDescGeneric;
+}
+
 extern long long *g_trace;              // gfx_fused6.cu (gfx_debug_fused_trace)
 
 int fused8_layer(const gfx_model *m, int layer, const __half *h, const int32_t *row_ptr,
@@ -640,3 +665,30 @@ int fused8_layer(const gfx_model *m, int layer, const __half *h, const int32_t *
 }
 
 }  // namespace gfx
+
+extern "C" int gfx_row_describe(const int32_t *row_ptr, const int32_t *col_src,
+                                const uint8_t *col_type, int64_t n, uint32_t *desc, void *stream) {
+  using namespace gfx;
+  if (n <= 0) return GFX_OK;
+  if (!row_ptr || !desc) return fail(GFX_ERR_ARGUMENT, "gfx_row_describe: null array");
+  cudaStream_t st = as_stream(stream);
+  StageScope scope(GFX_STAGE_CSR, st, 1);
+  row_describe_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(row_ptr, col_src, col_type, n, desc);
+  GFX_LAUNCH_CHECK();
+  return GFX_OK;
+}
+
+extern "C" int gfx_layer_fused_banded(const gfx_model *m, int layer, const void *h,
+                                      const int32_t *row_ptr, const int32_t *col_src,
+                                      const uint8_t *col_type, const uint32_t *desc, int64_t n,
+                                      void *h_out, void *stream) {
+  using namespace gfx;
+  if (!m || layer < 0 || layer >= m->layers)
+    return fail(GFX_ERR_ARGUMENT, "gfx_layer_fused_banded: bad model or layer");
+  if (n <= 0) return GFX_OK;
+  if (!desc) return fail(GFX_ERR_ARGUMENT, "gfx_layer_fused_banded: null row descriptors");
+  cudaStream_t st = as_stream(stream);
+  StageScope scope(GFX_STAGE_FUSED_LAYER, st, 1);
+  return fused8_layer(m, layer, static_cast<const __half *>(h), row_ptr, col_src, col_type, desc, n,
+                      static_cast<__half *>(h_out), st);
+}

@@ -179,29 +179,73 @@ class ShardPrefetcher:
                 self._cond.notify_all()
 
 
+def shard_file_node_count(path) -> int:
+    """Node total of a graph-shard file from the safetensors header alone (8-byte length + a
+    small JSON header): the row count of `node_features`.  The JSON sidecar also has it, but
+    carries every sequence and structure string of the shard (megabytes to parse)."""
+    import json
+    with open(path, "rb") as fh:
+        size = int.from_bytes(fh.read(8), "little")
+        header = json.loads(fh.read(size).decode("utf-8"))
+    return int(header["node_features"]["shape"][0])
+
+
 def encode_shard_files(encoder, paths: Sequence, *, rank: int, world_size: int,
                        node_counts: Sequence[int] = None, prefetch: bool = True,
-                       **encode_kwargs) -> Dict[str, list]:
+                       consume=None, workers: int = 2, **encode_kwargs) -> Dict[str, list]:
     """Encode this rank's share of a list of graph-shard files (the
     reference's `embed-graphs` unit of work, cli.py:139-197).  Every rank must
-    pass the same `paths`; when `node_counts` is not given the JSON sidecars
-    are read for the node totals.  With `prefetch` the next file is loaded and
-    pinned while the current one is on the GPU.  Returns {path: [embeddings
-    per record]}."""
-    import json
+    pass the same `paths`; when `node_counts` is not given the safetensors
+    headers are read for the node totals.  With `prefetch` the next files are
+    memory-mapped, copied into reusable page-locked buffers and validated on
+    background threads while the current one is on the GPU.
 
-    from .graph import graph_metadata_path, load_graph_shard
+    Results.  Every shard's embeddings land in ONE page-locked table that is
+    reused from shard to shard (page-locking a fresh table per shard costs
+    ~0.6 s per GiB -- more than the encode).  `consume(path, arrays)`, when
+    given, is called with row-range views of that table and must be done with
+    them when it returns (write them out, reduce them, send them on); the
+    function then returns {path: record count}.  Without `consume` the arrays
+    are copied out into ordinary memory and returned as {path: [embeddings per
+    record]}."""
+    import numpy as np
+
+    from .encoder import Ginfinity, split_rows
+    from .graph import load_graph_shard
     paths = [str(p) for p in paths]
     if node_counts is None:
-        node_counts = [int(json.loads(graph_metadata_path(p).read_text())["node_count"])
-                       for p in paths]
-    mine = [paths[i] for i in assign_shards(node_counts, world_size)[rank]]
+        node_counts = [shard_file_node_count(p) for p in paths]
+    share = assign_shards(node_counts, world_size)[rank]
+    mine = [paths[i] for i in share]
+    dtype = np.dtype(encode_kwargs.get("embedding_dtype", np.float16))
+    table = None
     out = {}
+
+    def run(path, shard):
+        nonlocal table
+        if dtype.itemsize > 4:                      # float64: the encoder converts on the host
+            arrays = encoder.encode_graphs(shard, **encode_kwargs)
+        else:
+            rows = shard.node_count if shard.all_core else int(shard.core_count_array().sum())
+            if table is None or table.shape[0] < rows:
+                table = Ginfinity.pinned_table(max(rows, max(node_counts[i] for i in share)), dtype)
+            arrays = encoder.encode_graphs(shard, out=table[:rows], **encode_kwargs)
+        if consume is not None:
+            consume(path, arrays)
+            out[path] = len(arrays)
+        elif dtype.itemsize > 4:
+            out[path] = arrays
+        else:
+            kept = np.array(table[:rows])           # one copy out of the reused pinned table
+            ptr = np.zeros(len(arrays) + 1, np.int64)
+            np.cumsum([a.shape[0] for a in arrays], out=ptr[1:])
+            out[path] = split_rows(kept, ptr)
+
     if prefetch:
         index = getattr(getattr(encoder, "_torch_device", None), "index", None)
-        for path, shard in ShardPrefetcher(mine, device_index=index):
-            out[path] = encoder.encode_graphs(shard, **encode_kwargs)
+        for path, shard in ShardPrefetcher(mine, device_index=index, workers=workers, depth=1):
+            run(path, shard)
     else:
         for path in mine:
-            out[path] = encoder.encode_graphs(load_graph_shard(path), **encode_kwargs)
+            run(path, load_graph_shard(path))
     return out
