@@ -10,7 +10,10 @@ from pathlib import Path
 
 import numpy as np
 
-_LIB_PATH = Path(__file__).resolve().parent / "libgfx.so"
+import os
+
+# GFX_LIBRARY: developer override (A/B runs of two builds on the same board)
+_LIB_PATH = Path(os.environ.get("GFX_LIBRARY") or Path(__file__).resolve().parent / "libgfx.so")
 
 GFX_F16, GFX_F32 = 0, 1
 IMPL_AUTO, IMPL_SIMT, IMPL_UMMA, IMPL_UMMA_LEAN, IMPL_SPLIT = 0, 1, 2, 5, 8

@@ -361,46 +361,65 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
           for (int q = 0; q < kRun; ++q) pnext[q] = partner(kRun * (run ^ 1) + q);
         }
         // z = fma(1+eps, h, ((((m_prev + m_next) + m_pair) + m_prev2) + m_next2)) in fp16, the CSR
-        // order of a banded row; a missing edge contributes relu(x - 65504) = +0 exactly.
-        // INTERIOR: every row of the run has its four backbone / skip neighbours (all but the runs
-        // at molecule ends): their table rows are used as they are, no selects.
-        auto nodes = [&](auto interior_c) {
-          constexpr bool INTERIOR = decltype(interior_c)::value;
+        // order of a banded row.  Every row is computed as an INTERIOR row here (its four backbone /
+        // skip neighbours taken from the window as they are, no selects); the few rows that lack a
+        // neighbour (molecule ends: ~2 % of the rows) are recomputed after the runs (`ends` below).
+        // A row without a pair reads itself with the -65504 table value: relu(x - 65504) = +0.
 #pragma unroll
-          for (int j = 0; j < kRun; ++j) {
-            const uint32_t dd = dj[j];
-            uint2 t0 = INTERIOR || (dd & kDescPrev) ? tb[0] : kNone;
-            uint2 t1 = INTERIOR || (dd & kDescNext) ? tb[1] : kNone;
-            uint2 tp = (dd & kDescPairRev) ? tb[3] : tb[2];
-            tp = (dd & kDescPair) ? tp : kNone;
-            uint2 t4 = INTERIOR || (dd & kDescPrev2) ? tb[4] : kNone;
-            uint2 t5 = INTERIOR || (dd & kDescNext2) ? tb[5] : kNone;
-            const uint2 pp = pr[j];
-            uint2 acc;
-            acc.x = h2_relu_add(w[j + 1].x, t0.x);
-            acc.y = h2_relu_add(w[j + 1].y, t0.y);
-            acc.x = h2_add(acc.x, h2_relu_add(w[j + 3].x, t1.x));
-            acc.y = h2_add(acc.y, h2_relu_add(w[j + 3].y, t1.y));
-            acc.x = h2_add(acc.x, h2_relu_add(pp.x, tp.x));
-            acc.y = h2_add(acc.y, h2_relu_add(pp.y, tp.y));
-            acc.x = h2_add(acc.x, h2_relu_add(w[j].x, t4.x));
-            acc.y = h2_add(acc.y, h2_relu_add(w[j].y, t4.y));
-            acc.x = h2_add(acc.x, h2_relu_add(w[j + 4].x, t5.x));
-            acc.y = h2_add(acc.y, h2_relu_add(w[j + 4].y, t5.y));
-            uint2 o;
-            o.x = h2_fma(eps1, w[j + 2].x, acc.x);
-            o.y = h2_fma(eps1, w[j + 2].y, acc.y);
-            sts64(zbase + kboff + odd8 + uint32_t(base + j) * 128u + (c8s ^ (uint32_t(j & 7) << 4)), o);
-          }
+        for (int j = 0; j < kRun; ++j) {
+          const uint32_t dd = dj[j];
+          uint2 tp = (dd & kDescPairRev) ? tb[3] : tb[2];
+          tp = (dd & kDescPair) ? tp : kNone;
+          const uint2 pp = pr[j];
+          uint2 acc;
+          acc.x = h2_relu_add(w[j + 1].x, tb[0].x);
+          acc.y = h2_relu_add(w[j + 1].y, tb[0].y);
+          acc.x = h2_add(acc.x, h2_relu_add(w[j + 3].x, tb[1].x));
+          acc.y = h2_add(acc.y, h2_relu_add(w[j + 3].y, tb[1].y));
+          acc.x = h2_add(acc.x, h2_relu_add(pp.x, tp.x));
+          acc.y = h2_add(acc.y, h2_relu_add(pp.y, tp.y));
+          acc.x = h2_add(acc.x, h2_relu_add(w[j].x, tb[4].x));
+          acc.y = h2_add(acc.y, h2_relu_add(w[j].y, tb[4].y));
+          acc.x = h2_add(acc.x, h2_relu_add(w[j + 4].x, tb[5].x));
+          acc.y = h2_add(acc.y, h2_relu_add(w[j + 4].y, tb[5].y));
+          uint2 o;
+          o.x = h2_fma(eps1, w[j + 2].x, acc.x);
+          o.y = h2_fma(eps1, w[j + 2].y, acc.y);
+          sts64(zbase + kboff + odd8 + uint32_t(base + j) * 128u + (c8s ^ (uint32_t(j & 7) << 4)), o);
+        }
+      }
+      // molecule ends: banded rows that lack a backbone / skip neighbour, one row at a time
+      // (warp-uniform), same chain in the same order with the missing terms left out
+      constexpr uint32_t kBackbone = kDescPrev | kDescNext | kDescPrev2 | kDescNext2;
+      uint32_t ends = __ballot_sync(0xffffffffu, lane < kRowsPerWarp && !(d & kDescGeneric) &&
+                                                     (d & kBackbone) != kBackbone);
+      while (ends) {
+        const int idx = __ffs(int(ends)) - 1;
+        ends &= ends - 1;
+        const uint32_t dd = __shfl_sync(0xffffffffu, d, idx);
+        const int lr = kRowsPerWarp * pw + idx;
+        auto row_at = [&](int local) -> uint2 {         // tile row `local`, possibly just outside the tile
+          return uint32_t(local) < uint32_t(kTileM) ? lds64(hbase + cell(local))
+                                                     : __ldg(hg + int64_t(row0 + local) * 32);
         };
-        uint32_t all = dj[0];
-#pragma unroll
-        for (int j = 1; j < kRun; ++j) all &= dj[j];
-        constexpr uint32_t kBackbone = kDescPrev | kDescNext | kDescPrev2 | kDescNext2;
-        if ((all & kBackbone) == kBackbone)
-          nodes(std::true_type{});
-        else
-          nodes(std::false_type{});
+        uint2 acc = make_uint2(0u, 0u);
+        auto add = [&](const uint2 &v, const uint2 &t) {
+          acc.x = h2_add(acc.x, h2_relu_add(v.x, t.x));
+          acc.y = h2_add(acc.y, h2_relu_add(v.y, t.y));
+        };
+        if (dd & kDescPrev) add(row_at(lr - 1), tb[0]);
+        if (dd & kDescNext) add(row_at(lr + 1), tb[1]);
+        if (dd & kDescPair) {
+          const int src = int((dd >> kDescPartnerShift) & kDescPartnerMask);
+          add(row_at(src - row0), (dd & kDescPairRev) ? tb[3] : tb[2]);
+        }
+        if (dd & kDescPrev2) add(row_at(lr - 2), tb[4]);
+        if (dd & kDescNext2) add(row_at(lr + 2), tb[5]);
+        const uint2 self = lds64(hbase + cell(lr));
+        uint2 o;
+        o.x = h2_fma(eps1, self.x, acc.x);
+        o.y = h2_fma(eps1, self.y, acc.y);
+        sts64(zbase + cell(lr), o);
       }
       // rows that are not banded: recomputed from the CSR arrays, one row at a time (warp-uniform);
       // same fp16 chain in CSR order (the first message starts the sum)

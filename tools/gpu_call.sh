@@ -1,3 +1,5 @@
 #!/bin/bash
-python tools/c4_probe.py 2>&1 | tail -12
-timeout 600 python -m pytest tests/test_gpu_encoder.py -m gpu -q -k "shard_files" 2>&1 | tail -3
+for i in 1 2 3; do
+GFX_LIBRARY=$PWD/ginfinity_b200/libgfx_prev.so python tools/fused_probe.py gfx_layer_fused_banded 2>&1 | tail -1 | sed "s/^/prev /"
+python tools/fused_probe.py gfx_layer_fused_banded 2>&1 | tail -1 | sed "s/^/new  /"
+done
