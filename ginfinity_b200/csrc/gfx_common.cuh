@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <cstdio>
 #include <string>
 #include <vector>
@@ -22,6 +23,7 @@ constexpr int kFeat = 7;
 constexpr int kMaxLayers = 8;
 constexpr int kMaxEdgeDim = 16;
 constexpr int kNumSMs = 148;  // B200
+constexpr int kSchedSlots = 64; // tile-scheduler counters per model (one per launch in flight)
 
 void set_error(const std::string &msg);
 int fail(int code, const std::string &msg);
@@ -99,5 +101,9 @@ struct gfx_model {
   // lo parts of the same images, lo = fp16(w - fp16(w)): the split-fp16 tensor-core kernels of
   // the fp32 path (gfx_split9.cu) multiply by hi + lo
   const __half *w1_lo_img, *w2_lo_img, *wa_lo_img, *wb_lo_img;
+  // dynamic tile scheduler of the fused layer kernel: kSchedSlots device counters, handed out
+  // round-robin per launch (so launches of one model in flight on different streams do not share one)
+  uint32_t *sched_counters;
+  mutable std::atomic<uint32_t> sched_next{0};
   gfx_host_vectors host;
 };

@@ -75,8 +75,9 @@ constexpr uint32_t kDescPartnerMask = (1u << kDescPartnerBits) - 1u;
 enum Bar {
   kBarWLocal = 0, kBarWReady = 1, kBarHFull = 2, kBarHEmpty = 5, kBarOReady = 8, kBarA1Full = 11,
   kBarA1Empty = 13, kBarD1aFull = 15, kBarD1bFull = 16, kBarA2aFull = 17, kBarA2bFull = 18,
-  kBarD2Full = 19, kBarD2Empty = 21, kNumBars = 23
+  kBarD2Full = 19, kBarD2Empty = 21, kBarSched = 23, kNumBars = 23 + 16
 };
+constexpr int kRing = 16;                     // tile-pair indices in flight between the roles (kBarSched ..)
 
 struct Smem {
   static constexpr int off_w1 = 0;                                   // [kb 2] x 16 KB (128 rows)
@@ -84,7 +85,8 @@ struct Smem {
   static constexpr int off_z = off_w2 + 4 * kWPiece;                 // 2 stages x 32 KB
   static constexpr int off_h = off_z + kStages * kTileBytes;         // 3 tiles x 32 KB
   static constexpr int off_x = off_h + kHBufs * kTileBytes;          // float2 [2 halves][128 rows]
-  static constexpr int off_bar = off_x + 2 * kTileM * 8;
+  static constexpr int off_ring = off_x + 2 * kTileM * 8;             // int [kRing]: dynamic tile-pair indices
+  static constexpr int off_bar = off_ring + kRing * 4;
   static constexpr int off_tmem = off_bar + kNumBars * 8;
   static constexpr int total = off_tmem + 8;
 };
@@ -106,6 +108,7 @@ struct Args {
   uint32_t eps1_h2;          // (1 + eps) rounded to fp16, in both halves of the word
   long long *trace;          // developer timeline (tools/fused_trace.py); null in production
   uint32_t dbg;              // developer experiments (GFX_DBG): timing only, results are wrong
+  uint32_t *sched;           // dynamic tile scheduler: device counter, zero at launch (DYN kernels)
 };
 
 __device__ __forceinline__ void mbar_wait_c(uint64_t *bar, uint32_t parity) {
@@ -149,6 +152,13 @@ __device__ __forceinline__ void trace_ev(const Args &p, uint32_t it, int ev) {
   if (p.trace != nullptr && blockIdx.x == 0 && it < 64) p.trace[it * 16 + ev] = clock64();
 }
 
+// DYN (GFX_SCHED=dynamic; off by default, see fused8_layer): tile pairs are handed out by an
+// atomic counter instead of round-robin.  With equal static work the CTA pairs of one launch
+// finish 15 % apart (123 ... 143 us on a 603k-node chunk; the groups follow the GPC placement).
+// Rank 0's loader thread fetches the cluster's next pair index two iterations ahead and publishes
+// it to both CTAs through a 16-entry shared-memory ring (st.shared::cluster + a cluster-scope
+// mbarrier arrive for the peer); every role reads entry it + 1 at the top of iteration it.
+template <bool DYN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWarps * 32, 1)
 fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Consts c, const Args p) {
   using L = Smem;
@@ -175,6 +185,7 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
       mbar_init(bar + kBarHEmpty + s, 1);
       mbar_init(bar + kBarOReady + s, kEpiBWarps);
     }
+    for (int s = 0; s < kRing; ++s) mbar_init(bar + kBarSched + s, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar + kBarA1Full + s, 2 * kProdWarps);
       mbar_init(bar + kBarA1Empty + s, 1);
@@ -199,6 +210,26 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
   const int cluster_id = blockIdx.x >> 1, clusters = gridDim.x >> 1;
   // barriers of rank 0 that collect arrivals from both CTAs
   auto leader = [&](int b) { return map_to_cta(smem_u32(bar + b), 0); };
+  // the cluster's sequence of tile pairs: entry idx of the ring (DYN) or round-robin
+  int *ring = reinterpret_cast<int *>(smem + L::off_ring);
+  auto sched_read = [&](uint32_t idx) -> int {
+    const uint32_t slot = idx % kRing, addr = smem_u32(bar + kBarSched + slot);
+    uint32_t done;
+    do {
+      asm volatile(
+          "{\n.reg .pred q;\n"
+          "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 q, [%1], %2;\n"
+          "selp.u32 %0, 1, 0, q;\n}"
+          : "=r"(done)
+          : "r"(addr), "r"((idx / kRing) & 1u)
+          : "memory");
+    } while (!done);
+    int v;
+    asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(ring + slot)) : "memory");
+    return v;
+  };
+  auto first_pair = [&]() -> int { return DYN ? sched_read(0) : cluster_id; };
+  auto next_pair = [&](int pair, uint32_t it) -> int { return DYN ? sched_read(it + 1) : pair + clusters; };
 
   if (warp < kEpiBWarp0) {
     // ================= epilogue A =================================================
@@ -206,7 +237,7 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
     const uint32_t trow = tmem + (uint32_t(warp * 32) << 16);
     const uint32_t a2a = leader(kBarA2aFull), a2b = leader(kBarA2bFull);
     uint32_t it = 0;
-    for (int pair = cluster_id; pair < pairs; pair += clusters, ++it) {
+    for (int pair = first_pair(); pair < pairs; pair = next_pair(pair, it), ++it) {
       if (tid == 0) trace_ev(p, it, 6);
       epi_a<0>(c, trow, bar, it & 1, lane, a2a, p.sleep_ns, (p.dbg & 16u) != 0u);
       epi_a<1>(c, trow, bar, it & 1, lane, a2b, p.sleep_ns, (p.dbg & 16u) != 0u);
@@ -222,7 +253,7 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
     const uint32_t d2e[2] = {leader(kBarD2Empty), leader(kBarD2Empty + 1)};
     reg_inc<88>();
     uint32_t it = 0;
-    for (int pair = cluster_id; pair < pairs; pair += clusters, ++it) {
+    for (int pair = first_pair(); pair < pairs; pair = next_pair(pair, it), ++it) {
       const uint32_t g = it & 1, hb = it % kHBufs;
       const uint32_t tcol = tmem + (uint32_t(quad * 32) << 16) + kD2Col + g * kHidden + uint32_t(half) * 64u;
       mbar_wait_s(bar + kBarD2Full + g, (it >> 1) & 1, p.sleep_ns);
@@ -287,9 +318,11 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
     // ~250 instructions) before their first use and never carried across tile iterations: round
     // 1's kernel prefetched the halo rows one TILE ahead, the compiler spilled them, and the
     // spill store waited ~1.4 k cycles for the load it was meant to hide (timeline of r02_b).
-    uint32_t dnext = fetch_desc(cluster_id);
+    int pair = first_pair();
+    uint32_t dnext = fetch_desc(pair);
     uint32_t it = 0;
-    for (int pair = cluster_id; pair < pairs; pair += clusters, ++it) {
+    for (; pair < pairs; ++it) {
+      const int pair_next = next_pair(pair, it);       // known long before it is needed
       const uint32_t s = it & 1, hb = it % kHBufs;
       const int row0 = (2 * pair + int(rank)) * kTileM;
       const uint32_t d = dnext;
@@ -447,7 +480,8 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
       }
       // the next tile's descriptors: requested here so that nothing is live across the run loop;
       // the load completes during the hand-over and the waits of the next iteration
-      dnext = fetch_desc(pair + clusters);
+      dnext = fetch_desc(pair_next);
+      pair = pair_next;
       if (warp == kProdWarp0 && lane == 0) trace_ev(p, it, 15);
       if (warp == kProdWarp0 + 3 && lane == 0) trace_ev(p, it, 14);
       if (!(p.dbg & 4u)) fence_async_smem();
@@ -484,7 +518,7 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
         // runs on 40 registers).
         uint64_t w1d = smem_desc_sw128(smem_u32(w1s)), w2d = smem_desc_sw128(smem_u32(w2s));
         uint32_t it = 0;
-        for (int pair = cluster_id; pair < pairs; pair += clusters, ++it) {
+        for (int pair = first_pair(); pair < pairs; pair = next_pair(pair, it), ++it) {
           const uint32_t s = it & 1, g = it & 1, ph2 = (it >> 1) & 1, ph = it & 1;
           uint64_t zd = smem_desc_sw128(smem_u32(zs) + s * kTileBytes);
           asm volatile("" : "+l"(w1d), "+l"(w2d), "+l"(zd));
@@ -527,8 +561,7 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
     reg_dec<40>();
     if (lane == 0) {
       prefetch_tmap(&maps.h);
-      uint32_t it = 0;
-      for (int pair = cluster_id; pair < pairs; pair += clusters, ++it) {
+      auto load_tile = [&](int pair, uint32_t it) {
         const uint32_t hb = it % kHBufs;
         const int row0 = (2 * pair + int(rank)) * kTileM;
         uint8_t *dst = hs + hb * kTileBytes;
@@ -537,6 +570,35 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
         mbar_arrive_expect_tx(bar + kBarHFull + hb, kTileBytes);
         tma_load_2d(dst, &maps.h, 0, row0, bar + kBarHFull + hb);
         tma_load_2d(dst + kKbBytes, &maps.h, 64, row0, bar + kBarHFull + hb);
+      };
+      if (DYN && rank == 0) {
+        // the cluster's scheduler: entries it + 1 and it + 2 of the ring are always published
+        // before the tile of iteration `it` is requested; once the counter passes the last pair
+        // its value is the end mark every role stops at
+        auto publish = [&](uint32_t idx, int value) {
+          const uint32_t slot = idx % kRing;
+          const uint32_t own = smem_u32(ring + slot), ownbar = smem_u32(bar + kBarSched + slot);
+          asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(own), "r"(value) : "memory");
+          mbar_arrive(bar + kBarSched + slot);
+          asm volatile("st.shared::cluster.s32 [%0], %1;" ::"r"(map_to_cta(own, 1)), "r"(value) : "memory");
+          asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(map_to_cta(ownbar, 1))
+                       : "memory");
+        };
+        auto fetch = [&](int prev) -> int { return prev < pairs ? int(atomicAdd(p.sched, 1u)) : prev; };
+        int cur = int(atomicAdd(p.sched, 1u));
+        publish(0, cur);
+        int nxt = fetch(cur);
+        publish(1, nxt);
+        for (uint32_t it = 0; cur < pairs; ++it) {
+          const int after = fetch(nxt);              // in flight while this tile's buffer is awaited
+          load_tile(cur, it);
+          publish(it + 2, after);
+          cur = nxt;
+          nxt = after;
+        }
+      } else {
+        uint32_t it = 0;
+        for (int pair = first_pair(); pair < pairs; pair = next_pair(pair, it), ++it) load_tile(pair, it);
       }
     }
     __syncwarp();
@@ -546,7 +608,7 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
     if (lane == 0) {
       prefetch_tmap(&maps.out);
       uint32_t it = 0;
-      for (int pair = cluster_id; pair < pairs; pair += clusters, ++it) {
+      for (int pair = first_pair(); pair < pairs; pair = next_pair(pair, it), ++it) {
         const uint32_t hb = it % kHBufs;
         const int row0 = (2 * pair + int(rank)) * kTileM;
         const uint8_t *src = hs + hb * kTileBytes;
@@ -648,7 +710,22 @@ int fused8_layer(const gfx_model *m, int layer, const __half *h, const int32_t *
     return uint32_t(v ? atoi(v) : 0);
   }();
   a.dbg = dbg;
-  auto kernel = v8::fused_banded8_kernel;
+  // GFX_SCHED=dynamic: tile pairs from an atomic counter.  Built to recover the 15 % spread of CTA
+  // durations under round-robin assignment (123 ... 143 us on a 603k-node chunk); measured on the
+  // same board it evens them out (139 ... 146 us) and the kernel takes the SAME time (0.145 vs
+  // 0.146 ms): the early finishers were not idle capacity, the aggregate rate of the chip (clock
+  // under load) is what is conserved.  Round-robin stays the default: no counter, no extra
+  // memset per launch.
+  static const bool dynamic = [] {
+    const char *v = getenv("GFX_SCHED");
+    return v && v[0] == 'd';
+  }();
+  if (dynamic) {
+    const uint32_t slot = m->sched_next.fetch_add(1u, std::memory_order_relaxed) % kSchedSlots;
+    a.sched = m->sched_counters + slot;
+    GFX_CUDA(cudaMemsetAsync(a.sched, 0, sizeof(uint32_t), st));
+  }
+  auto kernel = dynamic ? v8::fused_banded8_kernel<true> : v8::fused_banded8_kernel<false>;
   GFX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v8::Smem::total));
   const int64_t tiles = (n + v8::kTileM - 1) / v8::kTileM;
   const int64_t pairs = (tiles + 1) / 2;
