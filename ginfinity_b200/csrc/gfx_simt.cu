@@ -430,6 +430,101 @@ aggregate_f16_q_kernel(const __half *__restrict__ h, const int32_t *__restrict__
 }
 
 // ---------------------------------------------------------------------------
+// K1, fp32 storage (full_precision): the quarter-warp scheme above with a HALF warp per node (a
+// 512-byte row is 16 lanes x two 128-bit loads), edges fetched by one lane each and exchanged by
+// shuffle, a missing edge pointing at the node itself with a -FLT_MAX table row (message +0),
+// software-pipelined two nodes deep.  Same operations in the same order as aggregate_kernel<float>
+// (fp32 message, fp32 sum in CSR order, one fma for the self term): the same bits.
+// ---------------------------------------------------------------------------
+constexpr int kWinH = 5;
+
+__global__ void __launch_bounds__(256, 2)
+aggregate_f32_h_kernel(const float *__restrict__ h, const int32_t *__restrict__ row_ptr,
+                       const int32_t *__restrict__ col_src, const uint8_t *__restrict__ col_type,
+                       const float *__restrict__ table, int edge_dim, float eps1, int64_t n,
+                       float *__restrict__ z) {
+  __shared__ __align__(16) float tab[(kMaxEdgeDim + 1) * kHidden];
+  for (int i = threadIdx.x; i < edge_dim * kHidden; i += blockDim.x) tab[i] = table[i];
+  for (int i = threadIdx.x; i < kHidden; i += blockDim.x) tab[edge_dim * kHidden + i] = -3.0e38f;
+  __syncthreads();
+  const int sub = threadIdx.x & 15;
+  const int hbase = threadIdx.x & 16;                               // first lane of this half warp
+  const float4 *hv = reinterpret_cast<const float4 *>(h) + sub;     // row r -> hv[r*32], hv[r*32+16]
+  const float4 *tv = reinterpret_cast<const float4 *>(tab) + sub;
+  const uint32_t none = uint32_t(edge_dim) << kSrcBits;
+  const int64_t stride = int64_t(gridDim.x) * (blockDim.x >> 4);
+  int64_t i = int64_t(blockIdx.x) * (blockDim.x >> 4) + (threadIdx.x >> 4);
+  const int64_t last = n - 1;                                        // descending node order (L2 hand-over)
+  auto rp = [&](int64_t v, int &b, int &e) {
+    b = e = 0;
+    if (v < n) {
+      b = row_ptr[last - v];
+      e = row_ptr[last - v + 1];
+    }
+  };
+  auto fetch_edge = [&](int64_t v, int b, int e) -> uint32_t {       // this lane's edge of node v
+    uint32_t pk = (uint32_t(v < n ? last - v : 0) & kSrcMask) | none;
+    if (b + sub < e) pk = uint32_t(col_src[b + sub]) | (uint32_t(col_type[b + sub]) << kSrcBits);
+    return pk;
+  };
+  int beg, end, beg1, end1;
+  rp(i, beg, end);
+  int64_t i1 = i + stride;
+  rp(i1, beg1, end1);
+  uint32_t pk = fetch_edge(i, beg, end);
+  while (true) {                                                     // warp-uniform trip count
+    const int64_t i2 = i1 + stride;
+    int beg2, end2;
+    rp(i2, beg2, end2);
+    const uint32_t pk1 = fetch_edge(i1, beg1, end1);
+    const int64_t node = i < n ? last - i : 0;
+    const float4 self0 = hv[node * 32], self1 = hv[node * 32 + 16];
+    uint32_t e[kWinH];
+    float4 nb0[kWinH], nb1[kWinH];
+#pragma unroll
+    for (int u = 0; u < kWinH; ++u) {
+      e[u] = __shfl_sync(0xffffffffu, pk, hbase + u);
+      const float4 *src = hv + int64_t(e[u] & kSrcMask) * 32;
+      nb0[u] = src[0];
+      nb1[u] = src[16];
+    }
+    float acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+    auto add = [&](const float4 &a, const float4 &b, const float4 &t0, const float4 &t1) {
+      acc[0] += fmaxf(a.x + t0.x, 0.f); acc[1] += fmaxf(a.y + t0.y, 0.f);
+      acc[2] += fmaxf(a.z + t0.z, 0.f); acc[3] += fmaxf(a.w + t0.w, 0.f);
+      acc[4] += fmaxf(b.x + t1.x, 0.f); acc[5] += fmaxf(b.y + t1.y, 0.f);
+      acc[6] += fmaxf(b.z + t1.z, 0.f); acc[7] += fmaxf(b.w + t1.w, 0.f);
+    };
+#pragma unroll
+    for (int u = 0; u < kWinH; ++u) {
+      const float4 *t = tv + (e[u] >> kSrcBits) * 32;
+      add(nb0[u], nb1[u], t[0], t[16]);
+    }
+    const int deg = end - beg;
+    if (deg > kWinH) {                                               // rare: longer rows
+      for (int u = kWinH; u < deg; ++u) {
+        const int s = col_src[beg + u], ty = col_type[beg + u];
+        const float4 *src = hv + int64_t(s) * 32;
+        const float4 *t = tv + ty * 32;
+        add(src[0], src[16], t[0], t[16]);
+      }
+    }
+    if (i < n) {
+      float4 *zr = reinterpret_cast<float4 *>(z) + node * 32 + sub;
+      zr[0] = make_float4(fmaf(eps1, self0.x, acc[0]), fmaf(eps1, self0.y, acc[1]),
+                          fmaf(eps1, self0.z, acc[2]), fmaf(eps1, self0.w, acc[3]));
+      zr[16] = make_float4(fmaf(eps1, self1.x, acc[4]), fmaf(eps1, self1.y, acc[5]),
+                           fmaf(eps1, self1.z, acc[6]), fmaf(eps1, self1.w, acc[7]));
+    }
+    if (__shfl_sync(0xffffffffu, int(i1 >= n), 0)) break;
+    i = i1; beg = beg1; end = end1; pk = pk1;
+    i1 = i2; beg1 = beg2; end1 = end2;
+  }
+}
+
+// ---------------------------------------------------------------------------
 // SIMT MLP.  One warp owns 8 node rows end to end (both GEMMs, LayerNorm or
 // L2 norm), so nothing but weights is shared between warps and only
 // __syncwarp is needed.  Stage 1: lane owns HID/32 hidden columns of its 8
@@ -694,11 +789,23 @@ extern "C" int gfx_aggregate(const gfx_model *m, int layer, const void *h, const
           static_cast<const __half *>(h), row_ptr, col_src, col_type, m->table16 + toff,
           m->edge_dim, m->eps1[layer], n, static_cast<__half *>(z));
     }
-  } else if (dtype == GFX_F32)
-    aggregate_kernel<float><<<row_grid(n), 256, 0, st>>>(
-        static_cast<const float *>(h), row_ptr, col_src, col_type, m->table[0] + toff,
-        m->edge_dim, m->eps1[layer], n, static_cast<float *>(z));
-  else
+  } else if (dtype == GFX_F32) {
+    static const bool generic = [] {              // GFX_K1_F32_GENERIC=1: the unpipelined kernel
+      const char *v = getenv("GFX_K1_F32_GENERIC");
+      return v && *v && *v != '0';
+    }();
+    if (!generic && n <= (int64_t(1) << kSrcBits)) {
+      int64_t b = (n + 15) / 16;
+      const int grid = int(b > 2 * kNumSMs ? 2 * kNumSMs : b);
+      aggregate_f32_h_kernel<<<grid, 256, 0, st>>>(
+          static_cast<const float *>(h), row_ptr, col_src, col_type, m->table[0] + toff,
+          m->edge_dim, m->eps1[layer], n, static_cast<float *>(z));
+    } else {
+      aggregate_kernel<float><<<row_grid(n), 256, 0, st>>>(
+          static_cast<const float *>(h), row_ptr, col_src, col_type, m->table[0] + toff,
+          m->edge_dim, m->eps1[layer], n, static_cast<float *>(z));
+    }
+  } else
     return fail(GFX_ERR_ARGUMENT, "gfx_aggregate: unknown dtype");
   GFX_LAUNCH_CHECK();
   return GFX_OK;

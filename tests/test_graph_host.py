@@ -356,3 +356,38 @@ def test_position_table_reproduces_the_builder_columns_bit_for_bit():
     assert db.supports(g.GraphSpec(), windowed) and db.any_sliced(windowed)
     assert not db.any_sliced(records)
     assert not db.supports(g.GraphSpec(positional=False), records)
+
+
+def test_shard_files_load_through_a_caller_supplied_allocator(tmp_path):
+    """`load_graph_shard(allocate=)`: the safetensors file is memory-mapped and every tensor is copied
+    once into the buffer the caller hands out (page-locked pools on the GPU box); the result equals
+    the ordinary loader's array for array, header problems are still GraphValidationErrors, and
+    the node total can be read from the header alone."""
+    import ginfinity_b200 as g
+    from ginfinity_b200.multi_gpu import shard_file_node_count
+    records = [g.RNA("rna-1", "ACGUACGU", "((....))"), g.RNA("rna-2", "GGAACCUU", "........"),
+               g.RNA("stem", "GGGAAACCCUUUUGGG", "......(((....)))", start=9, end=16)]
+    shard = g.GraphBuilder(keep_paired_neighbours=True, context_hops=2).build_shard(records)
+    path = tmp_path / "s.safetensors"
+    g.save_graph_shard(shard, path)
+    handed = {}
+
+    def allocate(name, shape, dtype):
+        handed[name] = np.full(shape, 7, dtype)
+        return handed[name]
+
+    plain = g.load_graph_shard(path)
+    pooled = g.load_graph_shard(path, allocate=allocate, validation="full")
+    names = ("node_features", "edge_index", "edge_types", "node_ptr", "edge_ptr", "residue_index",
+             "node_roles")
+    for name in names:
+        assert np.array_equal(getattr(plain, name), getattr(pooled, name)), name
+        assert getattr(pooled, name) is handed[name]          # no second copy
+    assert pooled.identifiers == plain.identifiers and pooled.spec.sha256 == plain.spec.sha256
+    assert shard_file_node_count(path) == shard.node_count
+    # a truncated file is rejected, not read past its end
+    broken = tmp_path / "broken.safetensors"
+    broken.write_bytes(path.read_bytes()[:-16])
+    (tmp_path / "broken.json").write_bytes(g.graph_metadata_path(path).read_bytes())
+    with pytest.raises(g.GraphValidationError, match="cannot load graph shard tensors"):
+        g.load_graph_shard(broken, metadata_path=tmp_path / "broken.json", allocate=allocate)
