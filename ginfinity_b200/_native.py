@@ -55,6 +55,9 @@ _SIGNATURES = {
     "gfx_csr_workspace_bytes": (_sz, [_i64, _i64]),
     "gfx_csr_build": (C.c_int, [_p, _p, _p, _i64, _i64, _i32, _p, _p, _p, _p, _sz, _p]),
     "gfx_csr_build_checked": (C.c_int, [_p, _p, _p, _i64, _i64, _i32, _p, _p, _p, _p, _p, _sz, _p]),
+    "gfx_edge_describe_workspace_bytes": (_sz, [_i64]),
+    "gfx_edge_describe": (C.c_int, [_p, _p, _p, _i64, _i64, _i32, _p, _p, _p, _sz, _p]),
+    "gfx_csr_build_if": (C.c_int, [_p, _p, _p, _i64, _i64, _i32, _p, _p, _p, _p, _p, _sz, _p]),
     "gfx_graph_workspace_bytes": (_sz, [_i64, _i64]),
     "gfx_graph_count": (C.c_int, [_p, _p, _i64, _i64, C.c_int, _p, _p, _p, _sz, _p]),
     "gfx_graph_fill": (C.c_int, [_p, _p, _p, _p, _i64, _i64, _i64, C.c_int, _p, _p, _p, _p, _p,
@@ -76,6 +79,7 @@ _SIGNATURES = {
     "gfx_encode_workspace_bytes": (_sz, [_i64, C.c_int]),
     "gfx_encode": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _p, C.c_int, C.c_int,
                              C.c_int, C.c_int, _p, _sz, _p]),
+    "gfx_encode_described": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _p, C.c_int, _p, _sz, _p]),
     "gfx_topk_workspace_bytes": (_sz, [_i64, _i64, C.c_int]),
     "gfx_topk": (C.c_int, [_p, _i64, _p, _i64, C.c_int, C.c_int, C.c_int, _i64,
                            _p, _p, _p, _sz, _p]),

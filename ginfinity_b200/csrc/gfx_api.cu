@@ -254,11 +254,33 @@ extern "C" size_t gfx_encode_workspace_bytes(int64_t num_nodes, int dtype) {
   return 3 * act_bytes(num_nodes, dtype);
 }
 
+static int encode_chunk(const gfx_model *model, const float *x, const int32_t *row_ptr,
+                        const int32_t *col_src, const uint8_t *col_type, const uint32_t *desc_in,
+                        const int32_t *out_row, int64_t n, void *out, int dtype, int out_dtype, int impl,
+                        int fused, void *ws, size_t ws_bytes, void *stream);
+
 extern "C" int gfx_encode(const gfx_model *model, const float *x, const int32_t *row_ptr,
                           const int32_t *col_src, const uint8_t *col_type,
                           const int32_t *out_row, int64_t n, void *out, int dtype,
                           int out_dtype, int impl, int fused, void *ws, size_t ws_bytes,
                           void *stream) {
+  return encode_chunk(model, x, row_ptr, col_src, col_type, nullptr, out_row, n, out, dtype, out_dtype,
+                      impl, fused, ws, ws_bytes, stream);
+}
+
+extern "C" int gfx_encode_described(const gfx_model *model, const float *x, const uint32_t *desc,
+                                    const int32_t *row_ptr, const int32_t *col_src,
+                                    const uint8_t *col_type, int64_t n, void *out, int out_dtype,
+                                    void *ws, size_t ws_bytes, void *stream) {
+  if (!desc && n > 0) return fail(GFX_ERR_ARGUMENT, "gfx_encode_described: null row descriptors");
+  return encode_chunk(model, x, row_ptr, col_src, col_type, desc, nullptr, n, out, GFX_F16, out_dtype,
+                      GFX_IMPL_AUTO, 3, ws, ws_bytes, stream);
+}
+
+static int encode_chunk(const gfx_model *model, const float *x, const int32_t *row_ptr,
+                        const int32_t *col_src, const uint8_t *col_type, const uint32_t *desc_in,
+                        const int32_t *out_row, int64_t n, void *out, int dtype, int out_dtype, int impl,
+                        int fused, void *ws, size_t ws_bytes, void *stream) {
   if (!model) return fail(GFX_ERR_ARGUMENT, "gfx_encode: null model");
   if (n == 0) return GFX_OK;
   if (ws_bytes < gfx_encode_workspace_bytes(n, dtype))
@@ -269,16 +291,20 @@ extern "C" int gfx_encode(const gfx_model *model, const float *x, const int32_t 
   if (fused == 1) fused = 2;   // the one-CTA-per-SM form was removed; 1 is kept as an alias
   // the banded kernel covers >= 6 edge types and <= 2^25 nodes, the CTA-pair kernel <= 10 edge
   // types and <= 2^27 nodes; outside that: K1 + K2
+  if (desc_in != nullptr && (model->edge_dim < 6 || n > (int64_t(1) << 25)))
+    return fail(GFX_ERR_UNSUPPORTED, "gfx_encode_described: needs >= 6 edge types and <= 2^25 nodes");
   if (fused == 3 && (model->edge_dim < 6 || n > (int64_t(1) << 25))) fused = 2;
   if (fused == 2 && (model->edge_dim > 10 || n > (int64_t(1) << 27))) fused = 0;
   char *base = static_cast<char *>(ws);
   void *h = base, *z = base + act_bytes(n, dtype), *h2 = base + 2 * act_bytes(n, dtype);
   int rc = gfx_input_linear(model, x, n, h, dtype, stream);
   if (rc) return rc;
-  uint32_t *desc = static_cast<uint32_t *>(z);      // fused layers leave the z buffer free
-  if (fused == 3) {
-    rc = gfx_row_describe(row_ptr, col_src, col_type, n, desc, stream);
+  const uint32_t *desc = desc_in;
+  if (fused == 3 && desc == nullptr) {
+    uint32_t *made = static_cast<uint32_t *>(z);     // fused layers leave the z buffer free
+    rc = gfx_row_describe(row_ptr, col_src, col_type, n, made, stream);
     if (rc) return rc;
+    desc = made;
   }
   for (int l = 0; l < model->layers; ++l) {
     if (fused == 3) {   // CTA pairs, banded producers (gfx_fused8.cu)

@@ -25,6 +25,17 @@ constexpr int kMaxEdgeDim = 16;
 constexpr int kNumSMs = 148;  // B200
 constexpr int kSchedSlots = 64; // tile-scheduler counters per model (one per launch in flight)
 
+// Row descriptor of the banded fused layer (gfx_row_describe / gfx_edge_describe -> gfx_fused8.cu):
+// which of (i-1, type 0) (i+1, type 1) [(partner, type 2|3)] (i-2, type 4) (i+2, type 5) -- the
+// reference builder's edge order for nucleotide i (graph.py:494-561) -- the row holds, the partner
+// index, or GENERIC when the row is anything else.
+namespace rowdesc {
+constexpr uint32_t kPrev = 1u, kNext = 2u, kPair = 4u, kPairRev = 8u, kPrev2 = 16u, kNext2 = 32u,
+                   kGeneric = 0x80000000u;
+constexpr int kPartnerShift = 6, kPartnerBits = 25;
+constexpr uint32_t kPartnerMask = (1u << kPartnerBits) - 1u;
+}  // namespace rowdesc
+
 void set_error(const std::string &msg);
 int fail(int code, const std::string &msg);
 
@@ -45,7 +56,7 @@ inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s
 // *grand_total (optional, device) receives the sum of all n inputs.
 int scan_blocks(int64_t n);
 int exclusive_scan(const int *in, int *out, int64_t n, int *block_sums, int64_t *grand_total,
-                   cudaStream_t st);
+                   cudaStream_t st, const int32_t *gate = nullptr);
 inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 
 // Counts `launches` kernel launches for `stage`; if the stage is being

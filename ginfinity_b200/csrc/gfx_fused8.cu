@@ -67,10 +67,11 @@ constexpr int kRowsPerWarp = kTileM / kProdWarps;     // 16 consecutive rows of 
 constexpr int kRun = 8;                               // rows per register window
 static_assert(kRowsPerWarp % kRun == 0 && kRun % 4 == 0, "runs of whole partner groups");
 // row descriptor (gfx_row_describe, below)
-constexpr uint32_t kDescPrev = 1u, kDescNext = 2u, kDescPair = 4u, kDescPairRev = 8u, kDescPrev2 = 16u,
-                   kDescNext2 = 32u, kDescGeneric = 0x80000000u;
-constexpr int kDescPartnerShift = 6, kDescPartnerBits = 25;
-constexpr uint32_t kDescPartnerMask = (1u << kDescPartnerBits) - 1u;
+constexpr uint32_t kDescPrev = rowdesc::kPrev, kDescNext = rowdesc::kNext, kDescPair = rowdesc::kPair,
+                   kDescPairRev = rowdesc::kPairRev, kDescPrev2 = rowdesc::kPrev2,
+                   kDescNext2 = rowdesc::kNext2, kDescGeneric = rowdesc::kGeneric;
+constexpr int kDescPartnerShift = rowdesc::kPartnerShift, kDescPartnerBits = rowdesc::kPartnerBits;
+constexpr uint32_t kDescPartnerMask = rowdesc::kPartnerMask;
 
 enum Bar {
   kBarWLocal = 0, kBarWReady = 1, kBarHFull = 2, kBarHEmpty = 5, kBarOReady = 8, kBarA1Full = 11,

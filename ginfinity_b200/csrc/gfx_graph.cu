@@ -45,9 +45,10 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int *total) {
 }
 
 __global__ void __launch_bounds__(kScanThreads)
-scan_local_kernel(const int *__restrict__ in, int *__restrict__ out, int *__restrict__ block_sums,
-                  int64_t n) {
+scan_local_kernel(const int32_t *__restrict__ gate, const int *__restrict__ in, int *__restrict__ out,
+                  int *__restrict__ block_sums, int64_t n) {
   __shared__ int total;
+  if (gate != nullptr && *gate == 0) return;     // gated launch (gfx_csr_build_if): nothing to do
   const int64_t base = int64_t(blockIdx.x) * kScanTile + int64_t(threadIdx.x) * kScanItems;
   int v[kScanItems];
   int sum = 0;
@@ -67,8 +68,10 @@ scan_local_kernel(const int *__restrict__ in, int *__restrict__ out, int *__rest
 
 // single block: exclusive scan of block_sums in place (any length)
 __global__ void __launch_bounds__(kScanThreads)
-scan_sums_kernel(int *__restrict__ sums, int count, int64_t *__restrict__ grand_total) {
+scan_sums_kernel(const int32_t *__restrict__ gate, int *__restrict__ sums, int count,
+                 int64_t *__restrict__ grand_total) {
   __shared__ int total;
+  if (gate != nullptr && *gate == 0) return;
   int carry = 0;
   for (int base = 0; base < count; base += kScanThreads) {
     int i = base + threadIdx.x;
@@ -82,7 +85,9 @@ scan_sums_kernel(int *__restrict__ sums, int count, int64_t *__restrict__ grand_
 }
 
 __global__ void __launch_bounds__(kScanThreads)
-scan_add_kernel(int *__restrict__ out, const int *__restrict__ block_sums, int64_t n) {
+scan_add_kernel(const int32_t *__restrict__ gate, int *__restrict__ out, const int *__restrict__ block_sums,
+                int64_t n) {
+  if (gate != nullptr && *gate == 0) return;
   const int add = block_sums[blockIdx.x];
   const int64_t base = int64_t(blockIdx.x) * kScanTile + int64_t(threadIdx.x) * kScanItems;
 #pragma unroll
@@ -94,12 +99,12 @@ int scan_blocks(int64_t n) { return int((n + kScanTile - 1) / kScanTile); }
 
 // out[i] = sum(in[0..i)) for i in [0,n).  block_sums: scan_blocks(n) ints.
 int exclusive_scan(const int *in, int *out, int64_t n, int *block_sums,
-                   int64_t *grand_total, cudaStream_t st) {
+                   int64_t *grand_total, cudaStream_t st, const int32_t *gate) {
   if (n == 0) return GFX_OK;
   int nb = scan_blocks(n);
-  scan_local_kernel<<<nb, kScanThreads, 0, st>>>(in, out, block_sums, n);
-  scan_sums_kernel<<<1, kScanThreads, 0, st>>>(block_sums, nb, grand_total);
-  scan_add_kernel<<<nb, kScanThreads, 0, st>>>(out, block_sums, n);
+  scan_local_kernel<<<nb, kScanThreads, 0, st>>>(gate, in, out, block_sums, n);
+  scan_sums_kernel<<<1, kScanThreads, 0, st>>>(gate, block_sums, nb, grand_total);
+  scan_add_kernel<<<nb, kScanThreads, 0, st>>>(gate, out, block_sums, n);
   GFX_LAUNCH_CHECK();
   return GFX_OK;
 }
@@ -167,9 +172,10 @@ __device__ __forceinline__ bool edge_in_range(int32_t s, int32_t d, int32_t base
   return uint32_t(s - base) < N && uint32_t(d - base) < N;
 }
 
-__global__ void csr_count_kernel(const int32_t *__restrict__ src, const int32_t *__restrict__ dst,
-                                 int64_t E, int32_t base, uint32_t N, int *__restrict__ deg,
-                                 int32_t *__restrict__ status) {
+__global__ void csr_count_kernel(const int32_t *__restrict__ gate, const int32_t *__restrict__ src,
+                                 const int32_t *__restrict__ dst, int64_t E, int32_t base, uint32_t N,
+                                 int *__restrict__ deg, int32_t *__restrict__ status) {
+  if (gate != nullptr && *gate == 0) return;
   bool bad = false;
   for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < E;
        e += int64_t(gridDim.x) * blockDim.x) {
@@ -179,10 +185,11 @@ __global__ void csr_count_kernel(const int32_t *__restrict__ src, const int32_t 
   if (bad) atomicOr(status, GFX_GRAPH_BAD_EDGE);
 }
 
-__global__ void csr_scatter_kernel(const int32_t *__restrict__ src, const int32_t *__restrict__ dst,
-                                   int64_t E, int32_t base, uint32_t N,
+__global__ void csr_scatter_kernel(const int32_t *__restrict__ gate, const int32_t *__restrict__ src,
+                                   const int32_t *__restrict__ dst, int64_t E, int32_t base, uint32_t N,
                                    const int32_t *__restrict__ row_ptr, int *__restrict__ cursor,
                                    int32_t *__restrict__ eid) {
+  if (gate != nullptr && *gate == 0) return;
   for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < E;
        e += int64_t(gridDim.x) * blockDim.x) {
     if (!edge_in_range(src[e], dst[e], base, N)) continue;
@@ -192,11 +199,12 @@ __global__ void csr_scatter_kernel(const int32_t *__restrict__ src, const int32_
   }
 }
 
-__global__ void csr_place_kernel(const int32_t *__restrict__ src, const uint8_t *__restrict__ typ,
-                                 int32_t base, const int32_t *__restrict__ row_ptr,
-                                 const int32_t *__restrict__ eid, int64_t N,
-                                 int32_t *__restrict__ col_src, uint8_t *__restrict__ col_type,
+__global__ void csr_place_kernel(const int32_t *__restrict__ gate, const int32_t *__restrict__ src,
+                                 const uint8_t *__restrict__ typ, int32_t base,
+                                 const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ eid,
+                                 int64_t N, int32_t *__restrict__ col_src, uint8_t *__restrict__ col_type,
                                  int32_t *__restrict__ big_rows, int *__restrict__ n_big) {
+  if (gate != nullptr && *gate == 0) return;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < N;
        i += int64_t(gridDim.x) * blockDim.x) {
     const int s = row_ptr[i], t = row_ptr[i + 1];
@@ -214,7 +222,7 @@ __global__ void csr_place_kernel(const int32_t *__restrict__ src, const uint8_t 
   }
 }
 
-__global__ void csr_place_big_kernel(const int32_t *__restrict__ src,
+__global__ void csr_place_big_kernel(const int32_t *__restrict__ gate, const int32_t *__restrict__ src,
                                      const uint8_t *__restrict__ typ, int32_t base,
                                      const int32_t *__restrict__ row_ptr,
                                      const int32_t *__restrict__ eid,
@@ -222,6 +230,7 @@ __global__ void csr_place_big_kernel(const int32_t *__restrict__ src,
                                      const int *__restrict__ n_big,
                                      int32_t *__restrict__ col_src,
                                      uint8_t *__restrict__ col_type) {
+  if (gate != nullptr && *gate == 0) return;
   const int count = *n_big;
   for (int r = blockIdx.x; r < count; r += gridDim.x) {
     const int i = big_rows[r];
@@ -234,6 +243,85 @@ __global__ void csr_place_big_kernel(const int32_t *__restrict__ src,
       col_type[s + rank] = typ[ea];
     }
   }
+}
+
+// ---------------------------------------------------------------------------
+// Row descriptors straight from the edge list (no CSR).  Same result as gfx_row_describe on the
+// CSR of the same edges, bit for bit:
+//   1 per edge   class k of the edge for its destination d (0 prev: type 0 from d-1, 1 next: type 1
+//                from d+1, 2 pair: type 2|3, 3 prev2: type 4 from d-2, 4 next2: type 5 from d+2);
+//                state[d] |= 1 << k (one atomicOr), position[k][d] = e; an edge of no class, or a
+//                second edge of a class, marks the row GENERIC
+//   2 per node   a banded row's edges must also APPEAR in the order prev < next < pair < prev2 <
+//                next2 (the order of the CSR row, i.e. the summation order); then the descriptor
+//                is assembled, the pairing partner read from the pair edge
+// needs_csr[0] becomes 1 when any row is GENERIC (the banded kernel then reads the CSR arrays,
+// see gfx_csr_build_if); edges that leave the chunk are reported through *status like K0 does.
+// Measured on the 20 M-nt bench shard: 1.35 ms per pass against 1.63 for K0 + gfx_row_describe; an
+// atomic-free form (two passes over the edges that cross-check plain stores) took 1.75 ms.
+// ---------------------------------------------------------------------------
+constexpr uint32_t kEdgeStateGeneric = 1u << 8;
+
+__global__ void edge_classify_kernel(const int32_t *__restrict__ src, const int32_t *__restrict__ dst,
+                                     const uint8_t *__restrict__ typ, int64_t E, int32_t base, uint32_t N,
+                                     uint32_t *__restrict__ state, int32_t *__restrict__ position,
+                                     int32_t *__restrict__ status) {
+  bool bad = false;
+  for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < E;
+       e += int64_t(gridDim.x) * blockDim.x) {
+    const int32_t s = src[e] - base, d = dst[e] - base;
+    if (uint32_t(s) >= N || uint32_t(d) >= N) {
+      bad = true;                                  // dropped, as in csr_count_kernel
+      continue;
+    }
+    const int t = typ[e], off = s - d;
+    int k = -1;
+    if (t == 0 && off == -1) k = 0;
+    else if (t == 1 && off == 1) k = 1;
+    else if (t == 2 || t == 3) k = 2;
+    else if (t == 4 && off == -2) k = 3;
+    else if (t == 5 && off == 2) k = 4;
+    if (k < 0) {
+      atomicOr(&state[d], kEdgeStateGeneric);
+      continue;
+    }
+    const uint32_t old = atomicOr(&state[d], 1u << k);
+    if (old & (1u << k)) atomicOr(&state[d], kEdgeStateGeneric);   // a second edge of this class
+    else position[size_t(k) * N + d] = int32_t(e);
+  }
+  if (bad) atomicOr(status, GFX_GRAPH_BAD_EDGE);
+}
+
+__global__ void edge_describe_kernel(const int32_t *__restrict__ src, const uint8_t *__restrict__ typ,
+                                     int32_t base, int64_t N, const uint32_t *__restrict__ state,
+                                     const int32_t *__restrict__ position, uint32_t *__restrict__ desc,
+                                     int32_t *__restrict__ needs_csr) {
+  using namespace rowdesc;
+  bool generic_seen = false;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < N;
+       i += int64_t(gridDim.x) * blockDim.x) {
+    const uint32_t st = state[i];
+    uint32_t d = 0;
+    bool generic = (st & kEdgeStateGeneric) != 0;
+    int32_t prev_pos = -1;
+    constexpr uint32_t bits[5] = {kPrev, kNext, kPair, kPrev2, kNext2};
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      if (!(st & (1u << k)) || generic) continue;
+      const int32_t pos = position[size_t(k) * N + i];
+      if (pos < prev_pos) generic = true;          // not the CSR order of a banded row
+      prev_pos = pos;
+      d |= bits[k];
+      if (k == 2) {
+        const int32_t partner = src[pos] - base;
+        if (uint32_t(partner) > kPartnerMask) generic = true;
+        d |= (typ[pos] == 3 ? kPairRev : 0u) | (uint32_t(partner) << kPartnerShift);
+      }
+    }
+    desc[i] = generic ? kGeneric : d;
+    generic_seen |= generic;
+  }
+  if (generic_seen) *needs_csr = 1;                // benign race: every writer stores 1
 }
 
 // ---------------------------------------------------------------------------
@@ -293,11 +381,33 @@ extern "C" int gfx_csr_build(const int32_t *edge_src, const int32_t *edge_dst,
                                col_type, nullptr, ws, ws_bytes, stream);
 }
 
+static int csr_build(const int32_t *edge_src, const int32_t *edge_dst, const uint8_t *edge_type,
+                     int64_t N, int64_t E, int32_t node_base, int32_t *row_ptr, int32_t *col_src,
+                     uint8_t *col_type, int32_t *status, const int32_t *gate, void *ws, size_t ws_bytes,
+                     void *stream);
+
 extern "C" int gfx_csr_build_checked(const int32_t *edge_src, const int32_t *edge_dst,
                                      const uint8_t *edge_type, int64_t N, int64_t E,
                                      int32_t node_base, int32_t *row_ptr, int32_t *col_src,
                                      uint8_t *col_type, int32_t *status, void *ws,
                                      size_t ws_bytes, void *stream) {
+  return csr_build(edge_src, edge_dst, edge_type, N, E, node_base, row_ptr, col_src, col_type, status,
+                   nullptr, ws, ws_bytes, stream);
+}
+
+extern "C" int gfx_csr_build_if(const int32_t *edge_src, const int32_t *edge_dst,
+                                const uint8_t *edge_type, int64_t N, int64_t E, int32_t node_base,
+                                int32_t *row_ptr, int32_t *col_src, uint8_t *col_type,
+                                const int32_t *needs_csr, void *ws, size_t ws_bytes, void *stream) {
+  if (!needs_csr) return fail(GFX_ERR_ARGUMENT, "gfx_csr_build_if: null flag");
+  return csr_build(edge_src, edge_dst, edge_type, N, E, node_base, row_ptr, col_src, col_type, nullptr,
+                   needs_csr, ws, ws_bytes, stream);
+}
+
+static int csr_build(const int32_t *edge_src, const int32_t *edge_dst, const uint8_t *edge_type,
+                     int64_t N, int64_t E, int32_t node_base, int32_t *row_ptr, int32_t *col_src,
+                     uint8_t *col_type, int32_t *status, const int32_t *gate, void *ws, size_t ws_bytes,
+                     void *stream) {
   if (N < 0 || E < 0 || N >= (int64_t(1) << 31) - 1 || E >= (int64_t(1) << 31) - 1)
     return fail(GFX_ERR_ARGUMENT, "gfx_csr_build: sizes must fit int32");
   if (ws_bytes < gfx_csr_workspace_bytes(N, E))
@@ -314,21 +424,53 @@ extern "C" int gfx_csr_build_checked(const int32_t *edge_src, const int32_t *edg
   GFX_CUDA(cudaMemsetAsync(deg, 0, size_t(N + 1) * 4, st));
   GFX_CUDA(cudaMemsetAsync(n_big, 0, 8, st));
   if (E > 0)
-    csr_count_kernel<<<grid_for(E, 256), 256, 0, st>>>(edge_src, edge_dst, E, node_base,
+    csr_count_kernel<<<grid_for(E, 256), 256, 0, st>>>(gate, edge_src, edge_dst, E, node_base,
                                                        uint32_t(N), deg, status);
-  int rc = exclusive_scan(deg, row_ptr, N + 1, sums, nullptr, st);
+  int rc = exclusive_scan(deg, row_ptr, N + 1, sums, nullptr, st, gate);
   if (rc) return rc;
   if (N == 0 || E == 0) {
     GFX_LAUNCH_CHECK();
     return GFX_OK;
   }
   GFX_CUDA(cudaMemsetAsync(deg, 0, size_t(N + 1) * 4, st));  // reuse as cursor
-  csr_scatter_kernel<<<grid_for(E, 256), 256, 0, st>>>(edge_src, edge_dst, E, node_base,
+  csr_scatter_kernel<<<grid_for(E, 256), 256, 0, st>>>(gate, edge_src, edge_dst, E, node_base,
                                                        uint32_t(N), row_ptr, deg, eid);
-  csr_place_kernel<<<grid_for(N, 256), 256, 0, st>>>(edge_src, edge_type, node_base, row_ptr, eid,
-                                                     N, col_src, col_type, big_rows, n_big);
-  csr_place_big_kernel<<<kNumSMs, 256, 0, st>>>(edge_src, edge_type, node_base, row_ptr, eid,
+  csr_place_kernel<<<grid_for(N, 256), 256, 0, st>>>(gate, edge_src, edge_type, node_base, row_ptr,
+                                                     eid, N, col_src, col_type, big_rows, n_big);
+  csr_place_big_kernel<<<kNumSMs, 256, 0, st>>>(gate, edge_src, edge_type, node_base, row_ptr, eid,
                                                 big_rows, n_big, col_src, col_type);
+  GFX_LAUNCH_CHECK();
+  return GFX_OK;
+}
+
+// workspace: needs_csr int32 (256 B) | state uint32[N] | position int32[5][N]
+extern "C" size_t gfx_edge_describe_workspace_bytes(int64_t N) {
+  return 256 + align256(size_t(N) * 4) + align256(size_t(N) * 20);
+}
+
+extern "C" int gfx_edge_describe(const int32_t *edge_src, const int32_t *edge_dst,
+                                 const uint8_t *edge_type, int64_t N, int64_t E, int32_t node_base,
+                                 uint32_t *desc, int32_t *status, void *ws, size_t ws_bytes,
+                                 void *stream) {
+  if (N < 0 || E < 0 || N >= (int64_t(1) << 31) - 1 || E >= (int64_t(1) << 31) - 1)
+    return fail(GFX_ERR_ARGUMENT, "gfx_edge_describe: sizes must fit int32");
+  if (!ws || ws_bytes < gfx_edge_describe_workspace_bytes(N))
+    return fail(GFX_ERR_WORKSPACE, "gfx_edge_describe: workspace too small");
+  if (N > 0 && (!desc || !status)) return fail(GFX_ERR_ARGUMENT, "gfx_edge_describe: null array");
+  cudaStream_t st = as_stream(stream);
+  char *p = static_cast<char *>(ws);
+  int32_t *needs_csr = reinterpret_cast<int32_t *>(p); p += 256;
+  uint32_t *state = reinterpret_cast<uint32_t *>(p); p += align256(size_t(N) * 4);
+  int32_t *position = reinterpret_cast<int32_t *>(p);
+  StageScope scope(GFX_STAGE_CSR, st, (E > 0 ? 1 : 0) + (N > 0 ? 1 : 0));
+  GFX_CUDA(cudaMemsetAsync(needs_csr, 0, 256, st));
+  if (N == 0) return GFX_OK;
+  GFX_CUDA(cudaMemsetAsync(state, 0, size_t(N) * 4, st));
+  if (E > 0)
+    edge_classify_kernel<<<grid_for(E, 256), 256, 0, st>>>(edge_src, edge_dst, edge_type, E, node_base,
+                                                           uint32_t(N), state, position, status);
+  edge_describe_kernel<<<grid_for(N, 256), 256, 0, st>>>(edge_src, edge_type, node_base, N, state,
+                                                         position, desc, needs_csr);
   GFX_LAUNCH_CHECK();
   return GFX_OK;
 }

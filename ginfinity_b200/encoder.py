@@ -226,6 +226,8 @@ class Ginfinity:
         self.chunk_nodes = DEFAULT_CHUNK_NODES
         self.resident_chunk_nodes = RESIDENT_CHUNK_NODES
         self.device_builder = True       # encode_many builds full-molecule graphs on the GPU
+        # banded layer kernel: row descriptors from the edge list, CSR only for GENERIC rows
+        self.describe_from_edges = os.environ.get("GFX_DESCRIBE", "edges") != "csr"
         self.last_microbatch_bounds: Optional[np.ndarray] = None
 
     def __del__(self):
@@ -335,18 +337,51 @@ class Ginfinity:
                      ) -> np.ndarray:
         return self.encode_graphs([graph], embedding_dtype=embedding_dtype)[0]
 
-    def _gfx_encode(self, n: int, stream: int, *args_before, tail, banded: bool = True) -> None:
-        """gfx_encode on the current torch stream (`stream` is its raw handle) with the layer
-        kernel chosen as described in __init__.  `banded=False`: the shard holds context nodes
-        (windowed records), whose rows the banded kernel would take through its slow CSR
-        fallback; the pair kernel, which computes the same bits, is used instead (so a record
-        encodes to the same values alone, in a batch, and next to windowed records)."""
+    def _encode_chunk(self, *, src: int, dst: int, typ: int, n: int, e: int, node_base: int, x: int,
+                      out_row: Optional[int], out: int, act: int, out_code: int,
+                      status: torch.Tensor, stream: int, banded: bool) -> None:
+        """One chunk on the current torch stream (`stream` is its raw handle; the arguments are
+        device addresses): graph preparation + gfx_encode with the layer kernel of __init__.
+
+        Full-molecule shards of the fp16 model (`banded`): row descriptors straight from the
+        edge list (gfx_edge_describe) and a CSR build that runs only if some row is GENERIC
+        (gfx_csr_build_if, decided on the device) -- graphs in the reference builder's edge
+        order never need the CSR.  Shards with context nodes (whose remapped rows the banded
+        kernel would take through its slow GENERIC loop) use the pair kernel, which computes
+        the same bits, so a record encodes to the same values alone, in a batch, and next to
+        windowed records; K1 + K2 (`GFX_FUSED=0`, full_precision) use the plain CSR."""
+        lib = nat.lib
         if self.fused < 0:
             self._choose_layer_kernel()
         mode = int(self.fused)
         if mode == 3 and not banded:
             mode = 2
-        nat.check(nat.lib.gfx_encode(*args_before, self.impl, mode, *tail, stream))
+        row_ptr = self._scratch.get("row_ptr", 4 * (n + 1))
+        col_src = self._scratch.get("col_src", 4 * max(e, 1))
+        col_type = self._scratch.get("col_type", max(e, 1))
+        csr_ws_bytes = lib.gfx_csr_workspace_bytes(n, e)
+        csr_ws = self._scratch.get("csr_ws", csr_ws_bytes)
+        enc_ws_bytes = lib.gfx_encode_workspace_bytes(n, act)
+        enc_ws = self._scratch.get("enc_ws", enc_ws_bytes)
+        if mode == 3 and act == nat.GFX_F16 and out_row is None and self.describe_from_edges:
+            desc = self._scratch.get("desc", 4 * n)
+            dws_bytes = lib.gfx_edge_describe_workspace_bytes(n)
+            dws = self._scratch.get("desc_ws", dws_bytes)
+            nat.check(lib.gfx_edge_describe(src, dst, typ, n, e, node_base, desc.data_ptr(),
+                                            status.data_ptr(), dws.data_ptr(), dws_bytes, stream))
+            nat.check(lib.gfx_csr_build_if(src, dst, typ, n, e, node_base, row_ptr.data_ptr(),
+                                           col_src.data_ptr(), col_type.data_ptr(), dws.data_ptr(),
+                                           csr_ws.data_ptr(), csr_ws_bytes, stream))
+            nat.check(lib.gfx_encode_described(self._handle, x, desc.data_ptr(), row_ptr.data_ptr(),
+                                               col_src.data_ptr(), col_type.data_ptr(), n, out,
+                                               out_code, enc_ws.data_ptr(), enc_ws_bytes, stream))
+            return
+        nat.check(lib.gfx_csr_build_checked(src, dst, typ, n, e, node_base, row_ptr.data_ptr(),
+                                            col_src.data_ptr(), col_type.data_ptr(),
+                                            status.data_ptr(), csr_ws.data_ptr(), csr_ws_bytes, stream))
+        nat.check(lib.gfx_encode(self._handle, x, row_ptr.data_ptr(), col_src.data_ptr(),
+                                 col_type.data_ptr(), out_row, n, out, act, out_code, self.impl, mode,
+                                 enc_ws.data_ptr(), enc_ws_bytes, stream))
 
     def _choose_layer_kernel(self) -> None:
         """Once per device and process: encode a fixed synthetic chunk (2^19 nodes, banded RNA-like
@@ -591,13 +626,6 @@ class Ginfinity:
                 out=self._scratch.get(f"out{k}", 128 * esize * max_n),
                 in_ready=torch.cuda.Event(), in_free=torch.cuda.Event(),
                 out_ready=torch.cuda.Event(), out_free=torch.cuda.Event()))
-        row_ptr = self._scratch.get("row_ptr", 4 * (max_n + 1))
-        col_src = self._scratch.get("col_src", 4 * max(max_e, 1))
-        col_type = self._scratch.get("col_type", max(max_e, 1))
-        csr_ws_bytes = lib.gfx_csr_workspace_bytes(max_n, max_e)
-        enc_ws_bytes = lib.gfx_encode_workspace_bytes(max_n, act)
-        csr_ws = self._scratch.get("csr_ws", csr_ws_bytes)
-        enc_ws = self._scratch.get("enc_ws", enc_ws_bytes)
         s_in.wait_stream(main)
         s_out.wait_stream(main)
 
@@ -628,17 +656,13 @@ class Ginfinity:
             main.wait_event(slot["in_ready"])
             if c >= 2:
                 main.wait_event(slot["out_free"])
-            nat.check(lib.gfx_csr_build_checked(
-                slot["src"].data_ptr(), slot["dst"].data_ptr(), slot["typ"].data_ptr(),
-                n, e, n0, row_ptr.data_ptr(), col_src.data_ptr(), col_type.data_ptr(),
-                status.data_ptr(), csr_ws.data_ptr(), csr_ws_bytes, main.cuda_stream))
             # ranks in out_row are shard-global: bias the base so rank c0 lands on row 0
             out_base = slot["out"].data_ptr() - (0 if out_row is None else c0 * 128 * esize)
-            self._gfx_encode(
-                n, main.cuda_stream, self._handle, slot["x"].data_ptr(), row_ptr.data_ptr(),
-                col_src.data_ptr(), col_type.data_ptr(),
-                None if out_row is None else out_row[n0:].data_ptr(), n, out_base,
-                act, out_code, tail=(enc_ws.data_ptr(), enc_ws_bytes), banded=out_row is None)
+            self._encode_chunk(
+                src=slot["src"].data_ptr(), dst=slot["dst"].data_ptr(), typ=slot["typ"].data_ptr(),
+                n=n, e=e, node_base=n0, x=slot["x"].data_ptr(),
+                out_row=None if out_row is None else out_row[n0:].data_ptr(), out=out_base, act=act,
+                out_code=out_code, status=status, stream=main.cuda_stream, banded=out_row is None)
             slot["in_free"].record(main)
             slot["out_ready"].record(main)
             with torch.cuda.stream(s_out):
@@ -783,14 +807,7 @@ class Ginfinity:
         max_n = max(int(node_at[b] - node_at[a]) for a, b in chunks)
         max_e = max(int(edge_at[b] - edge_at[a]) for a, b in chunks)
         outs = [self._scratch.get(f"out{k}", 128 * esize * max_n) for k in range(2)]
-        row_ptr = self._scratch.get("row_ptr", 4 * (max_n + 1))
-        col_src = self._scratch.get("col_src", 4 * max(max_e, 1))
-        col_type = self._scratch.get("col_type", max(max_e, 1))
-        csr_ws_bytes = lib.gfx_csr_workspace_bytes(max_n, max_e)
-        enc_ws_bytes = lib.gfx_encode_workspace_bytes(max_n, act)
-        csr_ws = self._scratch.get("csr_ws", csr_ws_bytes)
-        enc_ws = self._scratch.get("enc_ws", enc_ws_bytes)
-        state["keep"].append((ds, outs, row_ptr, col_src, col_type, csr_ws, enc_ws))
+        state["keep"].append((ds, outs))
         ei = ds.edge_index
         for a, b in chunks:
             n0, n1 = int(node_at[a]), int(node_at[b])
@@ -801,15 +818,11 @@ class Ginfinity:
             out = outs[turn]
             if state["out_free"][turn] is not None:
                 main.wait_event(state["out_free"][turn])
-            nat.check(lib.gfx_csr_build_checked(
-                ei[0, e0:].data_ptr() if e else None, ei[1, e0:].data_ptr() if e else None,
-                ds.edge_types[e0:].data_ptr() if e else None, n, e, n0, row_ptr.data_ptr(),
-                col_src.data_ptr(), col_type.data_ptr(), state["status"].data_ptr(),
-                csr_ws.data_ptr(), csr_ws_bytes, main.cuda_stream))
-            self._gfx_encode(
-                n, main.cuda_stream, self._handle, ds.node_features[n0:].data_ptr(),
-                row_ptr.data_ptr(), col_src.data_ptr(), col_type.data_ptr(), None, n,
-                out.data_ptr(), act, out_code, tail=(enc_ws.data_ptr(), enc_ws_bytes))
+            self._encode_chunk(
+                src=ei[0, e0:].data_ptr() if e else None, dst=ei[1, e0:].data_ptr() if e else None,
+                typ=ds.edge_types[e0:].data_ptr() if e else None, n=n, e=e, node_base=n0,
+                x=ds.node_features[n0:].data_ptr(), out_row=None, out=out.data_ptr(), act=act,
+                out_code=out_code, status=state["status"], stream=main.cuda_stream, banded=True)
             ready = torch.cuda.Event()
             ready.record(main)
             with torch.cuda.stream(s_out):
@@ -893,31 +906,18 @@ class Ginfinity:
     def _run_chunk(self, ds, n0, n1, e0, e1, out_row, out, act, out_dtype,
                    stream, status) -> None:
         n, e = n1 - n0, e1 - e0
-        lib = nat.lib
-        csr_ws_bytes = lib.gfx_csr_workspace_bytes(n, e)
-        enc_ws_bytes = lib.gfx_encode_workspace_bytes(n, act)
-        row_ptr = self._scratch.get("row_ptr", 4 * (n + 1))
-        col_src = self._scratch.get("col_src", 4 * max(e, 1))
-        col_type = self._scratch.get("col_type", max(e, 1))
-        csr_ws = self._scratch.get("csr_ws", csr_ws_bytes)
-        enc_ws = self._scratch.get("enc_ws", enc_ws_bytes)
         ei = ds.edge_index
-        nat.check(lib.gfx_csr_build_checked(
-            ei[0, e0:].data_ptr() if e else None,
-            ei[1, e0:].data_ptr() if e else None,
-            ds.edge_types[e0:].data_ptr() if e else None, n, e, n0,
-            row_ptr.data_ptr(), col_src.data_ptr(), col_type.data_ptr(),
-            status.data_ptr(), csr_ws.data_ptr(), csr_ws_bytes, stream))
         if out_row is None:
             out_base = out[n0:].data_ptr()      # identity map: row i -> n0 + i
             map_ptr = None
         else:
             out_base = out.data_ptr()           # ranks in out_row are global
             map_ptr = out_row[n0:].data_ptr()
-        self._gfx_encode(
-            n, stream, self._handle, ds.node_features[n0:].data_ptr(), row_ptr.data_ptr(),
-            col_src.data_ptr(), col_type.data_ptr(), map_ptr, n, out_base, act,
-            out_dtype, tail=(enc_ws.data_ptr(), enc_ws_bytes), banded=map_ptr is None)
+        self._encode_chunk(
+            src=ei[0, e0:].data_ptr() if e else None, dst=ei[1, e0:].data_ptr() if e else None,
+            typ=ds.edge_types[e0:].data_ptr() if e else None, n=n, e=e, node_base=n0,
+            x=ds.node_features[n0:].data_ptr(), out_row=map_ptr, out=out_base, act=act,
+            out_code=out_dtype, status=status, stream=stream, banded=map_ptr is None)
 
 
 def _check_unique_ids(records) -> None:

@@ -137,6 +137,32 @@ int gfx_csr_build_checked(const int32_t *edge_src, const int32_t *edge_dst,
                           uint8_t *col_type, int32_t *status, void *workspace,
                           size_t workspace_bytes, void *stream);
 
+/* Row descriptors of the banded fused layer straight from the edge list, and a
+ * CSR build that only runs when they say it is needed.  For graphs in the
+ * reference builder's edge order (graph.py:494-561) every row is banded and
+ * the layer kernel never reads the CSR arrays: gfx_edge_describe (one pass over
+ * the edges, one over the nodes) replaces K0 + gfx_row_describe for them.
+ *   desc      uint32 [num_nodes], bit-identical to gfx_row_describe on the CSR
+ *             of the same edges
+ *   status    device int32, OR-ed with GFX_GRAPH_BAD_EDGE like
+ *             gfx_csr_build_checked (such edges are ignored)
+ *   workspace its first int32 is the needs_csr flag: 1 when some row is GENERIC
+ *             (anything but a banded row), else 0.  gfx_csr_build_if takes that
+ *             pointer: its kernels return at once when the flag is 0, so no
+ *             host synchronisation is needed to decide. */
+size_t gfx_edge_describe_workspace_bytes(int64_t num_nodes);
+int gfx_edge_describe(const int32_t *edge_src, const int32_t *edge_dst,
+                      const uint8_t *edge_type, int64_t num_nodes,
+                      int64_t num_edges, int32_t node_base, uint32_t *desc,
+                      int32_t *status, void *workspace, size_t workspace_bytes,
+                      void *stream);
+int gfx_csr_build_if(const int32_t *edge_src, const int32_t *edge_dst,
+                     const uint8_t *edge_type, int64_t num_nodes,
+                     int64_t num_edges, int32_t node_base, int32_t *row_ptr,
+                     int32_t *col_src, uint8_t *col_type,
+                     const int32_t *needs_csr, void *workspace,
+                     size_t workspace_bytes, void *stream);
+
 /* ------------------------------------------------------------------------
  * K6  graph construction on the device, for full-molecule records of the
  * bundled graph specification.  Replaces GraphBuilder._build_full,
@@ -294,6 +320,16 @@ int gfx_encode(const gfx_model *model, const float *x, const int32_t *row_ptr,
                const int32_t *out_row, int64_t num_nodes, void *out, int dtype,
                int out_dtype, int impl, int fused, void *workspace,
                size_t workspace_bytes, void *stream);
+
+/* The same forward for the fp16 model with the banded fused layer and row
+ * descriptors supplied by the caller (gfx_edge_describe): row_ptr / col_src /
+ * col_type are read only for GENERIC rows (gfx_csr_build_if built them iff
+ * there are any).  Every node is a core node (no out_row map). */
+int gfx_encode_described(const gfx_model *model, const float *x,
+                         const uint32_t *desc, const int32_t *row_ptr,
+                         const int32_t *col_src, const uint8_t *col_type,
+                         int64_t num_nodes, void *out, int out_dtype,
+                         void *workspace, size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------
  * K5  similarity search (no reference counterpart; north-star item 4).

@@ -526,6 +526,108 @@ def test_banded_layer_arbitrary_graph(nat, dev, problem):
     assert (got[[300, 301, 500]] & 0x3f == 0x37).all() and (got & 0x80000000).sum() > 500
 
 
+def _edge_describe(nat, dev, edge_index, edge_types, n, base=0):
+    """(descriptors, needs_csr flag, status word, workspace) of gfx_edge_describe."""
+    ei, et = _up(np.ascontiguousarray(edge_index), dev), _up(np.ascontiguousarray(edge_types), dev)
+    e = int(et.shape[0])
+    desc = torch.full((n,), -7, dtype=torch.int32, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    need = nat.lib.gfx_edge_describe_workspace_bytes(n)
+    ws = torch.empty(need, dtype=torch.uint8, device=dev)
+    nat.check(nat.lib.gfx_edge_describe(ei[0].data_ptr() if e else None, ei[1].data_ptr() if e else None,
+                                        et.data_ptr() if e else None, n, e, base, desc.data_ptr(),
+                                        status.data_ptr(), ws.data_ptr(), need, _stream()))
+    torch.cuda.synchronize()
+    return desc, int(ws[:4].view(torch.int32).item()), int(status.item()), ws, (ei, et)
+
+
+def test_row_descriptors_from_the_edge_list(nat, dev, problem):
+    """gfx_edge_describe (no CSR) against gfx_row_describe on the CSR of the same edges, bit for
+    bit: full molecules (all banded, needs_csr = 0), windows with context nodes and an arbitrary
+    graph (GENERIC rows, needs_csr = 1), banded rows whose edges appear in another ORDER (the
+    summation order would differ: GENERIC), duplicates, an edge that leaves the chunk (dropped
+    and reported), a graph without edges; gfx_csr_build_if builds exactly when the flag says so;
+    gfx_encode_described computes the bits of gfx_encode(fused = 3)."""
+    import ginfinity_b200 as g
+
+    def check(edge_index, edge_types, n, expect_flag=None):
+        rp, cs, ct = device_csr(nat, dev, edge_index, edge_types, n)
+        want = _device_describe(nat, dev, rp, cs, ct, n).cpu().numpy().view(np.uint32)
+        desc, flag, status, ws, (ei, et) = _edge_describe(nat, dev, edge_index, edge_types, n)
+        got = desc.cpu().numpy().view(np.uint32)
+        assert np.array_equal(got, want)
+        assert flag == int(bool((want & 0x80000000).any())) and status == 0
+        if expect_flag is not None:
+            assert flag == expect_flag
+        # the gated build leaves poisoned arrays alone when nothing is GENERIC, else equals K0
+        e = int(et.shape[0])
+        rp2 = torch.full((n + 1,), -5, dtype=torch.int32, device=dev)
+        cs2 = torch.full((max(e, 1),), -5, dtype=torch.int32, device=dev)
+        ct2 = torch.full((max(e, 1),), 99, dtype=torch.uint8, device=dev)
+        need = nat.lib.gfx_csr_workspace_bytes(n, e)
+        cws = torch.empty(need, dtype=torch.uint8, device=dev)
+        nat.check(nat.lib.gfx_csr_build_if(ei[0].data_ptr() if e else None, ei[1].data_ptr() if e else None,
+                                           et.data_ptr() if e else None, n, e, 0, rp2.data_ptr(),
+                                           cs2.data_ptr(), ct2.data_ptr(), ws.data_ptr(),
+                                           cws.data_ptr(), need, _stream()))
+        torch.cuda.synchronize()
+        if flag:
+            assert torch.equal(rp2, rp) and torch.equal(cs2[:e], cs[:e]) and torch.equal(ct2[:e], ct[:e])
+        else:
+            assert bool((rp2 == -5).all()) and bool((cs2 == -5).all())
+        return desc, flag, (rp2, cs2, ct2)
+
+    full = g.GraphBuilder().build_shard(random_records(81, 60))
+    desc, flag, csr = check(full.edge_index, full.edge_types, full.node_count, expect_flag=0)
+    # the described forward == the forward that classifies the CSR rows itself
+    x = _up(full.node_features, dev)
+    n = full.node_count
+    rp, cs, ct = device_csr(nat, dev, full.edge_index, full.edge_types, n)
+    need = nat.lib.gfx_encode_workspace_bytes(n, 0)
+    ws = torch.empty(need, dtype=torch.uint8, device=dev)
+    a = torch.empty((n, 128), dtype=torch.float16, device=dev)
+    b = torch.empty((n, 128), dtype=torch.float16, device=dev)
+    nat.check(nat.lib.gfx_encode(problem["handle"], x.data_ptr(), rp.data_ptr(), cs.data_ptr(),
+                                 ct.data_ptr(), None, n, a.data_ptr(), 0, 0, 0, 3, ws.data_ptr(), need,
+                                 _stream()))
+    nat.check(nat.lib.gfx_encode_described(problem["handle"], x.data_ptr(), desc.data_ptr(),
+                                           csr[0].data_ptr(), csr[1].data_ptr(), csr[2].data_ptr(), n,
+                                           b.data_ptr(), 0, ws.data_ptr(), need, _stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
+
+    recs = [g.RNA(r.identifier, r.sequence, r.structure, start=r.length // 4, end=r.length // 4 + r.length // 3)
+            for r in random_records(82, 40) if r.length >= 40]
+    win = g.GraphBuilder(keep_paired_neighbours=True, context_hops=2).build_shard(recs)
+    check(win.edge_index, win.edge_types, win.node_count)
+
+    rng = np.random.default_rng(83)
+    n, e = 700, 2500
+    src, dst = rng.integers(0, n, e).astype(np.int32), rng.integers(0, n, e).astype(np.int32)
+    typ = rng.integers(0, 10, e).astype(np.uint8)
+    keep = ~np.isin(dst, [300, 301, 400, 401, 402])
+    extra = []
+    for i in (300, 301):                                   # banded, canonical order
+        extra += [(i - 1, i, 0), (i + 1, i, 1), (i + 40, i, 3), (i - 2, i, 4), (i + 2, i, 5)]
+    extra += [(401, 400, 1), (399, 400, 0)]                # banded edges in the wrong order
+    extra += [(400, 401, 0), (400, 401, 0)]                # a duplicate
+    extra += [(401, 402, 0), (403, 402, 1), (404, 402, 5), (400, 402, 4)]   # skip-2 edges swapped
+    src = np.concatenate([src[keep], np.array([a for a, _, _ in extra], np.int32)])
+    dst = np.concatenate([dst[keep], np.array([b for _, b, _ in extra], np.int32)])
+    typ = np.concatenate([typ[keep], np.array([c for _, _, c in extra], np.uint8)])
+    desc, flag, _ = check(np.stack([src, dst]), typ, n, expect_flag=1)
+    got = desc.cpu().numpy().view(np.uint32)
+    assert (got[[300, 301]] & 0x3f == 0x3f).all() and (got[[400, 401, 402]] == 0x80000000).all()
+
+    check(np.zeros((2, 0), np.int32), np.zeros(0, np.uint8), 5, expect_flag=0)      # no edges at all
+
+    # an edge into another chunk: ignored by the descriptors, reported in the status word
+    bad_index = full.edge_index.copy()
+    bad_index[0, 7] = full.node_count + 3
+    desc2, flag2, status2, _, _ = _edge_describe(nat, dev, bad_index, full.edge_types, full.node_count)
+    assert status2 == 16 and flag2 == 0
+
+
 @pytest.mark.parametrize("n", [1, 127, 128, 129, 200, 64 * 3 + 1])
 def test_tile_edges(nat, dev, problem, n):
     """Ragged sizes around the 128-row tile / 64-row block boundaries: all
