@@ -53,7 +53,6 @@ METRIC = "nucleotides/sec embedded"
 UNIT = "nt/s"
 MAX_BATCH_NODES, MAX_BATCH_EDGES = 60_000, 300_000
 FLOP_PER_NODE_MLP = 2 * 128 * 256 * 2            # K2, per layer  
-FLOP_PER_NODE_FP32 = FLOP_PER_NODE_MLP           # fp32 path: the same contraction (split fp16 MMAs)
 BYTES_PER_NODE_AGG = 539.0                        # K1 fp16, per layer
 BYTES_PER_NODE_FUSED = 539.0                      # fused layer: h in 256, h' out 256, CSR 26.7
 BYTES_PER_NODE_BANDED = 516.0                     # banded fused layer: h in 256, h' out 256, row descriptor 4

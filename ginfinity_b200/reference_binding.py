@@ -24,6 +24,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 from pathlib import Path
 
 import numpy as np
@@ -107,6 +108,7 @@ def _run_graph_shard(self, shard, embedding_dtype):
         if getattr(self, "_gfx_model", None) is None:
             # the fp16 module was rounded by .half(); the kernels fold the same values
             self._gfx_model = create_model(self._model)
+            weakref.finalize(self, _lib.gfx_model_destroy, self._gfx_model)
         st = torch.cuda.current_stream().cuda_stream
         n, e = shard.node_count, shard.edge_count
         up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev, non_blocking=True)  # noqa: E731
