@@ -87,7 +87,8 @@ struct Smem {
   static constexpr int off_h = off_z + kStages * kTileBytes;         // 3 tiles x 32 KB
   static constexpr int off_x = off_h + kHBufs * kTileBytes;          // float2 [2 halves][128 rows]
   static constexpr int off_ring = off_x + 2 * kTileM * 8;             // int [kRing]: dynamic tile-pair indices
-  static constexpr int off_bar = off_ring + kRing * 4;
+  static constexpr int off_tab = off_ring + kRing * 4;                // uint32 [8 producer warps][16 rows]: row words
+  static constexpr int off_bar = off_tab + 8 * 16 * 4;
   static constexpr int off_tmem = off_bar + kNumBars * 8;
   static constexpr int total = off_tmem + 8;
 };
@@ -146,6 +147,28 @@ __device__ __forceinline__ void epi_a(const Consts &c, uint32_t trow, uint64_t *
   tc_fence_before();
   __syncwarp();
   if (lane == 0) mbar_arrive_cluster(leader_bar);
+}
+
+// table row of a row's pair message: bit 0 of `word` clear -> -65504 everywhere (relu(x - 65504)
+// = +0: no message), else bit 1 ? t3 : t2.  Written as and/setp pairs so that ptxas turns the two
+// bit tests into ONE R2P instead of a LOP3 + ISETP each.
+__device__ __forceinline__ uint2 pair_table_row(uint32_t word, const uint2 &t2, const uint2 &t3) {
+  uint2 t;
+  asm("{\n"
+      ".reg .pred pa, pr;\n"
+      ".reg .b32 f, g;\n"
+      "and.b32 f, %2, 1;\n"
+      "setp.ne.u32 pa, f, 0;\n"
+      "and.b32 g, %2, 2;\n"
+      "setp.ne.u32 pr, g, 0;\n"
+      "selp.b32 %0, %5, %3, pr;\n"
+      "selp.b32 %1, %6, %4, pr;\n"
+      "selp.b32 %0, %0, 0xFBFFFBFF, pa;\n"
+      "selp.b32 %1, %1, 0xFBFFFBFF, pa;\n"
+      "}"
+      : "=&r"(t.x), "=&r"(t.y)
+      : "r"(word), "r"(t2.x), "r"(t2.y), "r"(t3.x), "r"(t3.y));
+  return t;
 }
 
 // developer timeline: event `ev` of tile iteration `it`, CTA 0 only
@@ -291,127 +314,152 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
     }
   } else if (warp < kMmaWarp) {
     // ================= producers: banded aggregation into the z stage ================
+    // Everything that is the same for the 32 lanes of a row -- where its pairing partner lives,
+    // which table row the pair message takes -- is computed ONCE per row by one lane (lane l and
+    // l + 16 <-> the warp's row l) and handed to the warp through a 64-byte table in shared memory
+    // (one LDS.128 fetches four rows' words).  The per-row code is then: partner address = one
+    // LOP3 + one IADD on the row's word, one LDS.64, the table-row selects and the 20 packed-half
+    // instructions.  Partners in OTHER tiles (15-30 % of the paired rows) are first copied from
+    // global memory into the row's own slot of the z stage (cp.async, no registers; the slot is
+    // free until the row's z is written by the same lane), so the row loop has one kind of load.
     reg_inc<104>();
     const int pw = warp - kProdWarp0;                 // rows [16 pw, 16 pw + 16) of every tile
+    const int li = lane & (kRowsPerWarp - 1);
     // this lane's 4 channels = 8 bytes of a row: 16-byte chunk lane / 2 of the 256-byte row
     const uint32_t kboff = uint32_t(lane >> 4) * kKbBytes;
-    const uint32_t c8 = uint32_t(lane >> 1) & 7u, odd8 = uint32_t(lane & 1) * 8u;
+    const uint32_t c8 = uint32_t(lane >> 1) & 7u, c8s = c8 << 4, odd8 = uint32_t(lane & 1) * 8u;
+    const uint32_t lx = c8s | odd8;
     auto cell = [&](int r) -> uint32_t {              // byte offset of this lane's piece of tile row r
       return kboff + uint32_t(r) * 128u + (((c8 ^ uint32_t(r)) & 7u) << 4) + odd8;
     };
+    // cj[j]: the same for the warp's row j < 8; rows 8 apart share the swizzle term, so every
+    // window / output address of the tile is one of these + the tile's base + an immediate
+    uint32_t cj[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      cj[j] = kboff + odd8 + uint32_t(kRowsPerWarp * pw + j) * 128u + (c8s ^ (uint32_t(j) << 4));
+      asm volatile("" : "+r"(cj[j]));                 // kept in registers, not recomputed per tile
+    }
     const uint2 *hg = reinterpret_cast<const uint2 *>(p.h) + lane;     // row r -> hg[r * 32]
     const uint32_t a1f[2] = {leader(kBarA1Full), leader(kBarA1Full + 1)};
-    const uint2 kNone = make_uint2(0xFBFFFBFFu, 0xFBFFFBFFu);          // -65504: relu(x + it) = +0
+    const uint32_t tab = smem_u32(smem + L::off_tab) + uint32_t(pw) * (kRowsPerWarp * 4);
     const uint32_t eps1 = p.eps1_h2;
     uint2 tb[6];                                                       // table rows of types 0..5
 #pragma unroll
     for (int k = 0; k < 6; ++k)
       tb[k] = reinterpret_cast<const uint2 *>(p.table16 + k * kHidden)[lane];
 
-    // lane l < 16 holds the descriptor of the warp's row l, fetched one tile ahead
+    // descriptor of the warp's row li of a tile pair
     auto fetch_desc = [&](int pr) -> uint32_t {
-      if (pr >= pairs || lane >= kRowsPerWarp) return 0u;
-      const int row = (2 * pr + int(rank)) * kTileM + kRowsPerWarp * pw + lane;
+      if (pr >= pairs) return 0u;
+      const int row = (2 * pr + int(rank)) * kTileM + kRowsPerWarp * pw + li;
       return row < n ? p.desc[row] : 0u;
     };
-    // Loads that leave the SM (the two halo rows just outside the tile that the first / last
-    // warp's windows reach, and pairing partners in other tiles) are issued a whole run (8 rows,
-    // ~250 instructions) before their first use and never carried across tile iterations: round
-    // 1's kernel prefetched the halo rows one TILE ahead, the compiler spilled them, and the
-    // spill store waited ~1.4 k cycles for the load it was meant to hide (timeline of r02_b).
+    // the two rows just outside the tile that the first / last warp's windows reach
+    auto fetch_halo = [&](int pr, uint2 &h0, uint2 &h1) {
+      h0 = make_uint2(0u, 0u);
+      h1 = make_uint2(0u, 0u);
+      if (pr < pairs && (pw == 0 || pw == kProdWarps - 1)) {           // warp-uniform
+        const int r0 = (2 * pr + int(rank)) * kTileM;
+        const int g0 = pw == 0 ? r0 - 2 : r0 + kTileM, g1 = g0 + 1;
+        if (g0 >= 0 && g0 < n) h0 = __ldg(hg + int64_t(g0) * 32);
+        if (g1 >= 0 && g1 < n) h1 = __ldg(hg + int64_t(g1) * 32);
+      }
+    };
+    // Requested at the hand-over of the previous tile, used after this tile's barrier waits:
+    // five registers live across the waits, none across the row code.
     int pair = first_pair();
     uint32_t dnext = fetch_desc(pair);
+    uint2 hn0, hn1;
+    fetch_halo(pair, hn0, hn1);
     uint32_t it = 0;
     for (; pair < pairs; ++it) {
-      const int pair_next = next_pair(pair, it);       // known long before it is needed
+      const int pair_next = next_pair(pair, it);
       const uint32_t s = it & 1, hb = it % kHBufs;
       const int row0 = (2 * pair + int(rank)) * kTileM;
       const uint32_t d = dnext;
+      const uint2 halo0 = hn0, halo1 = hn1;
       const uint32_t hbase = smem_u32(hs) + hb * kTileBytes;
       const uint32_t zbase = smem_u32(zs) + s * kTileBytes;
       mbar_wait_s(bar + kBarHFull + hb, (it / kHBufs) & 1, p.sleep_ns);
       mbar_wait_s(bar + kBarA1Empty + s, ((it >> 1) & 1) ^ 1, p.sleep_ns);
       if (warp == kProdWarp0 && lane == 0) trace_ev(p, it, 0);
       if (warp == kProdWarp0 + 3 && lane == 0) trace_ev(p, it, 13);
-      uint2 halo0 = make_uint2(0u, 0u), halo1 = make_uint2(0u, 0u);
-      if ((pw == 0 || pw == kProdWarps - 1) && !(p.dbg & 2u)) {               // warp-uniform
-        const int g0 = pw == 0 ? row0 - 2 : row0 + kTileM, g1 = g0 + 1;
-        if (g0 >= 0 && g0 < n) halo0 = __ldg(hg + int64_t(g0) * 32);
-        if (g1 >= 0 && g1 < n) halo1 = __ldg(hg + int64_t(g1) * 32);
+
+      // ---- one word per row: [17:3] shared-memory address of the partner row's first chunk
+      // (kb 0, swizzle term of the row in bits 4-6), bit 0 = has a pair message, bit 1 = of type 3
+      const uint32_t self = uint32_t(kRowsPerWarp * pw + li);
+      const bool paired = (d & (kDescPair | kDescGeneric)) == kDescPair;
+      const uint32_t psrc = (d >> kDescPartnerShift) & kDescPartnerMask;
+      const uint32_t plocal = psrc - uint32_t(row0);
+      const bool away = paired && plocal >= uint32_t(kTileM);          // partner in another tile
+      const uint32_t tgt = (paired && !away) ? plocal : self;          // no pair: reads itself
+      uint32_t word = (away ? zbase : hbase) + (tgt << 7) + ((tgt & 7u) << 4);
+      word |= (paired ? 1u : 0u) | ((d & kDescPairRev) ? 2u : 0u);
+      if (lane < kRowsPerWarp) sts32(tab + 4u * uint32_t(lane), word);
+      uint32_t stage = __ballot_sync(0xffffffffu, away) & ((1u << kRowsPerWarp) - 1u);
+      __syncwarp();
+      while (stage) {                                                  // warp-uniform
+        const int idx = __ffs(int(stage)) - 1;
+        stage &= stage - 1;
+        const uint32_t g = __shfl_sync(0xffffffffu, psrc, idx);
+        cp_async8(zbase + cell(kRowsPerWarp * pw + idx), hg + int64_t(g) * 32);
       }
-      // partner row of tile row `idx` of this warp (a row without a pair reads itself; its message is +0)
-      auto partner = [&](int idx) -> uint2 {
-        const uint32_t dj = __shfl_sync(0xffffffffu, d, idx);
-        const int self = kRowsPerWarp * pw + idx;
-        const int src = (dj & kDescPair) ? int((dj >> kDescPartnerShift) & kDescPartnerMask) : row0 + self;
-        const uint32_t local = uint32_t(src - row0);
-        const uint32_t in_tile = (local < uint32_t(kTileM) || (p.dbg & 1u)) ? 1u : 0u;
-        return ld_tile_or_global8(in_tile, hbase + cell(int(local & (kTileM - 1))), hg + int64_t(src) * 32);
-      };
-      // the first warp takes its runs in reverse: the run that needs the halo rows comes last
-      const int first_run = pw == 0 ? 1 : 0;
-      uint2 pnext[kRun];
+
+      // ---- the 16 rows, two runs of 8 with a 12-row window each (rows 8 run - 2 .. 8 run + 9).
+      // z = fma(1+eps, h, ((((m_prev + m_next) + m_pair) + m_prev2) + m_next2)) in fp16, the CSR
+      // order of a banded row.  Every row is computed as an INTERIOR row here (its four backbone /
+      // skip neighbours taken from the window as they are, no selects); the few rows that lack a
+      // neighbour (molecule ends: ~2 % of the rows) are recomputed after the runs (`ends` below).
+      // A row without a pair reads itself with the -65504 table value: relu(x - 65504) = +0.
+      static_assert(kRowsPerWarp / kRun == 2 && kRun == 8, "two runs of 8 rows per warp and tile");
+      uint2 w[kRun + 4];
 #pragma unroll
-      for (int q = 0; q < kRun; ++q) pnext[q] = partner(kRun * first_run + q);
-#pragma unroll 1
-      for (int step = 0; step < ((p.dbg & 32u) ? 0 : kRowsPerWarp / kRun); ++step) {
-        static_assert(kRowsPerWarp / kRun == 2, "two runs per warp and tile");
-        const int run = first_run ^ step;
-        const int base = kRowsPerWarp * pw + kRun * run;   // first tile row of the run
-        uint32_t dj[kRun];                                 // the run's descriptors, warp-uniform
+      for (int run = 0; run < 2; ++run) {
+        if (p.dbg & 32u) break;                                        // timing experiments only
+        const uint32_t ro = uint32_t(run) * 1024u;
+        if (run == 0) {
+          if (pw == 0) {                                               // warp-uniform
+            w[0] = halo0;
+            w[1] = halo1;
+          } else {
+            w[0] = lds64(hbase + cj[6] - 1024u);
+            w[1] = lds64(hbase + cj[7] - 1024u);
+          }
+          w[2] = lds64(hbase + cj[0]);
+          w[3] = lds64(hbase + cj[1]);
+        } else {                                                       // rows 6 .. 9: still in registers
 #pragma unroll
-        for (int j = 0; j < kRun; ++j) dj[j] = __shfl_sync(0xffffffffu, d, kRun * run + j);
+          for (int k = 0; k < 4; ++k) w[k] = w[kRun + k];
+        }
+#pragma unroll
+        for (int k = 2; k < kRun; ++k) w[2 + k] = lds64(hbase + cj[k] + ro);
+        if (run == 0) {
+          w[kRun + 2] = lds64(hbase + cj[0] + 1024u);
+          w[kRun + 3] = lds64(hbase + cj[1] + 1024u);
+        } else if (pw == kProdWarps - 1) {                             // warp-uniform
+          w[kRun + 2] = halo0;
+          w[kRun + 3] = halo1;
+        } else {
+          w[kRun + 2] = lds64(hbase + cj[0] + 2048u);
+          w[kRun + 3] = lds64(hbase + cj[1] + 2048u);
+        }
+        const uint4 wa = lds128(tab + 32u * uint32_t(run)), wb = lds128(tab + 32u * uint32_t(run) + 16u);
+        const uint32_t wd[kRun] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+        if (run == 0) cp_async_wait_all();                             // the staged partner rows
         uint2 pr[kRun];
 #pragma unroll
-        for (int q = 0; q < kRun; ++q) pr[q] = pnext[q];
-        // window: tile rows base - 2 .. base + kRun + 1.  base is a multiple of 8, so the swizzle
-        // term of row base - 2 + k depends on k only: one XOR with an immediate per row.  Only
-        // the first two / last two rows of the window can lie outside the tile (first / last run
-        // of the tile: warp-uniform), where the prefetched halo rows stand in.
-        static_assert(kRun == 8, "the swizzle pattern repeats every 8 rows");
-        const uint32_t wbase = hbase + kboff + odd8 + uint32_t(base) * 128u;   // row `base`, chunk 0
-        const uint32_t c8s = c8 << 4;
-        auto wrow = [&](int k) -> uint2 {                   // k = 0 .. kRun + 3 <-> row base - 2 + k
-          return lds64(wbase + uint32_t((k - 2) * 128) + (c8s ^ (uint32_t((k - 2) & 7) << 4)));
-        };
-        const bool first = base == 0, last = base + kRun == kTileM;
-        uint2 w[kRun + 4];
-        w[0] = halo0;
-        w[1] = halo1;
-        if (!first) {
-          w[0] = wrow(0);
-          w[1] = wrow(1);
-        }
-#pragma unroll
-        for (int k = 2; k < kRun + 2; ++k) w[k] = wrow(k);
-        w[kRun + 2] = halo0;
-        w[kRun + 3] = halo1;
-        if (!last) {
-          w[kRun + 2] = wrow(kRun + 2);
-          w[kRun + 3] = wrow(kRun + 3);
-        }
-        if (step == 0) {                                   // the other run's partners, a run ahead
-#pragma unroll
-          for (int q = 0; q < kRun; ++q) pnext[q] = partner(kRun * (run ^ 1) + q);
-        }
-        // z = fma(1+eps, h, ((((m_prev + m_next) + m_pair) + m_prev2) + m_next2)) in fp16, the CSR
-        // order of a banded row.  Every row is computed as an INTERIOR row here (its four backbone /
-        // skip neighbours taken from the window as they are, no selects); the few rows that lack a
-        // neighbour (molecule ends: ~2 % of the rows) are recomputed after the runs (`ends` below).
-        // A row without a pair reads itself with the -65504 table value: relu(x - 65504) = +0.
+        for (int j = 0; j < kRun; ++j) pr[j] = lds64(((wd[j] ^ lx) & ~7u) + kboff);
 #pragma unroll
         for (int j = 0; j < kRun; ++j) {
-          const uint32_t dd = dj[j];
-          uint2 tp = (dd & kDescPairRev) ? tb[3] : tb[2];
-          tp = (dd & kDescPair) ? tp : kNone;
-          const uint2 pp = pr[j];
           uint2 acc;
           acc.x = h2_relu_add(w[j + 1].x, tb[0].x);
           acc.y = h2_relu_add(w[j + 1].y, tb[0].y);
           acc.x = h2_add(acc.x, h2_relu_add(w[j + 3].x, tb[1].x));
           acc.y = h2_add(acc.y, h2_relu_add(w[j + 3].y, tb[1].y));
-          acc.x = h2_add(acc.x, h2_relu_add(pp.x, tp.x));
-          acc.y = h2_add(acc.y, h2_relu_add(pp.y, tp.y));
+          const uint2 tp = pair_table_row(wd[j], tb[2], tb[3]);
+          acc.x = h2_add(acc.x, h2_relu_add(pr[j].x, tp.x));
+          acc.y = h2_add(acc.y, h2_relu_add(pr[j].y, tp.y));
           acc.x = h2_add(acc.x, h2_relu_add(w[j].x, tb[4].x));
           acc.y = h2_add(acc.y, h2_relu_add(w[j].y, tb[4].y));
           acc.x = h2_add(acc.x, h2_relu_add(w[j + 4].x, tb[5].x));
@@ -419,7 +467,7 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
           uint2 o;
           o.x = h2_fma(eps1, w[j + 2].x, acc.x);
           o.y = h2_fma(eps1, w[j + 2].y, acc.y);
-          sts64(zbase + kboff + odd8 + uint32_t(base + j) * 128u + (c8s ^ (uint32_t(j & 7) << 4)), o);
+          sts64(zbase + cj[j] + ro, o);
         }
       }
       // molecule ends: banded rows that lack a backbone / skip neighbour, one row at a time
@@ -449,10 +497,10 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
         }
         if (dd & kDescPrev2) add(row_at(lr - 2), tb[4]);
         if (dd & kDescNext2) add(row_at(lr + 2), tb[5]);
-        const uint2 self = lds64(hbase + cell(lr));
+        const uint2 self_h = lds64(hbase + cell(lr));
         uint2 o;
-        o.x = h2_fma(eps1, self.x, acc.x);
-        o.y = h2_fma(eps1, self.y, acc.y);
+        o.x = h2_fma(eps1, self_h.x, acc.x);
+        o.y = h2_fma(eps1, self_h.y, acc.y);
         sts64(zbase + cell(lr), o);
       }
       // rows that are not banded: recomputed from the CSR arrays, one row at a time (warp-uniform);
@@ -472,16 +520,16 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
             acc.x = h2_add(acc.x, h2_relu_add(v.x, tt.x));
             acc.y = h2_add(acc.y, h2_relu_add(v.y, tt.y));
           }
-          const uint2 self = lds64(hbase + cell(lr));
+          const uint2 self_h = lds64(hbase + cell(lr));
           uint2 o;
-          o.x = h2_fma(eps1, self.x, acc.x);
-          o.y = h2_fma(eps1, self.y, acc.y);
+          o.x = h2_fma(eps1, self_h.x, acc.x);
+          o.y = h2_fma(eps1, self_h.y, acc.y);
           sts64(zbase + cell(lr), o);
         }
       }
-      // the next tile's descriptors: requested here so that nothing is live across the run loop;
-      // the load completes during the hand-over and the waits of the next iteration
+      // the next tile's descriptors and halo rows: in flight during the hand-over and the waits
       dnext = fetch_desc(pair_next);
+      fetch_halo(pair_next, hn0, hn1);
       pair = pair_next;
       if (warp == kProdWarp0 && lane == 0) trace_ev(p, it, 15);
       if (warp == kProdWarp0 + 3 && lane == 0) trace_ev(p, it, 14);

@@ -86,6 +86,15 @@ __device__ __forceinline__ uint2 lds64(uint32_t saddr) {
 __device__ __forceinline__ void sts64(uint32_t saddr, const uint2 &v) {
   asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(saddr), "r"(v.x), "r"(v.y) : "memory");
 }
+__device__ __forceinline__ void sts32(uint32_t saddr, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
+// 8 bytes global -> shared without a register in between (LDGSTS); complete for the issuing
+// thread after cp_async_wait_all()
+__device__ __forceinline__ void cp_async8(uint32_t saddr, const void *gptr) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(saddr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ float2 lds_f2(uint32_t saddr) {
   float2 v;
   asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(saddr));
