@@ -171,6 +171,19 @@ __device__ __forceinline__ uint2 pair_table_row(uint32_t word, const uint2 &t2, 
   return t;
 }
 
+// one lane of the (converged) warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // developer timeline: event `ev` of tile iteration `it`, CTA 0 only
 __device__ __forceinline__ void trace_ev(const Args &p, uint32_t it, int ev) {
   if (p.trace != nullptr && blockIdx.x == 0 && it < 64) p.trace[it * 16 + ev] = clock64();
@@ -558,50 +571,64 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
                  bar + kBarWLocal);
       mbar_wait_parked(bar + kBarWLocal, 0);
       mbar_arrive_cluster(leader(kBarWReady));
-      if (rank == 0) {
-        mbar_wait_c(bar + kBarWReady, 0);
-        constexpr uint32_t idesc = idesc_f16(2 * kTileM, H);     // M = 256 over the pair, N = 128
-        // descriptors = one 64-bit base per operand + a small immediate per MMA.  The bases are
-        // laundered through an empty asm inside the tile loop: otherwise the compiler hoists all
-        // 32 descriptors of the two unrolled GEMMs out of the loop and spills them (this role
-        // runs on 40 registers).
-        uint64_t w1d = smem_desc_sw128(smem_u32(w1s)), w2d = smem_desc_sw128(smem_u32(w2s));
-        uint32_t it = 0;
-        for (int pair = first_pair(); pair < pairs; pair = next_pair(pair, it), ++it) {
-          const uint32_t s = it & 1, g = it & 1, ph2 = (it >> 1) & 1, ph = it & 1;
-          uint64_t zd = smem_desc_sw128(smem_u32(zs) + s * kTileBytes);
-          asm volatile("" : "+l"(w1d), "+l"(w2d), "+l"(zd));
-          mbar_wait_c(bar + kBarA1Full + s, ph2);
-          tc_fence_after();
+    }
+    __syncwarp();
+    if (rank == 0) {
+      // The WHOLE warp runs the tile loop and waits on the barriers; one elected lane issues.
+      // Issued from inside an `if (lane == 0)` region the operands of every MMA (descriptors,
+      // TMEM addresses) were ordinary registers to the compiler, and each tcgen05.mma came
+      // wrapped in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop: 11-13 instructions per MMA on a
+      // warp that gets one issue slot in six -- GEMM 2's sixteen MMAs took ~1.4 k cycles to
+      // ISSUE (timeline of r02_e).  With warp-uniform operands they live in uniform registers.
+      mbar_wait_c(bar + kBarWReady, 0);
+      const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+      const bool issuer = elect_one();
+      constexpr uint32_t idesc = idesc_f16(2 * kTileM, H);       // M = 256 over the pair, N = 128
+      constexpr uint32_t idesc_w = idesc_f16(2 * kTileM, HID);   // GEMM 1: N = 256
+      const uint64_t w1d = smem_desc_sw128(smem_u32(w1s)), w2d = smem_desc_sw128(smem_u32(w2s));
+      uint32_t it = 0;
+      for (int pair = first_pair(); pair < pairs; pair = next_pair(pair, it), ++it) {
+        const uint32_t s = it & 1, g = it & 1, ph2 = (it >> 1) & 1, ph = it & 1;
+        const uint64_t zd = smem_desc_sw128(smem_u32(zs) + s * kTileBytes);
+        mbar_wait_c(bar + kBarA1Full + s, ph2);
+        tc_fence_after();
+        if (issuer) {
           trace_ev(p, it, 2);
-          constexpr uint32_t idesc_w = idesc_f16(2 * kTileM, HID);   // GEMM 1: N = 256
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk) {
             const int kb = kk >> 2, k = kk & 3;
-            mma2_f16_ss(tmem, zd + uint64_t((kb * kKbBytes + k * 32) >> 4),
+            mma2_f16_ss(tm, zd + uint64_t((kb * kKbBytes + k * 32) >> 4),
                         w1d + uint64_t((kb * 2 * kWPiece + k * 32) >> 4), idesc_w, kk != 0);
           }
           mma2_commit(bar + kBarD1aFull);
           mma2_commit(bar + kBarD1bFull);
           mma2_commit(bar + kBarA1Empty + s);          // z consumed in both CTAs
           trace_ev(p, it, 3);
-          mbar_wait_c(bar + kBarA2aFull, ph);
-          mbar_wait_c(bar + kBarD2Empty + g, ph2 ^ 1);
-          tc_fence_after();
+        }
+        __syncwarp();
+        mbar_wait_c(bar + kBarA2aFull, ph);
+        mbar_wait_c(bar + kBarD2Empty + g, ph2 ^ 1);
+        tc_fence_after();
+        const uint32_t d2 = tm + kD2Col + g * kHidden;
+        if (issuer) {
           trace_ev(p, it, 4);
-          const uint32_t d2 = tmem + kD2Col + g * kHidden;
 #pragma unroll
-          for (int kk = 0; kk < HID / 16; ++kk) {
-            if (kk == H / 16) {
-              mbar_wait_c(bar + kBarA2bFull, ph);
-              tc_fence_after();
-            }
-            mma2_f16_ts(d2, tmem + kk * 8, w2d + uint64_t(((kk >> 2) * kWPiece + (kk & 3) * 32) >> 4),
+          for (int kk = 0; kk < H / 16; ++kk)
+            mma2_f16_ts(d2, tm + kk * 8, w2d + uint64_t(((kk >> 2) * kWPiece + (kk & 3) * 32) >> 4),
                         idesc, kk != 0);
-          }
+        }
+        __syncwarp();
+        mbar_wait_c(bar + kBarA2bFull, ph);
+        tc_fence_after();
+        if (issuer) {
+#pragma unroll
+          for (int kk = H / 16; kk < HID / 16; ++kk)
+            mma2_f16_ts(d2, tm + kk * 8, w2d + uint64_t(((kk >> 2) * kWPiece + (kk & 3) * 32) >> 4),
+                        idesc, 1u);
           mma2_commit(bar + kBarD2Full + g);
           trace_ev(p, it, 5);
         }
+        __syncwarp();
       }
     }
     __syncwarp();
