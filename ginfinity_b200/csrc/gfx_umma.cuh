@@ -106,6 +106,13 @@ template <int N>
 __device__ __forceinline__ void bulk_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
+// 2-D tile into L2 only (no shared-memory destination, no completion to wait for)
+__device__ __forceinline__ void tma_prefetch_2d(const void *tmap, int x, int y) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(
+                   reinterpret_cast<uint64_t>(tmap)),
+               "r"(x), "r"(y)
+               : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const void *tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
 }
