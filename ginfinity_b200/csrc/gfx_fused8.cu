@@ -493,23 +493,30 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
         ends &= ends - 1;
         const uint32_t dd = __shfl_sync(0xffffffffu, d, idx);
         const int lr = kRowsPerWarp * pw + idx;
-        auto row_at = [&](int local) -> uint2 {         // tile row `local`, possibly just outside the tile
-          return uint32_t(local) < uint32_t(kTileM) ? lds64(hbase + cell(local))
-                                                     : __ldg(hg + int64_t(row0 + local) * 32);
+        // all five rows are requested before the first is used (a missing neighbour reads the
+        // row itself with the -65504 table value: its message is +0, and acc + 0 = acc): four
+        // such rows in a row -- wherever two molecules meet -- otherwise cost the warp ~2 k
+        // cycles of dependent shared-memory latency, and the MMA waits for the slowest of the
+        // pair's sixteen producer warps
+        auto value = [&](uint32_t has, int local) -> uint2 {
+          local = has ? local : lr;
+          return ld_tile_or_global8(uint32_t(local) < uint32_t(kTileM) ? 1u : 0u,
+                                    hbase + cell(local & (kTileM - 1)), hg + int64_t(row0 + local) * 32);
         };
         uint2 acc = make_uint2(0u, 0u);
         auto add = [&](const uint2 &v, const uint2 &t) {
           acc.x = h2_add(acc.x, h2_relu_add(v.x, t.x));
           acc.y = h2_add(acc.y, h2_relu_add(v.y, t.y));
         };
-        if (dd & kDescPrev) add(row_at(lr - 1), tb[0]);
-        if (dd & kDescNext) add(row_at(lr + 1), tb[1]);
-        if (dd & kDescPair) {
-          const int src = int((dd >> kDescPartnerShift) & kDescPartnerMask);
-          add(row_at(src - row0), (dd & kDescPairRev) ? tb[3] : tb[2]);
-        }
-        if (dd & kDescPrev2) add(row_at(lr - 2), tb[4]);
-        if (dd & kDescNext2) add(row_at(lr + 2), tb[5]);
+        const uint2 kNone = make_uint2(0xFBFFFBFFu, 0xFBFFFBFFu);      // -65504
+        const uint2 v0 = value(dd & kDescPrev, lr - 1), v1 = value(dd & kDescNext, lr + 1);
+        const uint2 v2 = value(dd & kDescPair, int((dd >> kDescPartnerShift) & kDescPartnerMask) - row0);
+        const uint2 v3 = value(dd & kDescPrev2, lr - 2), v4 = value(dd & kDescNext2, lr + 2);
+        add(v0, (dd & kDescPrev) ? tb[0] : kNone);
+        add(v1, (dd & kDescNext) ? tb[1] : kNone);
+        add(v2, (dd & kDescPair) ? ((dd & kDescPairRev) ? tb[3] : tb[2]) : kNone);
+        add(v3, (dd & kDescPrev2) ? tb[4] : kNone);
+        add(v4, (dd & kDescNext2) ? tb[5] : kNone);
         const uint2 self_h = lds64(hbase + cell(lr));
         uint2 o;
         o.x = h2_fma(eps1, self_h.x, acc.x);
