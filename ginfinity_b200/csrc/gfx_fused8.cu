@@ -195,9 +195,18 @@ __device__ __forceinline__ void trace_ev(const Args &p, uint32_t it, int ev) {
 // Rank 0's loader thread fetches the cluster's next pair index two iterations ahead and publishes
 // it to both CTAs through a 16-entry shared-memory ring (st.shared::cluster + a cluster-scope
 // mbarrier arrive for the peer); every role reads entry it + 1 at the top of iteration it.
-template <bool DYN>
+// DEV: the developer build (timeline stamps, GFX_DBG experiments, GFX_SCHED=dynamic).  The
+// production instance has none of those tests in its loops: the kernel is bound by the number of
+// instructions its warps issue.
+template <bool DYN, bool DEV>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWarps * 32, 1)
-fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Consts c, const Args p) {
+fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Consts c, const Args p_in) {
+  static_assert(DEV || !DYN, "the dynamic scheduler is a developer option");
+  Args p = p_in;
+  if (!DEV) {
+    p.dbg = 0u;
+    p.trace = nullptr;
+  }
   using L = Smem;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t *w1s = smem + L::off_w1, *w2s = smem + L::off_w2, *zs = smem + L::off_z;
@@ -821,7 +830,9 @@ int fused8_layer(const gfx_model *m, int layer, const __half *h, const int32_t *
     a.sched = m->sched_counters + slot;
     GFX_CUDA(cudaMemsetAsync(a.sched, 0, sizeof(uint32_t), st));
   }
-  auto kernel = dynamic ? v8::fused_banded8_kernel<true> : v8::fused_banded8_kernel<false>;
+  const bool dev = dynamic || a.dbg != 0u || a.trace != nullptr;
+  auto kernel = dynamic ? v8::fused_banded8_kernel<true, true>
+                        : dev ? v8::fused_banded8_kernel<false, true> : v8::fused_banded8_kernel<false, false>;
   GFX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v8::Smem::total));
   const int64_t tiles = (n + v8::kTileM - 1) / v8::kTileM;
   const int64_t pairs = (tiles + 1) / 2;
