@@ -206,6 +206,7 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
   if (!DEV) {
     p.dbg = 0u;
     p.trace = nullptr;
+    p.sleep_ns = 64u;                            // (GFX_FUSED_SLEEP_NS selects the developer instance)
   }
   using L = Smem;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -296,7 +297,7 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
     const uint32_t xme = smem_u32(smem + L::off_x) + uint32_t(half * kTileM + r) * 8u;
     const uint32_t xother = smem_u32(smem + L::off_x) + uint32_t((half ^ 1) * kTileM + r) * 8u;
     const uint32_t named = 1u + uint32_t(quad);                    // bar.sync id of this row group
-    const uint32_t d2e[2] = {leader(kBarD2Empty), leader(kBarD2Empty + 1)};
+    const uint32_t d2e0 = leader(kBarD2Empty);                    // + 8 g: consecutive barriers
     reg_inc<88>();
     uint32_t it = 0;
     for (int pair = first_pair(); pair < pairs; pair = next_pair(pair, it), ++it) {
@@ -313,7 +314,7 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
       } else if (half) epi_b_load<1>(c, tcol, t); else epi_b_load<0>(c, tcol, t);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(d2e[g]);
+      if (lane == 0) mbar_arrive_cluster(d2e0 + 8u * g);
       const float2 mine = epi_b_stats(t);
       sts_f2(xme, mine);
       named_bar_sync(named, 64);
@@ -363,7 +364,7 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
       asm volatile("" : "+r"(cj[j]));                 // kept in registers, not recomputed per tile
     }
     const uint2 *hg = reinterpret_cast<const uint2 *>(p.h) + lane;     // row r -> hg[r * 32]
-    const uint32_t a1f[2] = {leader(kBarA1Full), leader(kBarA1Full + 1)};
+    const uint32_t a1f0 = leader(kBarA1Full);                     // + 8 s: consecutive barriers
     const uint32_t tab = smem_u32(smem + L::off_tab) + uint32_t(pw) * (kRowsPerWarp * 4);
     const uint32_t eps1 = p.eps1_h2;
     uint2 tb[6];                                                       // table rows of types 0..5
@@ -419,13 +420,22 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
       uint32_t word = (away ? zbase : hbase) + (tgt << 7) + ((tgt & 7u) << 4);
       word |= (paired ? 1u : 0u) | ((d & kDescPairRev) ? 2u : 0u);
       if (lane < kRowsPerWarp) sts32(tab + 4u * uint32_t(lane), word);
+      // two rows per step: lanes 0-15 copy the 16 chunks (16 bytes each) of one row, lanes 16-31
+      // those of the next; every lane later reads back the 8 bytes of ITS column slice, which
+      // another lane copied: cp_async_wait_all + __syncwarp before the first use (in the runs)
       uint32_t stage = __ballot_sync(0xffffffffu, away) & ((1u << kRowsPerWarp) - 1u);
       __syncwarp();
       while (stage) {                                                  // warp-uniform
-        const int idx = __ffs(int(stage)) - 1;
-        stage &= stage - 1;
+        const uint32_t first = stage & (0u - stage), rest = stage ^ first;
+        const uint32_t second = rest & (0u - rest);
+        stage = rest ^ second;
+        const uint32_t mine = (lane < 16 || second == 0u) ? first : second;
+        const int idx = __ffs(int(mine)) - 1;
         const uint32_t g = __shfl_sync(0xffffffffu, psrc, idx);
-        cp_async8(zbase + cell(kRowsPerWarp * pw + idx), hg + int64_t(g) * 32);
+        const uint32_t r = uint32_t(kRowsPerWarp * pw + idx), c16 = uint32_t(lane) & 15u;
+        const uint32_t dst = zbase + (c16 >> 3) * kKbBytes + r * 128u + (((c16 ^ r) & 7u) << 4);
+        if (lane < 16 || second != 0u)
+          cp_async16_plain(dst, reinterpret_cast<const uint8_t *>(p.h) + int64_t(g) * (kHidden * 2) + c16 * 16u);
       }
 
       // ---- the 16 rows, two runs of 8 with a 12-row window each (rows 8 run - 2 .. 8 run + 9).
@@ -468,7 +478,10 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
         }
         const uint4 wa = lds128(tab + 32u * uint32_t(run)), wb = lds128(tab + 32u * uint32_t(run) + 16u);
         const uint32_t wd[kRun] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-        if (run == 0) cp_async_wait_all();                             // the staged partner rows
+        if (run == 0) {                                                // the staged partner rows
+          cp_async_wait_all();
+          __syncwarp();
+        }
         uint2 pr[kRun];
 #pragma unroll
         for (int j = 0; j < kRun; ++j) pr[j] = lds64(((wd[j] ^ lx) & ~7u) + kboff);
@@ -564,7 +577,7 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
       if (warp == kProdWarp0 + 3 && lane == 0) trace_ev(p, it, 14);
       if (!(p.dbg & 4u)) fence_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(a1f[s]);
+      if (lane == 0) mbar_arrive_cluster(a1f0 + 8u * s);
       if (warp == kProdWarp0 && lane == 0) trace_ev(p, it, 1);
     }
   } else if (warp == kMmaWarp) {
@@ -830,7 +843,7 @@ int fused8_layer(const gfx_model *m, int layer, const __half *h, const int32_t *
     a.sched = m->sched_counters + slot;
     GFX_CUDA(cudaMemsetAsync(a.sched, 0, sizeof(uint32_t), st));
   }
-  const bool dev = dynamic || a.dbg != 0u || a.trace != nullptr;
+  const bool dev = dynamic || a.dbg != 0u || a.trace != nullptr || a.sleep_ns != 64u;
   auto kernel = dynamic ? v8::fused_banded8_kernel<true, true>
                         : dev ? v8::fused_banded8_kernel<false, true> : v8::fused_banded8_kernel<false, false>;
   GFX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v8::Smem::total));

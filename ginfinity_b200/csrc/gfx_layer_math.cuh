@@ -94,6 +94,9 @@ __device__ __forceinline__ void sts32(uint32_t saddr, uint32_t v) {
 __device__ __forceinline__ void cp_async8(uint32_t saddr, const void *gptr) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(saddr), "l"(gptr) : "memory");
 }
+__device__ __forceinline__ void cp_async16_plain(uint32_t saddr, const void *gptr) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gptr) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ float2 lds_f2(uint32_t saddr) {
   float2 v;

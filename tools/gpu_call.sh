@@ -4,5 +4,4 @@ timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -x -q > gpurun_out
 for i in 1 2 3; do
   GFX_LIBRARY=$PWD/ginfinity_b200/libgfx_prev.so timeout 120 python tools/fused_probe.py gfx_layer_fused_banded 2>&1 | tail -1 | sed 's/^/prev /'
   timeout 120 python tools/fused_probe.py gfx_layer_fused_banded 2>&1 | tail -1 | sed 's/^/new  /'
-  GFX_DBG=256 timeout 120 python tools/fused_probe.py gfx_layer_fused_banded 2>&1 | tail -1 | sed 's/^/dev  /'
 done
