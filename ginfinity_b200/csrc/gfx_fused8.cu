@@ -508,8 +508,12 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
       // molecule ends: banded rows that lack a backbone / skip neighbour, one row at a time
       // (warp-uniform), same chain in the same order with the missing terms left out
       constexpr uint32_t kBackbone = kDescPrev | kDescNext | kDescPrev2 | kDescNext2;
-      uint32_t ends = __ballot_sync(0xffffffffu, lane < kRowsPerWarp && !(d & kDescGeneric) &&
-                                                     (d & kBackbone) != kBackbone);
+      // (one vote for both kinds of rows that are recomputed: bit l = row l is a molecule end,
+      // bit 16 + l = row l is not banded; lanes l and l + 16 hold the same descriptor)
+      const bool is_generic = (d & kDescGeneric) != 0u;
+      const uint32_t redo = __ballot_sync(0xffffffffu, lane < kRowsPerWarp ? (!is_generic && (d & kBackbone) != kBackbone)
+                                                                            : is_generic);
+      uint32_t ends = redo & ((1u << kRowsPerWarp) - 1u);
       while (ends) {
         const int idx = __ffs(int(ends)) - 1;
         ends &= ends - 1;
@@ -547,7 +551,7 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
       }
       // rows that are not banded: recomputed from the CSR arrays, one row at a time (warp-uniform);
       // same fp16 chain in CSR order (the first message starts the sum)
-      if (__ballot_sync(0xffffffffu, (d & kDescGeneric) != 0u) != 0u) {
+      if (redo >> kRowsPerWarp) {
 #pragma unroll 1
         for (int idx = 0; idx < kRowsPerWarp; ++idx) {
           if (!(__shfl_sync(0xffffffffu, d, idx) & kDescGeneric)) continue;
