@@ -30,6 +30,20 @@
 //    gfx_fused6.cu (the CSR-walking form used for shards with context nodes) follows the same
 //    order, so the two kernels still agree bit for bit.
 //
+//  * (later in round 2, after the timeline and the ncu source page showed that the kernel follows
+//    its executed-instruction count almost linearly -- +40 instructions per producer warp and
+//    tile cost 5 %) the producers are TABLE-DRIVEN: everything that is the same for the 32 lanes
+//    of a row (where its pairing partner lives, which table row the pair message takes) is
+//    computed once per row by one lane and handed to the warp through a 64-byte table in shared
+//    memory; partners in other tiles are staged by cp.async into the row's own z slot so that the
+//    row code has one kind of load: 67 -> 31 instructions per row.  The MMA warp runs its loop
+//    converged with one elected lane issuing (operands in uniform registers: 1-3 instead of 11-13
+//    instructions per tcgen05.mma), the loader prefetches the next h tile into L2, molecule-end
+//    rows request their five source rows before the chain, and the production instance
+//    (template DEV = false) carries none of the developer tests in its loops.
+//    603k-node probe: 0.146 -> 0.105 ms; ncu: 129 -> 89 warp instructions per node-layer, tensor
+//    pipe 28.6 -> 41.7 % active.
+//
 // Warps per CTA (24; 80 registers per thread at launch = 61,440 for the CTA, re-balanced with
 // setmaxnreg within that allocation: epilogue A 56, epilogue B 88, producers 104, utility 40 --
 // 128 x 56 + 256 x 88 + 256 x 104 + 128 x 40 = 61,440 exactly):
