@@ -682,7 +682,7 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
   } else if (warp == kLoadWarp) {
     // ================= h tiles (TMA) =================================================
     reg_dec<40>();
-    if (lane == 0) {
+    if (DYN && lane == 0) {                       // developer option: one thread, scheduler included
       prefetch_tmap(&maps.h);
       auto load_tile = [&](int pair, uint32_t it) {
         const uint32_t hb = it % kHBufs;
@@ -694,7 +694,7 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
         tma_load_2d(dst, &maps.h, 0, row0, bar + kBarHFull + hb);
         tma_load_2d(dst + kKbBytes, &maps.h, 64, row0, bar + kBarHFull + hb);
       };
-      if (DYN && rank == 0) {
+      if (rank == 0) {
         // the cluster's scheduler: entries it + 1 and it + 2 of the ring are always published
         // before the tile of iteration `it` is requested; once the counter passes the last pair
         // its value is the end mark every role stops at
@@ -720,46 +720,66 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
           nxt = after;
         }
       } else {
-        // the tile after the one being requested is pulled into L2 now: when its buffer frees, a
-        // period later, the TMA load finds it there (~0.8 k instead of ~1.8 k cycles, and the
-        // buffer's life cycle is what sets the period)
-        auto prefetch_tile = [&](int pair) {
-          const int row0 = (2 * pair + int(rank)) * kTileM;
-          if (pair < pairs && row0 < n && !(p.dbg & 2u)) {
-            tma_prefetch_2d(&maps.h, 0, row0);
-            tma_prefetch_2d(&maps.h, 64, row0);
-          }
-        };
         uint32_t it = 0;
-        for (int pair = first_pair(); pair < pairs; pair = next_pair(pair, it), ++it) {
-          load_tile(pair, it);
-          prefetch_tile(pair + clusters);
-        }
+        for (int pair = first_pair(); pair < pairs; pair = next_pair(pair, it), ++it) load_tile(pair, it);
       }
     }
     __syncwarp();
+    if (!DYN) {
+      // The whole warp runs the loop and waits; one elected lane issues (as in the MMA warp:
+      // issued from inside `if (lane == 0)` every TMA instruction came wrapped in an ELECT /
+      // R2UR.BROADCAST loop, ~70 instructions per tile on a warp that gets one issue slot in
+      // six -- between "buffer free" and "load issued", i.e. on the buffer's life cycle).
+      const bool issuer = elect_one();
+      if (issuer) prefetch_tmap(&maps.h);
+      uint32_t it = 0;
+      for (int pair = first_pair(); pair < pairs; pair = next_pair(pair, it), ++it) {
+        const uint32_t hb = it % kHBufs;
+        const int row0 = (2 * pair + int(rank)) * kTileM;
+        uint8_t *dst = hs + hb * kTileBytes;
+        mbar_wait_s(bar + kBarHEmpty + hb, ((it / kHBufs) & 1) ^ 1, p.sleep_ns);
+        if (issuer) {
+          trace_ev(p, it, 12);
+          mbar_arrive_expect_tx(bar + kBarHFull + hb, kTileBytes);
+          tma_load_2d(dst, &maps.h, 0, row0, bar + kBarHFull + hb);
+          tma_load_2d(dst + kKbBytes, &maps.h, 64, row0, bar + kBarHFull + hb);
+          // the tile after this one is pulled into L2 now: when its buffer frees, a period
+          // later, the TMA load finds it there (~0.8 k instead of ~1.8 k cycles)
+          const int next_row0 = row0 + 2 * clusters * kTileM;
+          if (pair + clusters < pairs && next_row0 < n && !(p.dbg & 2u)) {
+            tma_prefetch_2d(&maps.h, 0, next_row0);
+            tma_prefetch_2d(&maps.h, 64, next_row0);
+          }
+        }
+        __syncwarp();
+      }
+    }
   } else if (warp == kStoreWarp) {
     // ================= output store (TMA) ============================================
     reg_dec<40>();
-    if (lane == 0) {
-      prefetch_tmap(&maps.out);
+    {
+      const bool issuer = elect_one();            // the same lane every time: bulk groups are per thread
+      if (issuer) prefetch_tmap(&maps.out);
       uint32_t it = 0;
       for (int pair = first_pair(); pair < pairs; pair = next_pair(pair, it), ++it) {
         const uint32_t hb = it % kHBufs;
         const int row0 = (2 * pair + int(rank)) * kTileM;
         const uint8_t *src = hs + hb * kTileBytes;
         mbar_wait_s(bar + kBarOReady + hb, (it / kHBufs) & 1, p.sleep_ns);
-        trace_ev(p, it, 10);
-        if (row0 < n) {
-          tma_store_2d(&maps.out, 0, row0, src);
-          tma_store_2d(&maps.out, 64, row0, src + kKbBytes);
+        if (issuer) {
+          trace_ev(p, it, 10);
+          if (row0 < n) {
+            tma_store_2d(&maps.out, 0, row0, src);
+            tma_store_2d(&maps.out, 64, row0, src + kKbBytes);
+          }
+          bulk_commit();
+          bulk_wait_read<0>();                    // shared memory has been read: the buffer is free
+          mbar_arrive(bar + kBarHEmpty + hb);
+          trace_ev(p, it, 11);
         }
-        bulk_commit();
-        bulk_wait_read<0>();                      // shared memory has been read: the buffer is free
-        mbar_arrive(bar + kBarHEmpty + hb);
-        trace_ev(p, it, 11);
+        __syncwarp();
       }
-      bulk_wait_all();
+      if (issuer) bulk_wait_all();
     }
     __syncwarp();
   } else {
