@@ -109,7 +109,7 @@ struct Smem {
 static_assert(Smem::total <= 232448, "exceeds the 227 KB shared-memory limit of sm_100");
 
 struct alignas(64) Maps {
-  CUtensorMap h, out;        // [n, 128] fp16, box 64 x 128, SWIZZLE_128B
+  CUtensorMap h, out;        // [n, 128] fp16, SWIZZLE_128B; box 64 x 128 (h), 64 x 32 (out)
 };
 
 struct Args {
@@ -243,8 +243,8 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
     mbar_init(bar + kBarWReady, 2);
     for (int s = 0; s < kHBufs; ++s) {
       mbar_init(bar + kBarHFull + s, 1);
-      mbar_init(bar + kBarHEmpty + s, 1);
-      mbar_init(bar + kBarOReady + s, kEpiBWarps);
+      mbar_init(bar + kBarHEmpty + s, kEpiBWarps);
+      mbar_init(bar + kBarOReady + s, 1);              // (unused: every epilogue-B warp stores its own block)
     }
     for (int s = 0; s < kRing; ++s) mbar_init(bar + kBarSched + s, 1);
     for (int s = 0; s < 2; ++s) {
@@ -313,6 +313,8 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
     const uint32_t named = 1u + uint32_t(quad);                    // bar.sync id of this row group
     const uint32_t d2e0 = leader(kBarD2Empty);                    // + 8 g: consecutive barriers
     reg_inc<88>();
+    const bool issuer = elect_one();              // the same lane every time: bulk groups are per thread
+    if (issuer) prefetch_tmap(&maps.out);
     uint32_t it = 0;
     for (int pair = first_pair(); pair < pairs; pair = next_pair(pair, it), ++it) {
       const uint32_t g = it & 1, hb = it % kHBufs;
@@ -344,11 +346,26 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
       const uint32_t hrow = smem_u32(hs) + hb * kTileBytes;
       if (p.dbg & 8u) {
       } else if (half) epi_b_store<1>(c, t, hrow, r, rstd, nm); else epi_b_store<0>(c, t, hrow, r, rstd, nm);
+      // every warp stores its own 32 x 64 block (4 KB, contiguous in the swizzled tile) as soon
+      // as it is written and hands the buffer back when the TMA engine has read it: no store
+      // warp in between, no waiting for the slowest of the eight (the buffer's life cycle sets
+      // the kernel's period)
       fence_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar + kBarOReady + hb);
+      if (issuer) {
+        const int out_row = (2 * pair + int(rank)) * kTileM + 32 * quad;
+        if (out_row < n)
+          tma_store_2d(&maps.out, 64 * half, out_row,
+                       hs + hb * kTileBytes + half * kKbBytes + 32 * quad * 128);
+        bulk_commit();
+        bulk_wait_read<0>();
+        mbar_arrive(bar + kBarHEmpty + hb);
+      }
+      __syncwarp();
       if (lane == 0 && warp == kEpiBWarp0) trace_ev(p, it, 9);
     }
+    if (issuer) bulk_wait_all();
+    __syncwarp();
   } else if (warp < kMmaWarp) {
     // ================= producers: banded aggregation into the z stage ================
     // Everything that is the same for the 32 lanes of a row -- where its pairing partner lives,
@@ -754,36 +771,8 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
         __syncwarp();
       }
     }
-  } else if (warp == kStoreWarp) {
-    // ================= output store (TMA) ============================================
-    reg_dec<40>();
-    {
-      const bool issuer = elect_one();            // the same lane every time: bulk groups are per thread
-      if (issuer) prefetch_tmap(&maps.out);
-      uint32_t it = 0;
-      for (int pair = first_pair(); pair < pairs; pair = next_pair(pair, it), ++it) {
-        const uint32_t hb = it % kHBufs;
-        const int row0 = (2 * pair + int(rank)) * kTileM;
-        const uint8_t *src = hs + hb * kTileBytes;
-        mbar_wait_s(bar + kBarOReady + hb, (it / kHBufs) & 1, p.sleep_ns);
-        if (issuer) {
-          trace_ev(p, it, 10);
-          if (row0 < n) {
-            tma_store_2d(&maps.out, 0, row0, src);
-            tma_store_2d(&maps.out, 64, row0, src + kKbBytes);
-          }
-          bulk_commit();
-          bulk_wait_read<0>();                    // shared memory has been read: the buffer is free
-          mbar_arrive(bar + kBarHEmpty + hb);
-          trace_ev(p, it, 11);
-        }
-        __syncwarp();
-      }
-      if (issuer) bulk_wait_all();
-    }
-    __syncwarp();
   } else {
-    reg_dec<40>();                                // spare warp of the utility warpgroup
+    reg_dec<40>();                                // two spare warps of the utility warpgroup
   }
   tc_fence_before();
   __syncthreads();
@@ -837,7 +826,7 @@ int fused8_layer(const gfx_model *m, int layer, const __half *h, const int32_t *
     return fail(GFX_ERR_UNSUPPORTED, "fused layer (banded): needs the six backbone / pair / skip edge types");
   v8::Maps maps;
   int rc = tma::make_rows128_map(&maps.h, h, n, v8::kTileM);
-  if (!rc) rc = tma::make_rows128_map(&maps.out, h_out, n, v8::kTileM);
+  if (!rc) rc = tma::make_rows128_map(&maps.out, h_out, n, 32);      // one epilogue-B warp's 32 rows x 64 columns
   if (rc) return rc;
   v8::Consts c;
   const gfx_host_vectors &hv = m->host;
