@@ -469,11 +469,19 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
           cp_async16_plain(dst, reinterpret_cast<const uint8_t *>(p.h) + int64_t(g) * (kHidden * 2) + c16 * 16u);
       }
 
+      // one vote for both kinds of rows that are recomputed: bit l = row l is a molecule end (a
+      // banded row that lacks a backbone / skip neighbour), bit 16 + l = row l is not banded;
+      // lanes l and l + 16 hold the same descriptor
+      constexpr uint32_t kBackbone = kDescPrev | kDescNext | kDescPrev2 | kDescNext2;
+      const bool is_generic = (d & kDescGeneric) != 0u;
+      const uint32_t redo = __ballot_sync(0xffffffffu, lane < kRowsPerWarp ? (!is_generic && (d & kBackbone) != kBackbone)
+                                                                            : is_generic);
+
       // ---- the 16 rows, two runs of 8 with a 12-row window each (rows 8 run - 2 .. 8 run + 9).
       // z = fma(1+eps, h, ((((m_prev + m_next) + m_pair) + m_prev2) + m_next2)) in fp16, the CSR
       // order of a banded row.  Every row is computed as an INTERIOR row here (its four backbone /
       // skip neighbours taken from the window as they are, no selects); the few rows that lack a
-      // neighbour (molecule ends: ~2 % of the rows) are recomputed after the runs (`ends` below).
+      // neighbour (molecule ends: ~2 % of the rows) are recomputed at the end of their run.
       // A row without a pair reads itself with the -65504 table value: relu(x - 65504) = +0.
       static_assert(kRowsPerWarp / kRun == 2 && kRun == 8, "two runs of 8 rows per warp and tile");
       uint2 w[kRun + 4];
@@ -535,50 +543,39 @@ fused_banded8_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
           o.y = h2_fma(eps1, w[j + 2].y, acc.y);
           sts64(zbase + cj[j] + ro, o);
         }
-      }
-      // molecule ends: banded rows that lack a backbone / skip neighbour, one row at a time
-      // (warp-uniform), same chain in the same order with the missing terms left out
-      constexpr uint32_t kBackbone = kDescPrev | kDescNext | kDescPrev2 | kDescNext2;
-      // (one vote for both kinds of rows that are recomputed: bit l = row l is a molecule end,
-      // bit 16 + l = row l is not banded; lanes l and l + 16 hold the same descriptor)
-      const bool is_generic = (d & kDescGeneric) != 0u;
-      const uint32_t redo = __ballot_sync(0xffffffffu, lane < kRowsPerWarp ? (!is_generic && (d & kBackbone) != kBackbone)
-                                                                            : is_generic);
-      uint32_t ends = redo & ((1u << kRowsPerWarp) - 1u);
-      while (ends) {
-        const int idx = __ffs(int(ends)) - 1;
-        ends &= ends - 1;
-        const uint32_t dd = __shfl_sync(0xffffffffu, d, idx);
-        const int lr = kRowsPerWarp * pw + idx;
-        // all five rows are requested before the first is used (a missing neighbour reads the
-        // row itself with the -65504 table value: its message is +0, and acc + 0 = acc): four
-        // such rows in a row -- wherever two molecules meet -- otherwise cost the warp ~2 k
-        // cycles of dependent shared-memory latency, and the MMA waits for the slowest of the
-        // pair's sixteen producer warps
-        auto value = [&](uint32_t has, int local) -> uint2 {
-          local = has ? local : lr;
-          return ld_tile_or_global8(uint32_t(local) < uint32_t(kTileM) ? 1u : 0u,
-                                    hbase + cell(local & (kTileM - 1)), hg + int64_t(row0 + local) * 32);
-        };
-        uint2 acc = make_uint2(0u, 0u);
-        auto add = [&](const uint2 &v, const uint2 &t) {
-          acc.x = h2_add(acc.x, h2_relu_add(v.x, t.x));
-          acc.y = h2_add(acc.y, h2_relu_add(v.y, t.y));
-        };
-        const uint2 kNone = make_uint2(0xFBFFFBFFu, 0xFBFFFBFFu);      // -65504
-        const uint2 v0 = value(dd & kDescPrev, lr - 1), v1 = value(dd & kDescNext, lr + 1);
-        const uint2 v2 = value(dd & kDescPair, int((dd >> kDescPartnerShift) & kDescPartnerMask) - row0);
-        const uint2 v3 = value(dd & kDescPrev2, lr - 2), v4 = value(dd & kDescNext2, lr + 2);
-        add(v0, (dd & kDescPrev) ? tb[0] : kNone);
-        add(v1, (dd & kDescNext) ? tb[1] : kNone);
-        add(v2, (dd & kDescPair) ? ((dd & kDescPairRev) ? tb[3] : tb[2]) : kNone);
-        add(v3, (dd & kDescPrev2) ? tb[4] : kNone);
-        add(v4, (dd & kDescNext2) ? tb[5] : kNone);
-        const uint2 self_h = lds64(hbase + cell(lr));
-        uint2 o;
-        o.x = h2_fma(eps1, self_h.x, acc.x);
-        o.y = h2_fma(eps1, self_h.y, acc.y);
-        sts64(zbase + cell(lr), o);
+        // Molecule ends of this run (~2 % of the rows, four in a row wherever two molecules meet:
+        // one run in eight has some): recomputed HERE, from the window and partner registers that
+        // are still live, with -65504 selected for the table row of every missing neighbour: ~35
+        // instructions per row.  A separate pass that gathered each row's five source rows again
+        // (~130 instructions per row, ~520 for the warp that meets a boundary) made that warp the
+        // one the other fifteen of the pair wait for.
+        const uint32_t ends_run = (redo >> (kRun * run)) & 0xffu;              // warp-uniform
+        if (ends_run) {
+          const uint2 none = make_uint2(0xFBFFFBFFu, 0xFBFFFBFFu);             // -65504
+#pragma unroll
+          for (int j = 0; j < kRun; ++j) {
+            if (!(ends_run & (1u << j))) continue;
+            const uint32_t dd = __shfl_sync(0xffffffffu, d, kRun * run + j);
+            const uint2 t0 = (dd & kDescPrev) ? tb[0] : none, t1 = (dd & kDescNext) ? tb[1] : none;
+            const uint2 t4 = (dd & kDescPrev2) ? tb[4] : none, t5 = (dd & kDescNext2) ? tb[5] : none;
+            const uint2 tp = pair_table_row(wd[j], tb[2], tb[3]);
+            uint2 acc;
+            acc.x = h2_relu_add(w[j + 1].x, t0.x);
+            acc.y = h2_relu_add(w[j + 1].y, t0.y);
+            acc.x = h2_add(acc.x, h2_relu_add(w[j + 3].x, t1.x));
+            acc.y = h2_add(acc.y, h2_relu_add(w[j + 3].y, t1.y));
+            acc.x = h2_add(acc.x, h2_relu_add(pr[j].x, tp.x));
+            acc.y = h2_add(acc.y, h2_relu_add(pr[j].y, tp.y));
+            acc.x = h2_add(acc.x, h2_relu_add(w[j].x, t4.x));
+            acc.y = h2_add(acc.y, h2_relu_add(w[j].y, t4.y));
+            acc.x = h2_add(acc.x, h2_relu_add(w[j + 4].x, t5.x));
+            acc.y = h2_add(acc.y, h2_relu_add(w[j + 4].y, t5.y));
+            uint2 o;
+            o.x = h2_fma(eps1, w[j + 2].x, acc.x);
+            o.y = h2_fma(eps1, w[j + 2].y, acc.y);
+            sts64(zbase + cj[j] + ro, o);
+          }
+        }
       }
       // rows that are not banded: recomputed from the CSR arrays, one row at a time (warp-uniform);
       // same fp16 chain in CSR order (the first message starts the sum)
