@@ -168,39 +168,61 @@ topk_scan_kernel(const __grid_constant__ Maps maps, const Args p) {
 
   if (warp == kLoadWarp) {
     // ================================ TMA loader =================================
-    if (lane == 0) {
-      prefetch_tmap(&maps.q);
-      prefetch_tmap(&maps.db);
+    // (whole warp in the loop, one elected lane issues: see the MMA issuer below)
+    {
+      uint32_t elected;
+      asm volatile("{\n.reg .pred q;\nelect.sync _|q, 0xffffffff;\nselp.u32 %0, 1, 0, q;\n}" : "=r"(elected));
+      const bool issuer = elected != 0u;
+      if (issuer) {
+        prefetch_tmap(&maps.q);
+        prefetch_tmap(&maps.db);
+      }
       uint32_t it = 0, item_n = 0;
       for (int64_t item = blockIdx.x; item < items; item += gridDim.x, ++item_n) {
         const int64_t qt = item % p.tiles_q, seg = item / p.tiles_q;
         mbar_wait(bar + kBarQEmpty, (item_n & 1) ^ 1);
-        mbar_arrive_expect_tx(bar + kBarQFull, kQBytes);
+        if (issuer) {
+          mbar_arrive_expect_tx(bar + kBarQFull, kQBytes);
 #pragma unroll
-        for (int b = 0; b < 4; ++b)
-          tma_load_2d(qs + b * kBoxBytes, &maps.q, (b & 1) * 64, int(qt * kQTile + (b >> 1) * 128),
-                      bar + kBarQFull);
+          for (int b = 0; b < 4; ++b)
+            tma_load_2d(qs + b * kBoxBytes, &maps.q, (b & 1) * 64, int(qt * kQTile + (b >> 1) * 128),
+                        bar + kBarQFull);
+        }
+        __syncwarp();
         const int64_t t0 = seg * p.tiles_per_seg;
         const int64_t t1 = t0 + p.tiles_per_seg < p.tiles_db ? t0 + p.tiles_per_seg : p.tiles_db;
         for (int64_t t = t0; t < t1; ++t, ++it) {
           const uint32_t s = it % kStages, ph = (it / kStages) & 1;
           uint8_t *dst = dbs + s * kDbBytes;
           mbar_wait(bar + kBarBEmpty + s, ph ^ 1);
-          mbar_arrive_expect_tx(bar + kBarBFull + s, kDbBytes + (METRIC == 1 ? kDbTile * 4 : 0));
-          tma_load_2d(dst, &maps.db, 0, int(t * kDbTile), bar + kBarBFull + s);
-          tma_load_2d(dst + kBoxBytes, &maps.db, 64, int(t * kDbTile), bar + kBarBFull + s);
-          if (METRIC == 1)
-            bulk_g2s(d2s + (it % kD2Slots) * kDbTile, p.d2 + t * kDbTile, kDbTile * 4,
-                     bar + kBarBFull + s);
+          if (issuer) {
+            mbar_arrive_expect_tx(bar + kBarBFull + s, kDbBytes + (METRIC == 1 ? kDbTile * 4 : 0));
+            tma_load_2d(dst, &maps.db, 0, int(t * kDbTile), bar + kBarBFull + s);
+            tma_load_2d(dst + kBoxBytes, &maps.db, 64, int(t * kDbTile), bar + kBarBFull + s);
+            if (METRIC == 1)
+              bulk_g2s(d2s + (it % kD2Slots) * kDbTile, p.d2 + t * kDbTile, kDbTile * 4,
+                       bar + kBarBFull + s);
+          }
+          __syncwarp();
         }
       }
     }
     __syncwarp();
   } else if (warp == kMmaWarp) {
     // ================================ MMA issuer =================================
-    if (lane == 0) {
+    // The whole warp runs the loop and waits on the barriers; one elected lane issues.  Issued
+    // from inside `if (lane == 0)` the operands of every MMA were ordinary registers to the
+    // compiler and each tcgen05.mma came wrapped in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop
+    // (11-13 instructions per MMA on a warp that shares its scheduler with epilogue warps: more
+    // than the 64 cycles an MMA of this shape takes); with warp-uniform operands they live in
+    // uniform registers (measured on the fused layer kernel).
+    {
       constexpr uint32_t idesc = idesc_f16(128, kDbTile);
       const uint32_t qa = smem_u32(qs), ba = smem_u32(dbs);
+      const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+      uint32_t elected;
+      asm volatile("{\n.reg .pred q;\nelect.sync _|q, 0xffffffff;\nselp.u32 %0, 1, 0, q;\n}" : "=r"(elected));
+      const bool issuer = elected != 0u;
       uint32_t it = 0, item_n = 0;
       for (int64_t item = blockIdx.x; item < items; item += gridDim.x, ++item_n) {
         const int64_t seg = item / p.tiles_q;
@@ -212,20 +234,24 @@ topk_scan_kernel(const __grid_constant__ Maps maps, const Args p) {
           mbar_wait(bar + kBarBFull + s, ph);
           mbar_wait(bar + kBarDEmpty + a, pha ^ 1);
           tc_fence_after();
+          if (issuer) {
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
+            for (int half = 0; half < 2; ++half) {
 #pragma unroll
-            for (int kk = 0; kk < 8; ++kk) {
-              const int kb = kk >> 2, k = kk & 3;
-              const uint64_t da = smem_desc_sw128(qa + (half * 2 + kb) * kBoxBytes + k * 32);
-              const uint64_t db = smem_desc_sw128(ba + s * kDbBytes + kb * kBoxBytes + k * 32);
-              mma_f16_ss(tmem + a * 256 + half * 128, da, db, idesc, kk != 0);
+              for (int kk = 0; kk < 8; ++kk) {
+                const int kb = kk >> 2, k = kk & 3;
+                const uint64_t da = smem_desc_sw128(qa + (half * 2 + kb) * kBoxBytes + k * 32);
+                const uint64_t db = smem_desc_sw128(ba + s * kDbBytes + kb * kBoxBytes + k * 32);
+                mma_f16_ss(tm + a * 256 + half * 128, da, db, idesc, kk != 0);
+              }
             }
+            mma_commit(bar + kBarBEmpty + s);
+            mma_commit(bar + kBarDFull + a);
           }
-          mma_commit(bar + kBarBEmpty + s);
-          mma_commit(bar + kBarDFull + a);
+          __syncwarp();
         }
-        mma_commit(bar + kBarQEmpty);         // every MMA reading this item's queries is done
+        if (issuer) mma_commit(bar + kBarQEmpty);   // every MMA reading this item's queries is done
+        __syncwarp();
       }
     }
     __syncwarp();
