@@ -462,8 +462,18 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Con
                  bar + kBarWLocal);
       mbar_wait_parked(bar + kBarWLocal, 0);
       mbar_arrive_cluster(leader(kBarWReady));
-      if (rank == 0) {
-        mbar_wait_c(bar + kBarWReady, 0);
+    }
+    __syncwarp();
+    if (rank == 0) {
+      // the whole warp runs the tile loop and waits, one elected lane issues: MMA operands in
+      // uniform registers instead of an ELECT / R2UR.BROADCAST loop around every tcgen05.mma
+      // (gfx_fused8.cu)
+      mbar_wait_c(bar + kBarWReady, 0);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+      uint32_t elected;
+      asm volatile("{\n.reg .pred q;\nelect.sync _|q, 0xffffffff;\nselp.u32 %0, 1, 0, q;\n}" : "=r"(elected));
+      const bool issuer = elected != 0u;
+      {
         constexpr uint32_t idesc = idesc_f16(2 * kTileM, H);     // M = 256 over the pair, N = 128
         const uint32_t w1a = smem_u32(w1s), w2a = smem_u32(w2s);
         uint32_t it = 0;
@@ -472,6 +482,7 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Con
           const uint32_t za = smem_u32(zs) + s * kTileBytes;
           mbar_wait_c(bar + kBarA1Full + s, ph2);
           tc_fence_after();
+          if (issuer) {
           trace_ev(p, it, 2);
           if (WIDE) {
             constexpr uint32_t idesc_w = idesc_f16(2 * kTileM, HID);   // GEMM 1: N = 256
@@ -480,7 +491,7 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Con
               const int kb = kk >> 2, k = kk & 3;
               const uint64_t da = smem_desc_sw128(za + kb * kKbBytes + k * 32);
               const uint64_t db = smem_desc_sw128(w1a + kb * 2 * kWPiece + k * 32);
-              mma2_f16_ss(tmem, da, db, idesc_w, kk != 0);
+              mma2_f16_ss(tmem_u, da, db, idesc_w, kk != 0);
             }
             mma2_commit(bar + kBarD1aFull);
             mma2_commit(bar + kBarD1bFull);
@@ -492,28 +503,39 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Con
                 const int kb = kk >> 2, k = kk & 3;
                 const uint64_t da = smem_desc_sw128(za + kb * kKbBytes + k * 32);
                 const uint64_t db = smem_desc_sw128(w1a + (kb * 2 + half) * kWPiece + k * 32);
-                mma2_f16_ss(tmem + half * H, da, db, idesc, kk != 0);
+                mma2_f16_ss(tmem_u + half * H, da, db, idesc, kk != 0);
               }
               mma2_commit(bar + (half ? kBarD1bFull : kBarD1aFull));
             }
           }
           mma2_commit(bar + kBarA1Empty + s);          // z consumed in both CTAs
           trace_ev(p, it, 3);
+          }
+          __syncwarp();
           mbar_wait_c(bar + kBarA2aFull, ph);
           mbar_wait_c(bar + kBarD2Empty + g, ph2 ^ 1);
           tc_fence_after();
-          trace_ev(p, it, 4);
+          if (issuer) {
+            trace_ev(p, it, 4);
 #pragma unroll
-          for (int kk = 0; kk < HID / 16; ++kk) {
-            if (kk == H / 16) {
-              mbar_wait_c(bar + kBarA2bFull, ph);
-              tc_fence_after();
+            for (int kk = 0; kk < H / 16; ++kk) {
+              const uint64_t db = smem_desc_sw128(w2a + (kk >> 2) * kWPiece + (kk & 3) * 32);
+              mma2_f16_ts(tmem_u + kD2Col + g * kHidden, tmem_u + kk * 8, db, idesc, kk != 0);
             }
-            const uint64_t db = smem_desc_sw128(w2a + (kk >> 2) * kWPiece + (kk & 3) * 32);
-            mma2_f16_ts(tmem + kD2Col + g * kHidden, tmem + kk * 8, db, idesc, kk != 0);
           }
-          mma2_commit(bar + kBarD2Full + g);
-          trace_ev(p, it, 5);
+          __syncwarp();
+          mbar_wait_c(bar + kBarA2bFull, ph);
+          tc_fence_after();
+          if (issuer) {
+#pragma unroll
+            for (int kk = H / 16; kk < HID / 16; ++kk) {
+              const uint64_t db = smem_desc_sw128(w2a + (kk >> 2) * kWPiece + (kk & 3) * 32);
+              mma2_f16_ts(tmem_u + kD2Col + g * kHidden, tmem_u + kk * 8, db, idesc, 1u);
+            }
+            mma2_commit(bar + kBarD2Full + g);
+            trace_ev(p, it, 5);
+          }
+          __syncwarp();
         }
       }
     }

@@ -314,18 +314,28 @@ split_kernel(const __grid_constant__ Consts c, const Args p) {
       }
       mbar_wait_parked(bar + kBarWLocal, 0);
       mbar_arrive_cluster(leader(kBarWReady));
-      if (rank == 0) {
-        mbar_wait_parked(bar + kBarWReady, 0);
-        constexpr uint32_t idesc1 = idesc_f16(2 * kTileM, N1);
-        constexpr uint32_t idesc2 = idesc_f16(2 * kTileM, kHidden);
-        uint64_t w1d[2] = {smem_desc_sw128(smem_u32(smem + L::off_w1h)), smem_desc_sw128(smem_u32(smem + L::off_w1l))};
-        uint64_t w2d[2] = {smem_desc_sw128(smem_u32(smem + L::off_w2h)), smem_desc_sw128(smem_u32(smem + L::off_w2l))};
-        uint64_t ad[2] = {smem_desc_sw128(smem_u32(smem + L::off_ah)), smem_desc_sw128(smem_u32(smem + L::off_al))};
-        uint32_t it = 0;
-        for (int pair = cluster_id; pair < pairs; pair += clusters, ++it) {
-          asm volatile("" : "+l"(w1d[0]), "+l"(w1d[1]), "+l"(w2d[0]), "+l"(w2d[1]), "+l"(ad[0]), "+l"(ad[1]));
-          mbar_wait_parked(bar + kBarA1Full, it & 1);
-          tc_fence_after();
+    }
+    __syncwarp();
+    if (rank == 0) {
+      // The whole warp runs the tile loop and waits; one elected lane issues, so that the MMA
+      // operands are warp-uniform to the compiler and live in uniform registers (issued from
+      // inside `if (lane == 0)` every tcgen05.mma came wrapped in an ELECT / R2UR.BROADCAST
+      // loop: 11-13 instructions for each of this kernel's 72 MMAs per tile pair).
+      mbar_wait_parked(bar + kBarWReady, 0);
+      const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+      uint32_t elected;
+      asm volatile("{\n.reg .pred q;\nelect.sync _|q, 0xffffffff;\nselp.u32 %0, 1, 0, q;\n}" : "=r"(elected));
+      const bool issuer = elected != 0u;
+      constexpr uint32_t idesc1 = idesc_f16(2 * kTileM, N1);
+      constexpr uint32_t idesc2 = idesc_f16(2 * kTileM, kHidden);
+      const uint64_t w1d[2] = {smem_desc_sw128(smem_u32(smem + L::off_w1h)), smem_desc_sw128(smem_u32(smem + L::off_w1l))};
+      const uint64_t w2d[2] = {smem_desc_sw128(smem_u32(smem + L::off_w2h)), smem_desc_sw128(smem_u32(smem + L::off_w2l))};
+      const uint64_t ad[2] = {smem_desc_sw128(smem_u32(smem + L::off_ah)), smem_desc_sw128(smem_u32(smem + L::off_al))};
+      uint32_t it = 0;
+      for (int pair = cluster_id; pair < pairs; pair += clusters, ++it) {
+        mbar_wait_parked(bar + kBarA1Full, it & 1);
+        tc_fence_after();
+        if (issuer) {
           // GEMM 1: hi x hi, lo x hi, hi x lo  (operand A index, operand B index)
 #pragma unroll
           for (int combo = 0; combo < 3; ++combo) {
@@ -333,28 +343,32 @@ split_kernel(const __grid_constant__ Consts c, const Args p) {
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk) {
               const int kb = kk >> 2, k = kk & 3;
-              mma2_f16_ss(tmem, ad[ai] + uint64_t((kb * kKbBytes + k * 32) >> 4),
+              mma2_f16_ss(tm, ad[ai] + uint64_t((kb * kKbBytes + k * 32) >> 4),
                           w1d[bi] + uint64_t((kb * L::w1_piece + k * 32) >> 4), idesc1,
                           (combo | kk) != 0);
             }
           }
           mma2_commit(bar + kBarD1Full);
           mma2_commit(bar + kBarA1Empty);
-          mbar_wait_parked(bar + kBarA2Full, it & 1);
-          mbar_wait_parked(bar + kBarD2Empty, (it & 1) ^ 1);
-          tc_fence_after();
+        }
+        __syncwarp();
+        mbar_wait_parked(bar + kBarA2Full, it & 1);
+        mbar_wait_parked(bar + kBarD2Empty, (it & 1) ^ 1);
+        tc_fence_after();
+        if (issuer) {
 #pragma unroll
           for (int combo = 0; combo < 3; ++combo) {
-            const uint32_t a_tmem = tmem + (combo == 1 ? kLoCol : 0u);
+            const uint32_t a_tmem = tm + (combo == 1 ? kLoCol : 0u);
             const int bi = combo == 2 ? 1 : 0;
 #pragma unroll
             for (int kk = 0; kk < N1 / 16; ++kk)
-              mma2_f16_ts(tmem + kD2Col, a_tmem + kk * 8,
+              mma2_f16_ts(tm + kD2Col, a_tmem + kk * 8,
                           w2d[bi] + uint64_t(((kk >> 2) * L::w2_piece + (kk & 3) * 32) >> 4), idesc2,
                           (combo | kk) != 0);
           }
           mma2_commit(bar + kBarD2Full);
         }
+        __syncwarp();
       }
     }
     __syncwarp();
