@@ -6,6 +6,9 @@ Bars: integer/index work bit-exact; fp32 path |err| <= 2e-5 on O(10) values;
 fp16-storage path compared with the oracle run with the same fp16 storage
 points (tolerances written at each assert).
 """
+import sys
+from pathlib import Path
+
 import numpy as np
 import pytest
 
@@ -730,3 +733,53 @@ def test_whole_forward(nat, dev, problem, code, impl, fused):
         ref = y32 / np.linalg.norm(y32.astype(np.float64), axis=1, keepdims=True)
         cos = (got.astype(np.float64) * ref).sum(1) / np.linalg.norm(got.astype(np.float64), axis=1)
         assert cos.min() >= 0.999
+
+
+_INSTANCE_SCRIPT = r"""
+import hashlib, sys
+import torch
+sys.path.insert(0, {root!r}); sys.path.insert(0, {tests!r})
+from ginfinity_b200 import _native as nat
+from ginfinity_b200.weights import fold, synthetic_state
+import ginfinity_b200 as gb
+from helpers import random_records
+dev = torch.device("cuda:0")
+lib = nat.lib
+S = torch.cuda.current_stream().cuda_stream
+handle = nat.model_create(fold(synthetic_state(seed=7)))
+shard = gb.GraphBuilder().build_shard(random_records(3, 300))
+N, E = shard.node_count, shard.edge_count
+ei = torch.from_numpy(shard.edge_index).to(dev); et = torch.from_numpy(shard.edge_types).to(dev)
+row_ptr = torch.empty(N + 1, dtype=torch.int32, device=dev)
+col_src = torch.empty(E, dtype=torch.int32, device=dev); col_type = torch.empty(E, dtype=torch.uint8, device=dev)
+need = lib.gfx_csr_workspace_bytes(N, E); ws = torch.empty(need, dtype=torch.uint8, device=dev)
+nat.check(lib.gfx_csr_build(ei[0].data_ptr(), ei[1].data_ptr(), et.data_ptr(), N, E, 0, row_ptr.data_ptr(),
+                            col_src.data_ptr(), col_type.data_ptr(), ws.data_ptr(), need, S))
+desc = torch.empty(N, dtype=torch.int32, device=dev)
+nat.check(lib.gfx_row_describe(row_ptr.data_ptr(), col_src.data_ptr(), col_type.data_ptr(), N, desc.data_ptr(), S))
+torch.manual_seed(5)
+h = torch.randn(N, 128, device=dev).half(); out = torch.empty_like(h)
+nat.check(lib.gfx_layer_fused_banded(handle, 1, h.data_ptr(), row_ptr.data_ptr(), col_src.data_ptr(),
+                                     col_type.data_ptr(), desc.data_ptr(), N, out.data_ptr(), S))
+torch.cuda.synchronize()
+print("digest", hashlib.sha256(out.cpu().numpy().tobytes()).hexdigest())
+"""
+
+
+def test_production_and_developer_instances_of_the_layer_kernel_agree():
+    """fused_banded8_kernel<false, false> (no developer code in its loops) and <false, true>
+    (selected by any GFX_DBG value; bit 256 switches nothing on) produce the same bits."""
+    import os
+    import subprocess
+    root = str(Path(__file__).resolve().parents[1])
+    script = _INSTANCE_SCRIPT.format(root=root, tests=str(Path(__file__).resolve().parent))
+    digests = []
+    for dbg in (None, "256"):
+        env = dict(os.environ)
+        env.pop("GFX_DBG", None)
+        if dbg:
+            env["GFX_DBG"] = dbg
+        run = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, env=env, timeout=600)
+        assert run.returncode == 0, run.stderr[-2000:]
+        digests.append([l for l in run.stdout.splitlines() if l.startswith("digest")][-1])
+    assert digests[0] == digests[1]

@@ -61,6 +61,34 @@ def test_library_is_sm_100a_and_uses_the_blackwell_units(nat):
     assert "STTM" in sass              # tcgen05.st: the hidden activation goes back into TMEM
 
 
+def _kernel_sass(sass: str, needle: str) -> str:
+    """SASS text of the first kernel whose (mangled) name contains `needle`."""
+    parts = sass.split("Function : ")
+    body = [p for p in parts if needle in p.split("\n", 1)[0]]
+    assert body, needle
+    return body[0]
+
+
+@pytest.mark.skipif(shutil.which("cuobjdump") is None, reason="cuobjdump is not installed here")
+def test_layer_kernel_issuers_use_uniform_registers(nat):
+    """The banded layer kernel follows its executed-instruction count: the
+    production instance must not carry the developer tests, and its MMA / TMA issuers must be
+    warp-converged with one elected lane -- issued from inside `if (lane == 0)` every
+    tcgen05.mma / TMA instruction comes wrapped in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop."""
+    sass = subprocess.run(["cuobjdump", "-sass", str(LIB)], capture_output=True, text=True).stdout
+    production = _kernel_sass(sass, "fused_banded8_kernelILb0ELb0")
+    developer = _kernel_sass(sass, "fused_banded8_kernelILb0ELb1")
+    assert production.count("UTCHMMA.2CTA") == 24          # 8 (GEMM 1, N = 256) + 16 (GEMM 2)
+    assert "R2UR.BROADCAST" not in production
+    assert "CS2R" not in production.split("USETMAXREG")[1]  # no clock64 stamps in epilogue A's loop
+    n_prod = sum(1 for line in production.splitlines() if "/*" in line and ";" in line)
+    n_dev = sum(1 for line in developer.splitlines() if "/*" in line and ";" in line)
+    assert n_prod < n_dev
+    # the same for the top-k scan's MMA issuer
+    scan = _kernel_sass(sass, "topk_scan")
+    assert scan.count("R2UR.BROADCAST") <= 2 * scan.count("UTMALDG")   # none left around the MMAs
+
+
 def test_argument_errors_surface_through_gfx_last_error(nat):
     rc = nat.lib.gfx_pack_microbatches(None, None, 0, 10, 10, None, None, None, None)
     assert rc != 0 and b"empty" in nat.lib.gfx_last_error()
