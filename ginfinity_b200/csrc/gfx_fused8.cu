@@ -38,11 +38,13 @@
 //    memory; partners in other tiles are staged by cp.async into the row's own z slot so that the
 //    row code has one kind of load: 67 -> 31 instructions per row.  The MMA warp runs its loop
 //    converged with one elected lane issuing (operands in uniform registers: 1-3 instead of 11-13
-//    instructions per tcgen05.mma), the loader prefetches the next h tile into L2, molecule-end
-//    rows request their five source rows before the chain, and the production instance
-//    (template DEV = false) carries none of the developer tests in its loops.
-//    603k-node probe: 0.146 -> 0.105 ms; ncu: 129 -> 89 warp instructions per node-layer, tensor
-//    pipe 28.6 -> 41.7 % active.
+//    instructions per tcgen05.mma), and so does the loader, which also prefetches the next h tile
+//    into L2; every epilogue-B warp stores its own 32 x 64 block by TMA and hands the buffer back
+//    itself (there is no store warp); molecule-end rows are recomputed at the end of their run
+//    from the registers that are still live; the production instance (template DEV = false)
+//    carries none of the developer tests in its loops.
+//    603k-node probe: 0.146 -> 0.099 ms; ncu: 129 -> 87.5 warp instructions per node-layer,
+//    tensor pipe 28.6 -> 45.4 % active (profiles/r02_f_full_encoder_kernels.txt).
 //
 // Warps per CTA (24; 80 registers per thread at launch = 61,440 for the CTA, re-balanced with
 // setmaxnreg within that allocation: epilogue A 56, epilogue B 88, producers 104, utility 40 --
@@ -50,8 +52,8 @@
 //    0-3   epilogue A   D1 -> + b1, ReLU, fp16 -> A2 (in place)
 //    4-11  epilogue B   warp = 4 + 4 half + quad, every tile
 //   12-19  producers    warp w owns tile rows [16 w, 16 w + 16), two runs of 8 rows
-//   20     MMA issuer (rank 0 issues for the pair; GEMM 1 as 8 MMAs of N = 256), 21 h-tile loader,
-//   22     output store (both TMA)
+//   20     MMA issuer (rank 0 issues for the pair; GEMM 1 as 8 MMAs of N = 256), 21 h-tile loader
+//          (TMA), 22-23 spare
 #include <cstdlib>
 #include <type_traits>
 
@@ -76,7 +78,7 @@ constexpr int kStages = 2, kHBufs = 3;
 constexpr int kWPiece = 64 * 128;             // 64 weight rows x 64 columns (one CTA's share)
 constexpr uint32_t kTmemCols = 512, kD2Col = 256;
 constexpr int kEpiBWarp0 = 4, kEpiBWarps = 8, kProdWarp0 = 12, kProdWarps = 8, kMmaWarp = 20,
-              kLoadWarp = 21, kStoreWarp = 22, kWarps = 24;
+              kLoadWarp = 21, kWarps = 24;
 constexpr int kRowsPerWarp = kTileM / kProdWarps;     // 16 consecutive rows of a tile per producer warp
 constexpr int kRun = 8;                               // rows per register window
 static_assert(kRowsPerWarp % kRun == 0 && kRun % 4 == 0, "runs of whole partner groups");

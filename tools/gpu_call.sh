@@ -1,5 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-N=8
-timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/bench_${N}gpu.json 2> gpurun_out/bench_${N}gpu.err; echo "bench $N rc=$?"
-tail -c 1200 gpurun_out/bench_${N}gpu.json | head -c 600
+timeout 120 python tools/fused_probe.py gfx_layer_fused_banded 2>&1 | tail -1
+timeout 120 python tools/fused_trace.py banded 2>&1 | grep "CTAs:" 
+timeout 120 python tools/fused_probe.py gfx_layer_fused_banded 2>&1 | tail -1
