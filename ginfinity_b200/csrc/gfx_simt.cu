@@ -731,6 +731,10 @@ int head8_l2norm(const gfx_model *m, const __half *h, int64_t n, __half *out, cu
 
 }  // namespace gfx
 
+namespace gfx {
+int input8_linear(const gfx_model *m, const float *x, int64_t n, __half *h, cudaStream_t st);   // gfx_input8.cu
+}
+
 using namespace gfx;
 
 extern "C" int gfx_input_linear(const gfx_model *m, const float *x, int64_t n, void *h, int dtype,
@@ -749,6 +753,15 @@ extern "C" int gfx_input_linear(const gfx_model *m, const float *x, int64_t n, v
   const int64_t rest = n - lead;
   if (dtype == GFX_F16) {
     __half *hh = static_cast<__half *>(h);
+    // the tensor-core kernel (gfx_input8.cu) when it applies; GFX_INPUT_SIMT=1: the SIMT kernels
+    static const bool simt = [] {
+      const char *v = getenv("GFX_INPUT_SIMT");
+      return v && *v && *v != '0';
+    }();
+    if (!simt) {
+      const int rc = input8_linear(m, x, n, hh, st);
+      if (rc != GFX_ERR_UNSUPPORTED) return rc;
+    }
     if (lead) input_linear_kernel<__half><<<row_grid(lead), 256, 0, st>>>(x, m->w_in[1], m->b_in, lead, hh);
     if (rest)
       input_linear4_kernel<__half><<<row_grid((rest + 3) / 4), 256, 0, st>>>(
