@@ -15,7 +15,7 @@ NCU_CMD="python bench.py --steps 1 --warmup 1 --records 20000 --no-cpu-baseline 
 timeout 300 $NCU_CMD > gpurun_out/ncu_plain.log 2>&1 && \
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $NCU_CMD > gpurun_out/ncu_launches.log 2>&1
 timeout 300 $NCU_CMD > gpurun_out/ncu_plain2.log 2>&1 && \
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"fused_banded8|head8|input_linear4|edge_classify|edge_describe" -s 4 -c 8 -o gpurun_out/prof_top $NCU_CMD > gpurun_out/ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"fused_banded8|head8|input_umma|edge_classify|edge_describe" -s 4 -c 8 -o gpurun_out/prof_top $NCU_CMD > gpurun_out/ncu_full.log 2>&1
 if [ "$1" != "ncu" ]; then
 SEARCH_CMD="python tools/search_bench.py 3"
 timeout 300 $SEARCH_CMD > gpurun_out/search.log 2>&1 && \
