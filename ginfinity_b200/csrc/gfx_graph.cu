@@ -262,64 +262,105 @@ __global__ void csr_place_big_kernel(const int32_t *__restrict__ gate, const int
 // ---------------------------------------------------------------------------
 constexpr uint32_t kEdgeStateGeneric = 1u << 8;
 
-__global__ void edge_classify_kernel(const int32_t *__restrict__ src, const int32_t *__restrict__ dst,
-                                     const uint8_t *__restrict__ typ, int64_t E, int32_t base, uint32_t N,
-                                     uint32_t *__restrict__ state, int32_t *__restrict__ position,
-                                     int32_t *__restrict__ status) {
+// Both kernels are latency chains (load -> atomic with return -> store; state -> position -> source
+// of the pair edge), so each thread carries kEdgeUnroll independent edges / nodes: all loads of a
+// group are issued before the first atomic, all atomics before the first use of a returned word.
+constexpr int kEdgeUnroll = 4;
+
+__global__ void __launch_bounds__(256)
+edge_classify_kernel(const int32_t *__restrict__ src, const int32_t *__restrict__ dst,
+                     const uint8_t *__restrict__ typ, int64_t E, int32_t base, uint32_t N,
+                     uint32_t *__restrict__ state, int32_t *__restrict__ position,
+                     int32_t *__restrict__ status) {
   bool bad = false;
-  for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < E;
-       e += int64_t(gridDim.x) * blockDim.x) {
-    const int32_t s = src[e] - base, d = dst[e] - base;
-    if (uint32_t(s) >= N || uint32_t(d) >= N) {
-      bad = true;                                  // dropped, as in csr_count_kernel
-      continue;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t e0 = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e0 < E;
+       e0 += stride * kEdgeUnroll) {
+    int32_t s[kEdgeUnroll], d[kEdgeUnroll], t[kEdgeUnroll];
+#pragma unroll
+    for (int j = 0; j < kEdgeUnroll; ++j) {
+      const int64_t e = e0 + j * stride;
+      const bool in = e < E;
+      s[j] = in ? src[e] - base : 0;
+      d[j] = in ? dst[e] - base : -1;              // -1: no edge here (not reported as bad)
+      t[j] = in ? int(typ[e]) : 0;
     }
-    const int t = typ[e], off = s - d;
-    int k = -1;
-    if (t == 0 && off == -1) k = 0;
-    else if (t == 1 && off == 1) k = 1;
-    else if (t == 2 || t == 3) k = 2;
-    else if (t == 4 && off == -2) k = 3;
-    else if (t == 5 && off == 2) k = 4;
-    if (k < 0) {
-      atomicOr(&state[d], kEdgeStateGeneric);
-      continue;
+    uint32_t bit[kEdgeUnroll], old[kEdgeUnroll];
+#pragma unroll
+    for (int j = 0; j < kEdgeUnroll; ++j) {
+      const bool in = e0 + j * stride < E;
+      const bool ok = uint32_t(s[j]) < N && uint32_t(d[j]) < N;
+      bad |= in && !ok;                            // dropped, as in csr_count_kernel
+      const int off = s[j] - d[j];
+      int k = -1;
+      if (t[j] == 0 && off == -1) k = 0;
+      else if (t[j] == 1 && off == 1) k = 1;
+      else if (t[j] == 2 || t[j] == 3) k = 2;
+      else if (t[j] == 4 && off == -2) k = 3;
+      else if (t[j] == 5 && off == 2) k = 4;
+      bit[j] = !ok ? 0u : (k < 0 ? kEdgeStateGeneric : (0x10000u | (1u << k)));   // bit 16: classified
     }
-    const uint32_t old = atomicOr(&state[d], 1u << k);
-    if (old & (1u << k)) atomicOr(&state[d], kEdgeStateGeneric);   // a second edge of this class
-    else position[size_t(k) * N + d] = int32_t(e);
+#pragma unroll
+    for (int j = 0; j < kEdgeUnroll; ++j)
+      old[j] = bit[j] ? atomicOr(&state[d[j]], bit[j] & 0xffffu) : 0u;
+#pragma unroll
+    for (int j = 0; j < kEdgeUnroll; ++j) {
+      if (!(bit[j] & 0x10000u)) continue;
+      const uint32_t mine = bit[j] & 0xffu;
+      if (old[j] & mine) atomicOr(&state[d[j]], kEdgeStateGeneric);   // a second edge of this class
+      else position[size_t(__ffs(int(mine)) - 1) * N + d[j]] = int32_t(e0 + j * stride);
+    }
   }
   if (bad) atomicOr(status, GFX_GRAPH_BAD_EDGE);
 }
 
-__global__ void edge_describe_kernel(const int32_t *__restrict__ src, const uint8_t *__restrict__ typ,
-                                     int32_t base, int64_t N, const uint32_t *__restrict__ state,
-                                     const int32_t *__restrict__ position, uint32_t *__restrict__ desc,
-                                     int32_t *__restrict__ needs_csr) {
+__global__ void __launch_bounds__(256)
+edge_describe_kernel(const int32_t *__restrict__ src, const uint8_t *__restrict__ typ, int32_t base,
+                     int64_t N, const uint32_t *__restrict__ state,
+                     const int32_t *__restrict__ position, uint32_t *__restrict__ desc,
+                     int32_t *__restrict__ needs_csr) {
   using namespace rowdesc;
   bool generic_seen = false;
-  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < N;
-       i += int64_t(gridDim.x) * blockDim.x) {
-    const uint32_t st = state[i];
-    uint32_t d = 0;
-    bool generic = (st & kEdgeStateGeneric) != 0;
-    int32_t prev_pos = -1;
-    constexpr uint32_t bits[5] = {kPrev, kNext, kPair, kPrev2, kNext2};
+  constexpr int U = 2;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t i0 = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i0 < N; i0 += stride * U) {
+    uint32_t st[U];
+    int32_t pos[U][5], partner[U], ptyp[U];
 #pragma unroll
-    for (int k = 0; k < 5; ++k) {
-      if (!(st & (1u << k)) || generic) continue;
-      const int32_t pos = position[size_t(k) * N + i];
-      if (pos < prev_pos) generic = true;          // not the CSR order of a banded row
-      prev_pos = pos;
-      d |= bits[k];
-      if (k == 2) {
-        const int32_t partner = src[pos] - base;
-        if (uint32_t(partner) > kPartnerMask) generic = true;
-        d |= (typ[pos] == 3 ? kPairRev : 0u) | (uint32_t(partner) << kPartnerShift);
-      }
+    for (int u = 0; u < U; ++u) st[u] = i0 + u * stride < N ? state[i0 + u * stride] : 0u;
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int k = 0; k < 5; ++k)                  // a class bit is set by the thread that then
+        pos[u][k] = (st[u] >> k) & 1u              // stored the position: valid whenever set
+                        ? position[size_t(k) * N + i0 + u * stride] : -1;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const bool pair = (st[u] >> 2) & 1u;
+      partner[u] = pair ? src[pos[u][2]] - base : 0;
+      ptyp[u] = pair ? int(typ[pos[u][2]]) : 0;
     }
-    desc[i] = generic ? kGeneric : d;
-    generic_seen |= generic;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (i0 + u * stride >= N) continue;
+      uint32_t d = 0;
+      bool generic = (st[u] & kEdgeStateGeneric) != 0;
+      int32_t prev_pos = -1;
+      constexpr uint32_t bits[5] = {kPrev, kNext, kPair, kPrev2, kNext2};
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        if (!((st[u] >> k) & 1u)) continue;
+        generic |= pos[u][k] < prev_pos;           // not the CSR order of a banded row
+        prev_pos = pos[u][k];
+        d |= bits[k];
+      }
+      if ((st[u] >> 2) & 1u) {
+        generic |= uint32_t(partner[u]) > kPartnerMask;
+        d |= (ptyp[u] == 3 ? kPairRev : 0u) | (uint32_t(partner[u]) << kPartnerShift);
+      }
+      desc[i0 + u * stride] = generic ? kGeneric : d;
+      generic_seen |= generic;
+    }
   }
   if (generic_seen) *needs_csr = 1;                // benign race: every writer stores 1
 }
@@ -467,9 +508,9 @@ extern "C" int gfx_edge_describe(const int32_t *edge_src, const int32_t *edge_ds
   if (N == 0) return GFX_OK;
   GFX_CUDA(cudaMemsetAsync(state, 0, size_t(N) * 4, st));
   if (E > 0)
-    edge_classify_kernel<<<grid_for(E, 256), 256, 0, st>>>(edge_src, edge_dst, edge_type, E, node_base,
+    edge_classify_kernel<<<grid_for((E + kEdgeUnroll - 1) / kEdgeUnroll, 256), 256, 0, st>>>(edge_src, edge_dst, edge_type, E, node_base,
                                                            uint32_t(N), state, position, status);
-  edge_describe_kernel<<<grid_for(N, 256), 256, 0, st>>>(edge_src, edge_type, node_base, N, state,
+  edge_describe_kernel<<<grid_for((N + 1) / 2, 256), 256, 0, st>>>(edge_src, edge_type, node_base, N, state,
                                                          position, desc, needs_csr);
   GFX_LAUNCH_CHECK();
   return GFX_OK;

@@ -541,15 +541,22 @@ class Ginfinity:
                        RESIDENT_CHUNK_MICROBATCHES * int(max_batch_nodes))
         return min(self.chunk_nodes, CHUNK_MICROBATCHES * int(max_batch_nodes))
 
-    def _chunks(self, plan: np.ndarray, limit: int) -> list:
+    def _chunks(self, plan: np.ndarray, limit: int, ramp: bool = False) -> list:
         """Group consecutive microbatches into device chunks of at most
-        `limit` nodes (always at least one microbatch)."""
+        `limit` nodes (always at least one microbatch).  `ramp` (the streaming
+        path): the first chunks hold 1/8, 1/4 and 1/2 of `limit`, so the
+        device->host copies -- the bottleneck of an end-to-end call, which
+        nothing overlaps before the first chunk is encoded -- start after an
+        eighth of a chunk's copy-in and compute instead of a whole one."""
         node_at, count = plan[1], plan.shape[1]
         out, start = [], 0
+        shift = 3 if ramp else 0
         while start < count - 1:
+            cap = limit >> shift
+            shift = max(0, shift - 1)
             stop = start + 1
             while (stop < count - 1 and
-                   node_at[stop + 1] - node_at[start] <= limit):
+                   node_at[stop + 1] - node_at[start] <= cap):
                 stop += 1
             out.append((start, stop))
             start = stop
@@ -599,7 +606,7 @@ class Ginfinity:
         edge_ptr_d = as_t(shard.edge_ptr).to(dev, non_blocking=True)
         plan = self._plan(node_ptr_d, edge_ptr_d, B, max_batch_nodes,
                           max_batch_edges, main.cuda_stream)
-        chunks = self._chunks(plan, self._chunk_limit(max_batch_nodes))
+        chunks = self._chunks(plan, self._chunk_limit(max_batch_nodes), ramp=True)
         rec_at, node_at, edge_at = plan[0], plan[1], plan[2]
         out_row = None
         if not all_core:

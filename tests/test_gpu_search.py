@@ -1,8 +1,9 @@
 """K5 similarity search on the GPU against the oracle (oracle/gine_oracle.py:
 topk_exact / topk_bruteforce / merge_topk).  The reference has no search, so
-parity here is against this package's own stated contract (parity unpinned):
-indices bit-exact under (score desc, index asc), scores equal to the
-sequential-fp32 definition."""
+parity here is against this package's own stated contract (parity unpinned
+against the reference): indices bit-exact under (score desc, index asc), scores
+equal to the sequential-fp32 definition; plus a third-party cross-check against
+scikit-learn's exact brute-force k-NN (float64) on the same rows."""
 import numpy as np
 import pytest
 
@@ -59,6 +60,32 @@ def test_topk_agrees_with_float64_bruteforce_where_gaps_are_resolvable(search, m
     clear = np.all(gaps > 1e-5, axis=1)
     assert clear.mean() > 0.9
     np.testing.assert_array_equal(got_i[clear], want_i[clear, :k])
+
+
+@pytest.mark.parametrize("metric", ["cosine", "l2"])
+def test_topk_agrees_with_scikit_learn_bruteforce(search, metric):
+    """Third-party cross-check (the reference has no search): scikit-learn's exact
+    brute-force k-NN in float64 on the same fp16 rows.  Scores to 2e-6, neighbours
+    identical wherever scikit-learn's own gaps between ranks are resolvable."""
+    nn = pytest.importorskip("sklearn.neighbors")
+    q, db, k = unit_rows(21, 150), unit_rows(22, 20000), 10
+    got_s, got_i = run(search, q, db, k, metric)
+    q64, db64 = q.astype(np.float64), db.astype(np.float64)
+    if metric == "cosine":
+        qn, dn = np.linalg.norm(q64, axis=1), np.linalg.norm(db64, axis=1)
+        model = nn.NearestNeighbors(n_neighbors=k + 40, algorithm="brute", metric="cosine")
+        dist, near = model.fit(db64 / dn[:, None]).kneighbors(q64 / qn[:, None])
+        score = (1.0 - dist) * qn[:, None] * dn[near]      # back to the given rows' dot product
+        order = np.argsort(-score, axis=1, kind="stable")[:, :k + 1]
+        score, near = np.take_along_axis(score, order, 1), np.take_along_axis(near, order, 1)
+    else:
+        model = nn.NearestNeighbors(n_neighbors=k + 1, algorithm="brute", metric="euclidean")
+        dist, near = model.fit(db64).kneighbors(q64)
+        score = -dist * dist
+    np.testing.assert_allclose(got_s, score[:, :k], rtol=0, atol=2e-6)
+    clear = np.all(score[:, :-1] - score[:, 1:] > 1e-5, axis=1)
+    assert clear.mean() > 0.8
+    np.testing.assert_array_equal(got_i[clear], near[clear, :k])
 
 
 def test_ties_break_by_ascending_index(search):

@@ -195,3 +195,40 @@ def test_cpu_port_matches_reference(real_state, golden_shard, golden_embeddings)
     ref16 = golden_embeddings["full/fp16_model_f16"]
     assert got16.dtype == np.float16
     assert np.abs(got16.astype(np.float32) - ref16.astype(np.float32)).max() <= 1e-3
+
+
+@pytest.mark.parametrize("metric", ["cosine", "l2"])
+def test_topk_oracle_agrees_with_scikit_learn_bruteforce(metric):
+    """The reference has no search; the nearest published statement of the
+    same problem in this image is scikit-learn's exact brute-force k-NN
+    (sklearn.neighbors.NearestNeighbors(algorithm='brute'), 1.9.0).  The
+    oracle's fp32-chain scores must equal its float64 distances to 2e-6 and
+    pick the same neighbours wherever scikit-learn's own gaps between ranks
+    are resolvable."""
+    nn = pytest.importorskip("sklearn.neighbors")
+    rng = np.random.default_rng(11)
+    q = rng.normal(size=(60, 128)).astype(np.float32)
+    db = rng.normal(size=(2500, 128)).astype(np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    db /= np.linalg.norm(db, axis=1, keepdims=True)
+    q, db, k = q.astype(np.float16), db.astype(np.float16), 10
+    val, idx = O.topk_exact(q, db, k, metric)
+    q64, db64 = q.astype(np.float64), db.astype(np.float64)
+    if metric == "cosine":
+        # cosine DISTANCE of scikit-learn normalises its inputs; the package scores the
+        # given vectors' dot product, so hand scikit-learn exactly-unit float64 rows and
+        # undo the norms afterwards
+        qn, dn = np.linalg.norm(q64, axis=1), np.linalg.norm(db64, axis=1)
+        model = nn.NearestNeighbors(n_neighbors=k + 40, algorithm="brute", metric="cosine")
+        dist, near = model.fit(db64 / dn[:, None]).kneighbors(q64 / qn[:, None])
+        score = (1.0 - dist) * qn[:, None] * dn[near]
+        order = np.argsort(-score, axis=1, kind="stable")[:, :k + 1]
+        score, near = np.take_along_axis(score, order, 1), np.take_along_axis(near, order, 1)
+    else:
+        model = nn.NearestNeighbors(n_neighbors=k + 1, algorithm="brute", metric="euclidean")
+        dist, near = model.fit(db64).kneighbors(q64)
+        score = -dist * dist
+    np.testing.assert_allclose(val, score[:, :k], rtol=0, atol=2e-6)
+    clear = np.all(score[:, :-1] - score[:, 1:] > 1e-5, axis=1)
+    assert clear.mean() > 0.9
+    np.testing.assert_array_equal(idx[clear], near[clear, :k])

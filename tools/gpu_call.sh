@@ -1,3 +1,10 @@
 #!/bin/bash
-bash tools/gpu_round.sh > gpurun_out/round.log 2>&1
-tail -12 gpurun_out/round.log | cut -c1-300
+mkdir -p gpurun_out
+{
+echo "== previous build"; GFX_LIBRARY=$PWD/ginfinity_b200/libgfx_prev.so timeout 200 python tools/stage_probe.py
+echo "== this build";     timeout 200 python tools/stage_probe.py
+echo "== previous build"; GFX_LIBRARY=$PWD/ginfinity_b200/libgfx_prev.so timeout 200 python tools/stage_probe.py
+echo "== this build";     timeout 200 python tools/stage_probe.py
+timeout 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_encoder.py -m gpu -q -x 2>&1 | tail -5
+} > gpurun_out/call.log 2>&1
+tail -30 gpurun_out/call.log | cut -c1-300
