@@ -71,6 +71,7 @@ _SIGNATURES = {
     "gfx_core_rows": (C.c_int, [_p, _i64, _p, _p, _p, _sz, _p]),
     "gfx_input_linear": (C.c_int, [_p, _p, _i64, _p, C.c_int, _p]),
     "gfx_aggregate": (C.c_int, [_p, C.c_int, _p, _p, _p, _p, _i64, _p, C.c_int, _p]),
+    "gfx_aggregate_banded": (C.c_int, [_p, C.c_int, _p, _p, _p, _p, _p, _p, _i64, _p, C.c_int, _p]),
     "gfx_mlp_ln_residual": (C.c_int, [_p, C.c_int, _p, _p, _i64, _p, C.c_int, C.c_int, _p]),
     "gfx_layer_fused_pair": (C.c_int, [_p, C.c_int, _p, _p, _p, _p, _i64, _p, _p]),
     "gfx_row_describe": (C.c_int, [_p, _p, _p, _i64, _p, _p]),
@@ -80,6 +81,8 @@ _SIGNATURES = {
     "gfx_encode": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _p, C.c_int, C.c_int,
                              C.c_int, C.c_int, _p, _sz, _p]),
     "gfx_encode_described": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _p, C.c_int, _p, _sz, _p]),
+    "gfx_encode_described_f32": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _p, C.c_int, _p, _sz,
+                                           _p]),
     "gfx_topk_workspace_bytes": (_sz, [_i64, _i64, C.c_int]),
     "gfx_topk": (C.c_int, [_p, _i64, _p, _i64, C.c_int, C.c_int, C.c_int, _i64,
                            _p, _p, _p, _sz, _p]),

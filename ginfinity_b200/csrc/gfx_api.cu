@@ -256,7 +256,7 @@ extern "C" size_t gfx_encode_workspace_bytes(int64_t num_nodes, int dtype) {
 
 static int encode_chunk(const gfx_model *model, const float *x, const int32_t *row_ptr,
                         const int32_t *col_src, const uint8_t *col_type, const uint32_t *desc_in,
-                        const int32_t *out_row, int64_t n, void *out, int dtype, int out_dtype, int impl,
+                        const int32_t *needs_csr, const int32_t *out_row, int64_t n, void *out, int dtype, int out_dtype, int impl,
                         int fused, void *ws, size_t ws_bytes, void *stream);
 
 extern "C" int gfx_encode(const gfx_model *model, const float *x, const int32_t *row_ptr,
@@ -264,8 +264,8 @@ extern "C" int gfx_encode(const gfx_model *model, const float *x, const int32_t 
                           const int32_t *out_row, int64_t n, void *out, int dtype,
                           int out_dtype, int impl, int fused, void *ws, size_t ws_bytes,
                           void *stream) {
-  return encode_chunk(model, x, row_ptr, col_src, col_type, nullptr, out_row, n, out, dtype, out_dtype,
-                      impl, fused, ws, ws_bytes, stream);
+  return encode_chunk(model, x, row_ptr, col_src, col_type, nullptr, nullptr, out_row, n, out, dtype,
+                      out_dtype, impl, fused, ws, ws_bytes, stream);
 }
 
 extern "C" int gfx_encode_described(const gfx_model *model, const float *x, const uint32_t *desc,
@@ -273,13 +273,24 @@ extern "C" int gfx_encode_described(const gfx_model *model, const float *x, cons
                                     const uint8_t *col_type, int64_t n, void *out, int out_dtype,
                                     void *ws, size_t ws_bytes, void *stream) {
   if (!desc && n > 0) return fail(GFX_ERR_ARGUMENT, "gfx_encode_described: null row descriptors");
-  return encode_chunk(model, x, row_ptr, col_src, col_type, desc, nullptr, n, out, GFX_F16, out_dtype,
-                      GFX_IMPL_AUTO, 3, ws, ws_bytes, stream);
+  return encode_chunk(model, x, row_ptr, col_src, col_type, desc, nullptr, nullptr, n, out, GFX_F16,
+                      out_dtype, GFX_IMPL_AUTO, 3, ws, ws_bytes, stream);
+}
+
+extern "C" int gfx_encode_described_f32(const gfx_model *model, const float *x, const uint32_t *desc,
+                                        const int32_t *needs_csr, const int32_t *row_ptr,
+                                        const int32_t *col_src, const uint8_t *col_type, int64_t n,
+                                        void *out, int out_dtype, void *ws, size_t ws_bytes,
+                                        void *stream) {
+  if ((!desc || !needs_csr) && n > 0)
+    return fail(GFX_ERR_ARGUMENT, "gfx_encode_described_f32: null row descriptors or flag");
+  return encode_chunk(model, x, row_ptr, col_src, col_type, desc, needs_csr, nullptr, n, out, GFX_F32,
+                      out_dtype, GFX_IMPL_AUTO, 0, ws, ws_bytes, stream);
 }
 
 static int encode_chunk(const gfx_model *model, const float *x, const int32_t *row_ptr,
                         const int32_t *col_src, const uint8_t *col_type, const uint32_t *desc_in,
-                        const int32_t *out_row, int64_t n, void *out, int dtype, int out_dtype, int impl,
+                        const int32_t *needs_csr, const int32_t *out_row, int64_t n, void *out, int dtype, int out_dtype, int impl,
                         int fused, void *ws, size_t ws_bytes, void *stream) {
   if (!model) return fail(GFX_ERR_ARGUMENT, "gfx_encode: null model");
   if (n == 0) return GFX_OK;
@@ -314,7 +325,10 @@ static int encode_chunk(const gfx_model *model, const float *x, const int32_t *r
       rc = gfx_layer_fused_pair(model, l, h, row_ptr, col_src, col_type, n, h2, stream);
       if (rc) return rc;
     } else {
-      rc = gfx_aggregate(model, l, h, row_ptr, col_src, col_type, n, z, dtype, stream);
+      rc = (desc_in != nullptr && dtype == GFX_F32)
+               ? gfx_aggregate_banded(model, l, h, desc_in, needs_csr, row_ptr, col_src, col_type, n, z,
+                                      dtype, stream)
+               : gfx_aggregate(model, l, h, row_ptr, col_src, col_type, n, z, dtype, stream);
       if (rc) return rc;
       rc = gfx_mlp_ln_residual(model, l, z, h, n, h2, dtype, impl, stream);
       if (rc) return rc;

@@ -4,6 +4,7 @@
 #include <cstdlib>
 
 #include "gfx_common.cuh"
+#include "gfx_umma.cuh"
 
 namespace gfx {
 
@@ -442,7 +443,8 @@ __global__ void __launch_bounds__(256, 2)
 aggregate_f32_h_kernel(const float *__restrict__ h, const int32_t *__restrict__ row_ptr,
                        const int32_t *__restrict__ col_src, const uint8_t *__restrict__ col_type,
                        const float *__restrict__ table, int edge_dim, float eps1, int64_t n,
-                       float *__restrict__ z) {
+                       float *__restrict__ z, const int32_t *__restrict__ gate) {
+  if (gate != nullptr && *gate == 0) return;     // gfx_aggregate_banded: the banded kernel did the chunk
   __shared__ __align__(16) float tab[(kMaxEdgeDim + 1) * kHidden];
   for (int i = threadIdx.x; i < edge_dim * kHidden; i += blockDim.x) tab[i] = table[i];
   for (int i = threadIdx.x; i < kHidden; i += blockDim.x) tab[edge_dim * kHidden + i] = -3.0e38f;
@@ -521,6 +523,136 @@ aggregate_f32_h_kernel(const float *__restrict__ h, const int32_t *__restrict__ 
     if (__shfl_sync(0xffffffffu, int(i1 >= n), 0)) break;
     i = i1; beg = beg1; end = end1; pk = pk1;
     i1 = i2; beg1 = beg2; end1 = end2;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K1, fp32 storage, from ROW DESCRIPTORS (gfx_edge_describe): when every row of the chunk is one
+// of the reference builder's banded rows -- (i-1) (i+1) [(partner)] (i-2) (i+2), some missing at
+// molecule ends -- a block walks tiles of 64 consecutive rows.  A tile and its two halo rows on
+// either side (68 x 512 bytes, contiguous in h) arrive in shared memory by ONE bulk copy on the
+// TMA engine, three tiles deep (two in flight while one is computed: ~70 KB per block on the way
+// without holding registers); a warp owns 8 rows of the tile, one float4 per lane, slides a
+// five-row register window over them (one LDS.128 per row) and fetches only the pairing partners
+// from global memory, all eight up front (prefetched into L2 a tile ahead).  Each h row crosses
+// the LSU once instead of once per edge (the CSR kernel above is bound by the L1 / LSU pipe:
+// 3.5 KB per node through it, 84 % busy in ncu).  Same operations in the same order as the CSR
+// kernels (fp32 message, fp32 sum in CSR order with a missing edge adding nothing, one fma for
+// the self term): the same bits.  Runs only when *gate == 0 (no GENERIC row in the chunk);
+// otherwise the CSR kernel does the chunk.
+// ---------------------------------------------------------------------------
+constexpr int kBandTile = 64, kBandStages = 3;
+constexpr int kBandStageBytes = (kBandTile + 4) * kHidden * 4;
+constexpr int kBandSmemBytes = kBandStages * kBandStageBytes + 64;
+
+__device__ __forceinline__ void band_add(float4 &acc, const float4 &a, const float4 &t) {
+  acc.x += fmaxf(a.x + t.x, 0.f);
+  acc.y += fmaxf(a.y + t.y, 0.f);
+  acc.z += fmaxf(a.z + t.z, 0.f);
+  acc.w += fmaxf(a.w + t.w, 0.f);
+}
+
+__global__ void __launch_bounds__(256, 2)
+aggregate_f32_band_kernel(const float *__restrict__ h, const uint32_t *__restrict__ desc,
+                          const int32_t *__restrict__ gate, const float *__restrict__ table,
+                          float eps1, int n, float *__restrict__ z) {
+  using namespace rowdesc;
+  using namespace ptx;
+  extern __shared__ __align__(128) unsigned char band_smem[];
+  if (*gate != 0) return;
+  uint64_t *full = reinterpret_cast<uint64_t *>(band_smem + kBandStages * kBandStageBytes);
+  const int lane = threadIdx.x & 31;
+  // the warp's index through a shuffle: ptxas then knows that everything derived from it (rows,
+  // presence masks) is warp-uniform and emits plain uniform branches
+  const int warp = __shfl_sync(0xffffffffu, int(threadIdx.x >> 5), 0);
+  const float4 *hv = reinterpret_cast<const float4 *>(h) + lane;      // row r -> hv[r * 32]
+  float4 *zv = reinterpret_cast<float4 *>(z) + lane;
+  float4 t[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) t[k] = reinterpret_cast<const float4 *>(table + k * kHidden)[lane];
+  const int tiles = (n + kBandTile - 1) / kBandTile;
+  auto tile_row0 = [&](int j) {                    // first row of this block's j-th tile, or -1
+    const int v = int(blockIdx.x) + j * int(gridDim.x);
+    return v < tiles ? (tiles - 1 - v) * kBandTile : -1;              // descending (L2 hand-over)
+  };
+  auto issue = [&](int j) {                        // one thread: tile j -> stage j % 3
+    const int r0 = tile_row0(j);
+    if (r0 < 0) return;
+    const int lo = max(r0 - 2, 0), hi = min(r0 + kBandTile + 2, n);
+    const uint32_t bytes = uint32_t(hi - lo) * (kHidden * 4);
+    uint64_t *bar = &full[j % kBandStages];
+    mbar_arrive_expect_tx(bar, bytes);
+    bulk_g2s(band_smem + (j % kBandStages) * kBandStageBytes + (lo - (r0 - 2)) * (kHidden * 4),
+             h + int64_t(lo) * kHidden, bytes, bar);
+  };
+  auto my_desc = [&](int r0) {                     // lanes 0-7: the descriptors of the warp's rows
+    const int i = r0 + warp * 8 + lane;
+    return (r0 >= 0 && lane < 8 && i < n) ? desc[i] : 0u;
+  };
+  auto prefetch_mates = [&](uint32_t d) {          // lanes 0-7: partner row of my row into L2
+    if (d & kPair) {
+      const char *p = reinterpret_cast<const char *>(h) + (int64_t((d >> kPartnerShift) & kPartnerMask) << 9);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + q * 128));
+    }
+  };
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kBandStages; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kBandStages; ++s) issue(s);
+  }
+  uint32_t mine = my_desc(tile_row0(0));
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j = 0;; ++j) {
+    const int r0 = tile_row0(j);
+    if (r0 < 0) break;
+    const int first = r0 + warp * 8;                                   // the warp's rows: first .. first + 7
+    const int rows = min(n - first, 8);                                // <= 0: nothing to do in this tile
+    const uint32_t m_prev = __ballot_sync(0xffffffffu, mine & kPrev),
+                   m_next = __ballot_sync(0xffffffffu, mine & kNext),
+                   m_pair = __ballot_sync(0xffffffffu, mine & kPair),
+                   m_rev = __ballot_sync(0xffffffffu, mine & kPairRev),
+                   m_prev2 = __ballot_sync(0xffffffffu, mine & kPrev2),
+                   m_next2 = __ballot_sync(0xffffffffu, mine & kNext2);
+    float4 mate[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const uint32_t d = __shfl_sync(0xffffffffu, mine, q);
+      mate[q] = ((m_pair >> q) & 1u)
+                    ? __ldg(hv + int64_t((d >> kPartnerShift) & kPartnerMask) * 32) : zero;
+    }
+    const uint32_t next_mine = my_desc(tile_row0(j + 1));
+    prefetch_mates(next_mine);
+    mbar_wait(&full[j % kBandStages], uint32_t(j / kBandStages) & 1u);
+    // stage row s holds h row r0 - 2 + s; the warp's row q is stage row warp * 8 + q + 2
+    const float4 *sv = reinterpret_cast<const float4 *>(band_smem + (j % kBandStages) * kBandStageBytes) +
+                       warp * 8 * 32 + lane;
+    float4 w[5];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) w[s] = sv[s * 32];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      if (q >= rows) break;                                            // warp-uniform
+      w[(q + 4) % 5] = sv[(q + 4) * 32];
+      const float4 prev2 = w[q % 5], prev = w[(q + 1) % 5], self = w[(q + 2) % 5],
+                   next = w[(q + 3) % 5], next2 = w[(q + 4) % 5];
+      float4 acc = zero;
+      if ((m_prev >> q) & 1u) band_add(acc, prev, t[0]);
+      if ((m_next >> q) & 1u) band_add(acc, next, t[1]);
+      if ((m_pair >> q) & 1u) band_add(acc, mate[q], ((m_rev >> q) & 1u) ? t[3] : t[2]);
+      if ((m_prev2 >> q) & 1u) band_add(acc, prev2, t[4]);
+      if ((m_next2 >> q) & 1u) band_add(acc, next2, t[5]);
+      zv[int64_t(first + q) * 32] = make_float4(fmaf(eps1, self.x, acc.x), fmaf(eps1, self.y, acc.y),
+                                                fmaf(eps1, self.z, acc.z), fmaf(eps1, self.w, acc.w));
+    }
+    mine = next_mine;
+    __syncthreads();                                                   // every warp is done with the stage
+    if (threadIdx.x == 0) issue(j + kBandStages);
   }
 }
 
@@ -812,7 +944,7 @@ extern "C" int gfx_aggregate(const gfx_model *m, int layer, const void *h, const
       const int grid = int(b > 2 * kNumSMs ? 2 * kNumSMs : b);
       aggregate_f32_h_kernel<<<grid, 256, 0, st>>>(
           static_cast<const float *>(h), row_ptr, col_src, col_type, m->table[0] + toff,
-          m->edge_dim, m->eps1[layer], n, static_cast<float *>(z));
+          m->edge_dim, m->eps1[layer], n, static_cast<float *>(z), nullptr);
     } else {
       aggregate_kernel<float><<<row_grid(n), 256, 0, st>>>(
           static_cast<const float *>(h), row_ptr, col_src, col_type, m->table[0] + toff,
@@ -820,6 +952,43 @@ extern "C" int gfx_aggregate(const gfx_model *m, int layer, const void *h, const
     }
   } else
     return fail(GFX_ERR_ARGUMENT, "gfx_aggregate: unknown dtype");
+  GFX_LAUNCH_CHECK();
+  return GFX_OK;
+}
+
+extern "C" int gfx_aggregate_banded(const gfx_model *m, int layer, const void *h, const uint32_t *desc,
+                                    const int32_t *needs_csr, const int32_t *row_ptr,
+                                    const int32_t *col_src, const uint8_t *col_type, int64_t n,
+                                    void *z, int dtype, void *stream) {
+  if (!m || layer < 0 || layer >= m->layers)
+    return fail(GFX_ERR_ARGUMENT, "gfx_aggregate_banded: bad model or layer");
+  if (dtype != GFX_F32)
+    return fail(GFX_ERR_UNSUPPORTED, "gfx_aggregate_banded: fp32 storage only (the fp16 model has "
+                                     "gfx_layer_fused_banded)");
+  if (m->edge_dim < 6 || n > (int64_t(1) << rowdesc::kPartnerBits))
+    return fail(GFX_ERR_UNSUPPORTED, "gfx_aggregate_banded: needs >= 6 edge types and <= 2^25 nodes");
+  if (n <= 0) return GFX_OK;
+  if (!desc || !needs_csr) return fail(GFX_ERR_ARGUMENT, "gfx_aggregate_banded: null descriptors or flag");
+  cudaStream_t st = as_stream(stream);
+  StageScope scope(GFX_STAGE_AGGREGATE, st, 2);
+  const size_t toff = size_t(layer) * m->edge_dim * kHidden;
+  {   // every row banded (*needs_csr == 0): the tile kernel; two blocks of eight warps per SM
+    static const cudaError_t attr = cudaFuncSetAttribute(
+        aggregate_f32_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBandSmemBytes);
+    GFX_CUDA(attr);
+    const int64_t tiles = (n + kBandTile - 1) / kBandTile;
+    const int grid = int(tiles > 2 * kNumSMs ? 2 * kNumSMs : tiles);
+    aggregate_f32_band_kernel<<<grid, 256, kBandSmemBytes, st>>>(
+        static_cast<const float *>(h), desc, needs_csr, m->table[0] + toff, m->eps1[layer], int(n),
+        static_cast<float *>(z));
+  }
+  {   // some row GENERIC (*needs_csr != 0): the CSR kernel (gfx_csr_build_if built the arrays)
+    int64_t b = (n + 15) / 16;
+    const int grid = int(b > 2 * kNumSMs ? 2 * kNumSMs : b);
+    aggregate_f32_h_kernel<<<grid, 256, 0, st>>>(
+        static_cast<const float *>(h), row_ptr, col_src, col_type, m->table[0] + toff, m->edge_dim,
+        m->eps1[layer], n, static_cast<float *>(z), needs_csr);
+  }
   GFX_LAUNCH_CHECK();
   return GFX_OK;
 }

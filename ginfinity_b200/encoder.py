@@ -363,18 +363,26 @@ class Ginfinity:
         csr_ws = self._scratch.get("csr_ws", csr_ws_bytes)
         enc_ws_bytes = lib.gfx_encode_workspace_bytes(n, act)
         enc_ws = self._scratch.get("enc_ws", enc_ws_bytes)
-        if mode == 3 and act == nat.GFX_F16 and out_row is None and self.describe_from_edges:
+        described = (banded and out_row is None and self.describe_from_edges and n <= 1 << 25
+                     and (mode == 3 if act == nat.GFX_F16 else self.impl == nat.IMPL_AUTO))
+        if described:
             desc = self._scratch.get("desc", 4 * n)
             dws_bytes = lib.gfx_edge_describe_workspace_bytes(n)
-            dws = self._scratch.get("desc_ws", dws_bytes)
+            dws = self._scratch.get("desc_ws", dws_bytes)     # its first word: the needs-CSR flag
             nat.check(lib.gfx_edge_describe(src, dst, typ, n, e, node_base, desc.data_ptr(),
                                             status.data_ptr(), dws.data_ptr(), dws_bytes, stream))
             nat.check(lib.gfx_csr_build_if(src, dst, typ, n, e, node_base, row_ptr.data_ptr(),
                                            col_src.data_ptr(), col_type.data_ptr(), dws.data_ptr(),
                                            csr_ws.data_ptr(), csr_ws_bytes, stream))
-            nat.check(lib.gfx_encode_described(self._handle, x, desc.data_ptr(), row_ptr.data_ptr(),
-                                               col_src.data_ptr(), col_type.data_ptr(), n, out,
-                                               out_code, enc_ws.data_ptr(), enc_ws_bytes, stream))
+            if act == nat.GFX_F16:
+                nat.check(lib.gfx_encode_described(
+                    self._handle, x, desc.data_ptr(), row_ptr.data_ptr(), col_src.data_ptr(),
+                    col_type.data_ptr(), n, out, out_code, enc_ws.data_ptr(), enc_ws_bytes, stream))
+            else:       # full_precision: K1 from the descriptors, K2 / K3 as split-fp16 GEMMs
+                nat.check(lib.gfx_encode_described_f32(
+                    self._handle, x, desc.data_ptr(), dws.data_ptr(), row_ptr.data_ptr(),
+                    col_src.data_ptr(), col_type.data_ptr(), n, out, out_code, enc_ws.data_ptr(),
+                    enc_ws_bytes, stream))
             return
         nat.check(lib.gfx_csr_build_checked(src, dst, typ, n, e, node_base, row_ptr.data_ptr(),
                                             col_src.data_ptr(), col_type.data_ptr(),

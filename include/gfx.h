@@ -267,6 +267,19 @@ int gfx_aggregate(const gfx_model *model, int layer, const void *h,
                   const uint8_t *col_type, int64_t num_nodes, void *z,
                   int dtype, void *stream);
 
+/* K1 for GFX_F32 storage from ROW DESCRIPTORS (gfx_edge_describe) instead of the
+ * CSR arrays: when `*needs_csr == 0` (device flag written by gfx_edge_describe:
+ * every row of the chunk is one of the reference builder's banded rows,
+ * graph.py:494-561) a register-window kernel walks runs of consecutive rows and
+ * loads each h row once; otherwise the CSR kernel of gfx_aggregate runs on the
+ * arrays gfx_csr_build_if built.  Exactly one of the two does the work, decided
+ * on the device; both give the bits of gfx_aggregate.  (_model.py:41-46) */
+int gfx_aggregate_banded(const gfx_model *model, int layer, const void *h,
+                         const uint32_t *desc, const int32_t *needs_csr,
+                         const int32_t *row_ptr, const int32_t *col_src,
+                         const uint8_t *col_type, int64_t num_nodes, void *z,
+                         int dtype, void *stream);
+
 /* K2: h_out = h + LayerNorm_l(W2 relu(W1' z + b1') + b2)
  *                                (_model.py:34-36, 68-71) */
 int gfx_mlp_ln_residual(const gfx_model *model, int layer, const void *z,
@@ -330,6 +343,16 @@ int gfx_encode_described(const gfx_model *model, const float *x,
                          const int32_t *col_src, const uint8_t *col_type,
                          int64_t num_nodes, void *out, int out_dtype,
                          void *workspace, size_t workspace_bytes, void *stream);
+
+/* The same for the fp32 model (full_precision, api.py:110-112): K1 per layer by
+ * gfx_aggregate_banded (`needs_csr`: the flag gfx_edge_describe wrote; the CSR
+ * arrays are read only when it is set), K2 / K3 as in gfx_encode(GFX_F32). */
+int gfx_encode_described_f32(const gfx_model *model, const float *x,
+                             const uint32_t *desc, const int32_t *needs_csr,
+                             const int32_t *row_ptr, const int32_t *col_src,
+                             const uint8_t *col_type, int64_t num_nodes,
+                             void *out, int out_dtype, void *workspace,
+                             size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------
  * K5  similarity search (no reference counterpart; north-star item 4).

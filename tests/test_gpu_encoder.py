@@ -249,6 +249,41 @@ def test_layer_kernel_is_fixed_and_all_forms_agree(gb, syn16, synthetic_state, m
     assert full.fused == 0                                 # fp32 model: K1 + K2 (SIMT) only
 
 
+def test_full_precision_from_row_descriptors_equals_the_csr_path(gb, synthetic_state):
+    """full_precision=True: K1 from row descriptors (gfx_encode_described_f32, the default for
+    full-molecule shards) gives the bits of K1 on the CSR arrays (GFX_DESCRIBE=csr), over several
+    chunks and microbatches, host path and device-resident path; a shard whose edge order is not
+    the reference builder's takes the CSR kernel through the device flag and still agrees."""
+    from ginfinity_b200.encoder import DeviceShard
+    enc = gb.Ginfinity.from_state(synthetic_state, device="cuda:0", full_precision=True)
+    shard = gb.GraphBuilder().build_shard(random_records(37, 120))
+    limits = dict(max_batch_nodes=3000, max_batch_edges=15_000, embedding_dtype=np.float32)
+    keep = enc.chunk_nodes, enc.resident_chunk_nodes
+    enc.chunk_nodes = enc.resident_chunk_nodes = 7000
+    try:
+        assert enc.describe_from_edges
+        a = np.concatenate(enc.encode_graphs(shard, **limits))
+        ds = DeviceShard.from_shard(shard, "cuda:0")
+        c = enc.encode_device_shard(ds, max_batch_nodes=3000, max_batch_edges=15_000,
+                                    out_dtype=1).cpu().numpy()
+        # the same edges, the first record's edge list reversed: rows of that record are GENERIC
+        e1 = int(shard.edge_ptr[1])
+        ei, et = shard.edge_index.copy(), shard.edge_types.copy()
+        ei[:, :e1] = ei[:, :e1][:, ::-1]
+        et[:e1] = et[:e1][::-1]
+        other = _clone_shard(gb, shard, edge_index=ei, edge_types=et)
+        d = np.concatenate(enc.encode_graphs(other, **limits))
+        enc.describe_from_edges = False
+        b = np.concatenate(enc.encode_graphs(shard, **limits))
+        e = np.concatenate(enc.encode_graphs(other, **limits))
+    finally:
+        enc.chunk_nodes, enc.resident_chunk_nodes = keep
+    assert np.array_equal(a, b) and np.array_equal(a, c)
+    assert np.array_equal(d, e)
+    n1 = int(shard.node_ptr[1])
+    assert np.array_equal(d[n1:], a[n1:]) and np.abs(d[:n1] - a[:n1]).max() < 1e-5
+
+
 def test_simt_and_tcgen05_paths_agree(gb, syn16):
     from ginfinity_b200 import _native as nat
     shard = gb.GraphBuilder().build_shard(random_records(32, 60))

@@ -631,6 +631,66 @@ def test_row_descriptors_from_the_edge_list(nat, dev, problem):
     assert status2 == 16 and flag2 == 0
 
 
+def test_banded_fp32_aggregate_equals_the_csr_kernel(nat, dev, problem):
+    """gfx_aggregate_banded (fp32 storage: K1 from row descriptors, a register window over runs
+    of consecutive rows) against gfx_aggregate on the CSR of the same edges, bit for bit: full
+    molecules of ragged lengths (runs that start and end inside molecules, a last run shorter
+    than 32 rows, partners in other runs), every layer's table; the same shard with one row's
+    edges reordered (GENERIC: the device flag sends the chunk to the CSR kernel); tiny chunks;
+    gfx_encode_described_f32 == gfx_encode(GFX_F32)."""
+    import ginfinity_b200 as g
+
+    def both(edge_index, edge_types, n, h, layer, expect_flag):
+        rp, cs, ct = device_csr(nat, dev, edge_index, edge_types, n)
+        want = torch.full((n, 128), 7.0, dtype=torch.float32, device=dev)
+        nat.check(nat.lib.gfx_aggregate(problem["handle"], layer, h.data_ptr(), rp.data_ptr(),
+                                        cs.data_ptr(), ct.data_ptr(), n, want.data_ptr(), 1, _stream()))
+        desc, flag, status, ws, (ei, et) = _edge_describe(nat, dev, edge_index, edge_types, n)
+        assert flag == expect_flag and status == 0
+        got = torch.full((n + 1, 128), -7.0, dtype=torch.float32, device=dev)   # one guard row
+        nat.check(nat.lib.gfx_aggregate_banded(problem["handle"], layer, h.data_ptr(), desc.data_ptr(),
+                                               ws.data_ptr(), rp.data_ptr(), cs.data_ptr(),
+                                               ct.data_ptr(), n, got.data_ptr(), 1, _stream()))
+        torch.cuda.synchronize()
+        assert torch.equal(got[:n].view(torch.int32), want.view(torch.int32))
+        assert bool((got[n] == -7.0).all())
+        return desc, ws, (rp, cs, ct)
+
+    full = g.GraphBuilder().build_shard(random_records(91, 90))
+    n = full.node_count
+    gen = torch.Generator(device="cpu").manual_seed(5)
+    h = (torch.randn(n, 128, generator=gen) * 2).to(dev)
+    for layer in range(4):
+        desc, ws, csr = both(full.edge_index, full.edge_types, n, h, layer, 0)
+    # the whole forward from descriptors == the forward on the CSR
+    x = _up(full.node_features, dev)
+    need = nat.lib.gfx_encode_workspace_bytes(n, 1)
+    ews = torch.empty(need, dtype=torch.uint8, device=dev)
+    a = torch.empty((n, 128), dtype=torch.float32, device=dev)
+    b = torch.empty((n, 128), dtype=torch.float32, device=dev)
+    nat.check(nat.lib.gfx_encode(problem["handle"], x.data_ptr(), csr[0].data_ptr(), csr[1].data_ptr(),
+                                 csr[2].data_ptr(), None, n, a.data_ptr(), 1, 1, 0, 0, ews.data_ptr(),
+                                 need, _stream()))
+    nat.check(nat.lib.gfx_encode_described_f32(problem["handle"], x.data_ptr(), desc.data_ptr(),
+                                               ws.data_ptr(), None, None, None, n, b.data_ptr(), 1,
+                                               ews.data_ptr(), need, _stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(a.view(torch.int32), b.view(torch.int32))
+
+    # one row's backbone edges swapped in the edge list: GENERIC, the CSR kernel does the chunk
+    ei, et = full.edge_index.copy(), full.edge_types.copy()
+    into = np.flatnonzero(ei[1] == 40)
+    first, second = into[0], into[1]
+    ei[:, [first, second]] = ei[:, [second, first]]
+    et[[first, second]] = et[[second, first]]
+    both(ei, et, n, h, 1, 1)
+
+    for tiny in (1, 2, 3, 5, 31, 32, 33):                   # chunks shorter than the window / a run
+        one = g.GraphBuilder().build_shard([g.RNA("t", ("ACGU" * 9)[:tiny], "." * tiny)])
+        hh = (torch.randn(tiny, 128, generator=gen) * 2).to(dev)
+        both(one.edge_index, one.edge_types, tiny, hh, 2, 0)
+
+
 @pytest.mark.parametrize("n", [1, 127, 128, 129, 200, 64 * 3 + 1])
 def test_tile_edges(nat, dev, problem, n):
     """Ragged sizes around the 128-row tile / 64-row block boundaries: all
