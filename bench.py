@@ -640,6 +640,7 @@ def main() -> None:
     ap.add_argument("--c3-records", type=int, default=600)
     ap.add_argument("--c4-files", type=int, default=10)
     args = ap.parse_args()
+    t_start = time.perf_counter()
     protect_stdout()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -830,17 +831,32 @@ def main() -> None:
             go = lambda: enc32.encode_device_shard(  # noqa: E731
                 dshard, max_batch_nodes=MAX_BATCH_NODES, max_batch_edges=MAX_BATCH_EDGES,
                 out_dtype=nat.GFX_F32, out=o32)
-            go()
+            for _ in range(2):
+                go()
             torch.cuda.synchronize()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            go()
+            for _ in range(3):
+                go()
             b.record()
             torch.cuda.synchronize()
-            ms = a.elapsed_time(b)
+            ms = a.elapsed_time(b) / 3
+            nat.profile_enable(*nat.STAGES)
+            go()
+            torch.cuda.synchronize()
+            stages = {name: round(nat.profile_read(name)[0], 3) for name in nat.STAGES}
+            nat.profile_enable()
+            nat.launch_counts(reset=True)
+            k1_gbs = nodes * enc32._weights.cfg.layers * 1028 / (stages["aggregate"] * 1e-3) / 1e9
             return {"value": nodes / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "n_gpus": 1,
+                    "stage_ms": {k: v for k, v in stages.items() if v > 0},
+                    "k1_roofline": {"kernel": "aggregate_f32_band_kernel (K1 for fp32 storage from row "
+                                              "descriptors: 64-row tiles by bulk copy, register window)",
+                                    "bound": "hbm", "achieved": k1_gbs, "peak": peaks["hbm_gbs"],
+                                    "unit": "GB/s", "frac": k1_gbs / peaks["hbm_gbs"],
+                                    "algorithmic_bytes_per_node_layer": 1028},
                     "what": "full_precision=True (fp32 storage end to end, reference api.py:110-112) "
-                            "on this rank's shard, device-resident, one timed pass"}
+                            "on this rank's shard, device-resident, mean of three timed passes"}
         extras["value_fp32"] = guarded(fp32_pass)
         del dshard, out
         torch.cuda.empty_cache()
@@ -949,7 +965,8 @@ def main() -> None:
                              "how": "fixed (banded fused layer; the bit-identical pair kernel for "
                                     "shards with context nodes); GFX_FUSED=auto times the forms, "
                                     "GFX_FUSED=0|2|3 pins one"},
-            "setup": {"workload_generation_s": gen_s, "host_cpus": os.cpu_count(), "numa_binding": numa},
+            "setup": {"workload_generation_s": gen_s, "host_cpus": os.cpu_count(), "numa_binding": numa,
+                      "whole_run_wall_s": round(time.perf_counter() - t_start, 1)},
             **extras,
         }
         if cpu is not None:

@@ -110,6 +110,27 @@ __device__ __forceinline__ void split2(float2 x, uint32_t &hi, uint32_t &lo) {
   lo = pack2(x.x - back.x, x.y - back.y);
 }
 
+// 256-bit global accesses (LDG.E.ENL2.256 / STG.E.ENL2.256 on sm_100).  Epilogue B holds one ROW
+// per thread (the TMEM lane), so a warp's access touches 32 different 128-byte lines whatever its
+// width: with 16 bytes per thread the residual reads and the output stores of a tile were 8,192
+// L1 wavefronts (ncu: the LSU data pipe 79 % busy, the tensor pipe waiting behind it); 32 bytes
+// per thread -- a whole sector -- halves the requests and the wavefronts.  32-byte aligned.
+__device__ __forceinline__ void ldg256(const float *p, float *v) {
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(float *p, const float *v) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]),
+               "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void stg256(void *p, const uint32_t *v) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]),
+               "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+
 template <int N1, bool HEAD>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWarps * 32, 1)
 split_kernel(const __grid_constant__ Consts c, const Args p) {
@@ -217,18 +238,18 @@ split_kernel(const __grid_constant__ Consts c, const Args p) {
         const float rstd = rsqrtf(var + 1e-5f);
         const float nm = -mean * rstd;
         if (row < n) {
-          const float4 *res = reinterpret_cast<const float4 *>(p.res + row * kHidden + half * 64);
-          float4 *out = reinterpret_cast<float4 *>(static_cast<float *>(p.out) + row * kHidden + half * 64);
+          const float *res = p.res + row * kHidden + half * 64;
+          float *out = static_cast<float *>(p.out) + row * kHidden + half * 64;
 #pragma unroll
-          for (int k = 0; k < 16; ++k) {
-            const float4 rr = __ldg(res + k);
-            const int col = half * 64 + 4 * k;
-            float4 o;
-            o.x = fmaf(fmaf(t[4 * k], rstd, nm), c.g[col], c.be[col]) + rr.x;
-            o.y = fmaf(fmaf(t[4 * k + 1], rstd, nm), c.g[col + 1], c.be[col + 1]) + rr.y;
-            o.z = fmaf(fmaf(t[4 * k + 2], rstd, nm), c.g[col + 2], c.be[col + 2]) + rr.z;
-            o.w = fmaf(fmaf(t[4 * k + 3], rstd, nm), c.g[col + 3], c.be[col + 3]) + rr.w;
-            out[k] = o;
+          for (int k = 0; k < 8; ++k) {
+            float rr[8], o[8];
+            ldg256(res + 8 * k, rr);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int col = half * 64 + 8 * k + e;
+              o[e] = fmaf(fmaf(t[8 * k + e], rstd, nm), c.g[col], c.be[col]) + rr[e];
+            }
+            stg256(out + 8 * k, o);
           }
         }
       } else {
@@ -238,18 +259,23 @@ split_kernel(const __grid_constant__ Consts c, const Args p) {
         if (dst >= 0 && p.out_row != nullptr) dst = p.out_row[row];
         if (dst >= 0) {
           if (p.out_half) {
-            uint4 *out = reinterpret_cast<uint4 *>(static_cast<__half *>(p.out) + dst * kHidden + half * 64);
+            __half *out = static_cast<__half *>(p.out) + dst * kHidden + half * 64;
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-              out[k] = make_uint4(pack2(t[8 * k] * inv, t[8 * k + 1] * inv),
-                                  pack2(t[8 * k + 2] * inv, t[8 * k + 3] * inv),
-                                  pack2(t[8 * k + 4] * inv, t[8 * k + 5] * inv),
-                                  pack2(t[8 * k + 6] * inv, t[8 * k + 7] * inv));
+            for (int k = 0; k < 4; ++k) {
+              uint32_t o[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) o[e] = pack2(t[16 * k + 2 * e] * inv, t[16 * k + 2 * e + 1] * inv);
+              stg256(out + 16 * k, o);
+            }
           } else {
-            float4 *out = reinterpret_cast<float4 *>(static_cast<float *>(p.out) + dst * kHidden + half * 64);
+            float *out = static_cast<float *>(p.out) + dst * kHidden + half * 64;
 #pragma unroll
-            for (int k = 0; k < 16; ++k)
-              out[k] = make_float4(t[4 * k] * inv, t[4 * k + 1] * inv, t[4 * k + 2] * inv, t[4 * k + 3] * inv);
+            for (int k = 0; k < 8; ++k) {
+              float o[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) o[e] = t[8 * k + e] * inv;
+              stg256(out + 8 * k, o);
+            }
           }
         }
       }
@@ -423,8 +449,8 @@ static int launch(const Consts &c, const Args &a, cudaStream_t st) {
 int split9_mlp_ln_residual(const gfx_model *m, int layer, const float *z, const float *h, int64_t n,
                            float *h_out, cudaStream_t st) {
   if ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(h) |
-       reinterpret_cast<uintptr_t>(h_out)) & 15)
-    return fail(GFX_ERR_ARGUMENT, "split tcgen05 MLP: activation buffers must be 16-byte aligned");
+       reinterpret_cast<uintptr_t>(h_out)) & 31)
+    return fail(GFX_ERR_ARGUMENT, "split tcgen05 MLP: activation buffers must be 32-byte aligned");
   v9::Consts c{};
   const gfx_host_vectors &hv = m->host;
   for (int i = 0; i < kMlpHidden; ++i) c.b1[i] = hv.b1[size_t(layer) * kMlpHidden + i];
@@ -444,8 +470,8 @@ int split9_mlp_ln_residual(const gfx_model *m, int layer, const float *z, const 
 // K3 for fp32 storage: y = Wb relu(Wa h + ba) + bb; out[out_row[i]] = y_i / max(|y_i|, 1e-12)
 int split9_head_l2norm(const gfx_model *m, const float *h, const int32_t *out_row, int64_t n, void *out,
                        int out_dtype, cudaStream_t st) {
-  if ((reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(out)) & 15)
-    return fail(GFX_ERR_ARGUMENT, "split tcgen05 head: buffers must be 16-byte aligned");
+  if ((reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(out)) & 31)
+    return fail(GFX_ERR_ARGUMENT, "split tcgen05 head: buffers must be 32-byte aligned");
   v9::Consts c{};
   const gfx_host_vectors &hv = m->host;
   for (int i = 0; i < kHidden; ++i) {
