@@ -16,6 +16,10 @@ timeout 300 $NCU_CMD > gpurun_out/ncu_plain.log 2>&1 && \
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $NCU_CMD > gpurun_out/ncu_launches.log 2>&1
 timeout 300 $NCU_CMD > gpurun_out/ncu_plain2.log 2>&1 && \
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"fused_banded8|head8|input_umma|edge_classify|edge_describe" -s 4 -c 8 -o gpurun_out/prof_top $NCU_CMD > gpurun_out/ncu_full.log 2>&1
+# full_precision path: K1 from row descriptors and the split-fp16 K2 / K3 (first pass of the probe skipped)
+FP32_CMD="python tools/stage_probe.py 20000 fp32"
+timeout 300 $FP32_CMD > gpurun_out/fp32_plain.log 2>&1 && \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"aggregate_f32_band|split_kernel" -s 18 -c 9 -o gpurun_out/prof_fp32 $FP32_CMD > gpurun_out/ncu_fp32.log 2>&1
 if [ "$1" != "ncu" ]; then
 SEARCH_CMD="python tools/search_bench.py 3"
 timeout 300 $SEARCH_CMD > gpurun_out/search.log 2>&1 && \

@@ -15,7 +15,12 @@ KEEP = ("gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "lts__throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum",
         "sm__cycles_active.avg", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
-        "smsp__warp_issue_stalled", "sm__inst_executed.avg.per_cycle_active")
+        "smsp__warp_issue_stalled", "sm__inst_executed.avg.per_cycle_active",
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_lsu_wavefronts_mem_lgds.avg",
+        "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_st.sum",
+        "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio")
 
 
 def launches(path):
