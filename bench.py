@@ -696,6 +696,11 @@ def main() -> None:
     ev1.record()
     barrier()
     clocks = sampler.finish()
+    # rows of the TIMED device-resident passes, kept to be compared bit for bit with what the
+    # end-to-end call (other chunk sizes, host path) returns for the same records
+    sample_ids = sorted(set(range(min(200, shard.record_count))) | set(range(0, shard.record_count, 997)))
+    nptr = shard.node_ptr
+    resident_sample = {i: out[int(nptr[i]):int(nptr[i + 1])].cpu().numpy() for i in sample_ids}
     elapsed_ms = torch.tensor([ev0.elapsed_time(ev1)], device=device, dtype=torch.float64)
     total_nodes = torch.tensor([float(nodes)], device=device, dtype=torch.float64)
     launches = nat.launch_counts(reset=True)
@@ -747,6 +752,9 @@ def main() -> None:
     assert len(result) == shard.record_count and result[0].dtype == np.float16
     check_records = min(200, shard.record_count)
     kept_for_parity = [np.array(a) for a in result[:check_records]]
+    resident_equal = all(np.array_equal(result[i], rows) for i, rows in resident_sample.items())
+    resident_checked = (len(resident_sample), int(sum(r.shape[0] for r in resident_sample.values())))
+    del resident_sample
     del result
     barrier()
     t0 = time.perf_counter()
@@ -935,6 +943,12 @@ def main() -> None:
             cpu = guarded(cpu_reference_rate, state, shard, args.sample_records)
         cpu_outputs = cpu["outputs"] if cpu and "outputs" in cpu and cpu["kind"] == "reference" else None
         parity = guarded(parity_check, kept_for_parity, shard, cpu_outputs, check_records, state)
+        if isinstance(parity, dict):
+            parity["timed_resident_pass_equals_e2e_bit_for_bit"] = {
+                "ok": bool(resident_equal), "records": resident_checked[0],
+                "nucleotides": resident_checked[1],
+                "what": "rows written by the timed device-resident passes (`value`) against the "
+                        "end-to-end call's host arrays (`e2e`) for the same records"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
