@@ -277,21 +277,31 @@ umma2_kernel(const Args p) {
             op[g] = pack8(o);
           }
         } else if (sizeof(TOut) == 2) {
-          uint4 *op = reinterpret_cast<uint4 *>(static_cast<__half *>(p.out) + orow * kHidden + cb * 32);
+          // a thread holds one row: 256-bit stores (a whole sector per thread) halve the L1
+          // wavefronts of these 32-lines-per-warp accesses (gfx_split9.cu)
+          __half *op = static_cast<__half *>(p.out) + orow * kHidden + cb * 32;
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            float o[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] = (v[g * 16 + j] + b2s[cb * 32 + g * 16 + j]) * mul;
+            const uint4 lo = pack8(o), hi = pack8(o + 8);
+            asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(op + g * 16),
+                         "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z),
+                         "r"(hi.w)
+                         : "memory");
+          }
+        } else {
+          float *op = static_cast<float *>(p.out) + orow * kHidden + cb * 32;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             float o[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) o[j] = (v[g * 8 + j] + b2s[cb * 32 + g * 8 + j]) * mul;
-            op[g] = pack8(o);
-          }
-        } else {
-          float4 *op = reinterpret_cast<float4 *>(static_cast<float *>(p.out) + orow * kHidden + cb * 32);
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const int c = cb * 32 + g * 4;
-            op[g] = make_float4((v[g * 4] + b2s[c]) * mul, (v[g * 4 + 1] + b2s[c + 1]) * mul,
-                                (v[g * 4 + 2] + b2s[c + 2]) * mul, (v[g * 4 + 3] + b2s[c + 3]) * mul);
+            asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(op + g * 8),
+                         "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]), "f"(o[4]), "f"(o[5]), "f"(o[6]),
+                         "f"(o[7])
+                         : "memory");
           }
         }
       }
@@ -352,6 +362,8 @@ int umma_mlp_ln_residual(const gfx_model *m, int layer, const __half *z, const _
 
 int umma_head_l2norm(const gfx_model *m, const __half *h, const int32_t *out_row, int64_t n,
                      void *out, int out_dtype, cudaStream_t st) {
+  if (reinterpret_cast<uintptr_t>(out) & 31)
+    return fail(GFX_ERR_ARGUMENT, "tcgen05 head: the output table must be 32-byte aligned");
   v2::Args a{};
   a.a_in = h; a.w1_img = m->wa_img; a.w2_img = m->wb_img; a.b1 = m->ba; a.b2 = m->bb;
   a.out_row = out_row; a.n = n; a.out = out;
