@@ -973,9 +973,9 @@ extern "C" int gfx_aggregate_banded(const gfx_model *m, int layer, const void *h
   StageScope scope(GFX_STAGE_AGGREGATE, st, 2);
   const size_t toff = size_t(layer) * m->edge_dim * kHidden;
   {   // every row banded (*needs_csr == 0): the tile kernel; two blocks of eight warps per SM
-    static const cudaError_t attr = cudaFuncSetAttribute(
-        aggregate_f32_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBandSmemBytes);
-    GFX_CUDA(attr);
+    // per launch, not once per process: the attribute belongs to the current device
+    GFX_CUDA(cudaFuncSetAttribute(aggregate_f32_band_kernel,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kBandSmemBytes));
     const int64_t tiles = (n + kBandTile - 1) / kBandTile;
     const int grid = int(tiles > 2 * kNumSMs ? 2 * kNumSMs : tiles);
     aggregate_f32_band_kernel<<<grid, 256, kBandSmemBytes, st>>>(
