@@ -176,3 +176,29 @@ def test_bench_keeps_stdout_to_one_json_line():
     assert json.loads(run.stdout) == {"metric": "m", "value": 1.5}
     assert run.stdout.count("\n") == 1
     assert "NCCL version" in run.stderr and "stray" in run.stderr
+
+
+def test_chunks_cover_every_microbatch_and_ramp_up():
+    """Host logic of the streaming encode: consecutive microbatches are grouped into device
+    chunks of at most `limit` nodes (always at least one microbatch); with `ramp` the first
+    chunks hold 1/8, 1/4, 1/2 of the limit so the device->host copies start early."""
+    from ginfinity_b200.encoder import Ginfinity
+    rng = np.random.default_rng(0)
+    sizes = rng.integers(40_000, 60_000, 335)
+    node_at = np.concatenate([[0], np.cumsum(sizes)])
+    plan = np.stack([np.arange(336), node_at, node_at * 5])
+    limit = 960_000
+    for ramp in (False, True):
+        chunks = Ginfinity._chunks(None, plan, limit, ramp=ramp)
+        assert chunks[0][0] == 0 and chunks[-1][1] == 335
+        assert all(a[1] == b[0] for a, b in zip(chunks[:-1], chunks[1:]))
+        nodes = [int(node_at[b] - node_at[a]) for a, b in chunks]
+        assert all(b > a for a, b in chunks) and max(nodes) <= limit
+        if ramp:
+            assert nodes[0] <= limit // 8 and nodes[1] <= limit // 4 and nodes[2] <= limit // 2
+            assert min(nodes[3:-1]) > limit - 60_000
+        else:
+            assert min(nodes[:-1]) > limit - 60_000
+    # a microbatch larger than the (ramped) cap still gets its own chunk
+    one = Ginfinity._chunks(None, plan, 10_000, ramp=True)
+    assert one == [(i, i + 1) for i in range(335)]
