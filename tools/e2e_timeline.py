@@ -2,9 +2,10 @@
 """Developer tool: where one end-to-end `encode_graphs` call (page-locked shard in, host
 table out) spends its time against the raw copies it is bounded by.
 
-  1. wall clock of the call, split by host-side phase (front, enqueue, views, wait);
+  1. wall clock of the call (three runs);
   2. the same call under torch.profiler: busy time and idle gaps of the device->host copy
-     engine (the bottleneck: 256 B/nt out against 69 B/nt in), first copy start, last copy end;
+     engine (the bottleneck: 256 B/nt out against 69 B/nt in), first copy start, last copy end,
+     the device events before the first large copy, and per copy what ran beside it;
   3. raw device->host copies of the same bytes with no kernels, into (a) ONE reused 256 MiB
      page-locked buffer (what bench.py's copy ceiling does) and (b) the caller's whole
      [nodes, 128] table in the pipeline's piece size, alone and with the host->device
@@ -17,7 +18,6 @@ import time
 from collections import defaultdict
 from pathlib import Path
 
-import numpy as np
 import torch
 from torch.profiler import ProfilerActivity, profile
 
