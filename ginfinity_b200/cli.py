@@ -62,8 +62,11 @@ def _context(args) -> tuple[bool, int]:
 
 
 def _write_archive(path: Path, names, arrays) -> None:
-    path.parent.mkdir(parents=True, exist_ok=True)
-    np.savez_compressed(path, **dict(zip(names, arrays)))
+    """The reference's output format (numpy.savez_compressed, cli.py:86,159), its members
+    deflated on every host core (ginfinity_b200/npz.py): same member bytes, a fraction of the
+    time -- the archive, not the encode, was the wall time of `embed`."""
+    from .npz import write_npz_compressed
+    write_npz_compressed(path, names, arrays)
 
 
 def _write_manifest(path: Path, encoder, body: dict, started: float) -> None:

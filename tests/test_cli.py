@@ -193,3 +193,55 @@ def test_embed_writes_one_array_per_window_and_no_slices_ignores_them(tmp_path):
     assert main(["embed", "--input", str(single), "--output", str(whole), "--no-slices"]) == 0
     with np.load(whole) as archive:
         assert archive.files == ["stem"] and archive["stem"].shape == (16, 128)
+
+
+def test_parallel_npz_writer_is_numpy_compatible(tmp_path):
+    """ginfinity_b200/npz.py writes what numpy.savez_compressed writes (the reference's output
+    format, cli.py:86,159), members deflated concurrently: same names in the same order, same
+    arrays and dtypes, the same compressed member streams; ".npz" appended when missing; empty
+    and 0-row arrays, a non-ASCII name, float16 / float32 / float64; duplicates refused."""
+    import struct
+    import zipfile
+
+    from ginfinity_b200.npz import write_npz_compressed
+    rng = np.random.default_rng(3)
+    arrays = [rng.normal(size=(int(n), 128)).astype(dt)
+              for n, dt in zip((0, 1, 57, 300, 4096), (np.float16, np.float32, np.float16, np.float64, np.float16))]
+    arrays.append(np.zeros((0,), np.float16))
+    names = ["r0", "r1", "RNA two", "r3", "largest", "señal"]
+    ours = write_npz_compressed(tmp_path / "ours", names, arrays, workers=3)
+    assert ours == tmp_path / "ours.npz"
+    np.savez_compressed(tmp_path / "numpy.npz", **dict(zip(names, arrays)))
+    with np.load(ours) as a, np.load(tmp_path / "numpy.npz") as b:
+        assert a.files == b.files == names
+        for key in names:
+            assert a[key].dtype == b[key].dtype and a[key].shape == b[key].shape
+            assert np.array_equal(a[key], b[key])
+
+    def stream(z, info):
+        z.fp.seek(info.header_offset + 26)
+        n, e = struct.unpack("<HH", z.fp.read(4))
+        z.fp.seek(info.header_offset + 30 + n + e)
+        return z.fp.read(info.compress_size)
+
+    with zipfile.ZipFile(ours) as za, zipfile.ZipFile(tmp_path / "numpy.npz") as zb:
+        assert za.testzip() is None
+        for x, y in zip(za.infolist(), zb.infolist()):
+            assert (x.filename, x.CRC, x.file_size, x.compress_size) == (y.filename, y.CRC, y.file_size, y.compress_size)
+            assert stream(za, x) == stream(zb, y)
+    with pytest.raises(ValueError, match="duplicate"):
+        write_npz_compressed(tmp_path / "dup.npz", ["a", "a"], arrays[:2])
+
+
+def test_parallel_npz_writer_beyond_65535_members(tmp_path):
+    """More members than a classic ZIP end record can count (a 100k-record shard through
+    `embed-graphs`): the ZIP64 end-of-central-directory record is written and numpy reads every
+    member back."""
+    from ginfinity_b200.npz import write_npz_compressed
+    count = 66_000
+    arrays = [np.full((1, 4), i, np.float16) for i in range(count)]
+    path = write_npz_compressed(tmp_path / "many.npz", (f"m{i}" for i in range(count)), arrays)
+    with np.load(path) as z:
+        assert len(z.files) == count and z.files[0] == "m0" and z.files[-1] == f"m{count - 1}"
+        for i in (0, 1, 65_534, 65_535, 65_536, count - 1):
+            assert np.array_equal(z[f"m{i}"], arrays[i])
