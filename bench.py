@@ -476,9 +476,9 @@ def c1_embed(device):
             "embed_cli_wall_s": wall, "embed_cli_nt_per_s": nt / wall,
             "manifest_elapsed_s": manifest.get("elapsed_seconds"),
             "table_read_s": read_s, "encode_many_s": enc_s, "encode_many_nt_per_s": nt / enc_s,
-            "note": "the CLI's wall time is the compressed NPZ archive (np.savez_compressed, the "
-                    "reference's format) + table parsing + model load; encode_many is strings in, "
-                    "host arrays out"}
+            "note": "the CLI's wall time is the compressed NPZ archive (the reference's format; "
+                    "members deflated on every host core, ginfinity_b200/npz.py) + table parsing + "
+                    "model load + process start; encode_many is strings in, host arrays out"}
 
 
 def windows_bench(encoder, count: int = 20_000):
